@@ -1,0 +1,133 @@
+"""ctypes binding of ``libbaybe_b200.so`` (the C ABI declared in ``include/baybe_b200.h``).
+
+There is no CPU fallback: if the library is missing or cannot be loaded, every call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "_C" / "libbaybe_b200.so"
+ABI_VERSION = 1
+
+# enums (mirror include/baybe_b200.h)
+KERNEL_FAMILY = {"matern12": 0, "matern32": 1, "matern52": 2, "rbf": 3}
+LAYOUT = {"row_f32": 0, "col_f32": 1, "row_f64": 2, "col_f64": 3}
+ACQ_KIND = {
+    "qLogEI": 0, "qEI": 1, "qUCB": 2, "qSR": 3, "qPI": 4,
+    "UCB": 5, "EI": 6, "LogEI": 7, "PI": 8, "PM": 9, "PSTD": 10,
+}
+MC_KINDS = ("qLogEI", "qEI", "qUCB", "qSR", "qPI")
+MAX_PENDING = 31
+MAX_TRAIN = 512
+
+BB_ERR_INVALID, BB_ERR_UNSUPPORTED, BB_ERR_CUDA, BB_ERR_NOT_PD, BB_ERR_WORKSPACE = -1, -2, -3, -4, -5
+
+_dp = C.POINTER(C.c_double)
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("d", C.c_int32), ("family", C.c_int32), ("task_col", C.c_int32),
+        ("n_tasks", C.c_int32), ("has_outputscale", C.c_int32), ("outputscale", C.c_double),
+        ("train_x", _dp), ("train_y", _dp), ("lower", _dp), ("upper", _dp), ("lengthscale", _dp),
+        ("noise", _dp), ("mean_const", _dp), ("task_covar", _dp),
+    ]
+
+
+class Model(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("n", C.c_int32), ("n_pad", C.c_int32), ("d", C.c_int32), ("d_pad", C.c_int32),
+        ("family", C.c_int32), ("task_col", C.c_int32), ("n_tasks", C.c_int32),
+        ("n_chunks", C.c_int32), ("jitter_tries", C.c_int32),
+        ("y_mean", C.c_float), ("y_std", C.c_float), ("prior_scale", C.c_float),
+        ("r_scale", C.c_float), ("jitter", C.c_double),
+        ("d_blob", C.c_void_p), ("blob_bytes", C.c_size_t),
+        ("d_cand_scale", C.c_void_p), ("d_cand_shift", C.c_void_p), ("d_train_m2", C.c_void_p),
+        ("d_train_sq", C.c_void_p), ("d_alpha", C.c_void_p), ("d_train_task", C.c_void_p),
+        ("d_task_covar", C.c_void_p), ("d_mean_const", C.c_void_p), ("d_rimg", C.c_void_p),
+        ("d_linv", C.c_void_p), ("d_alpha64", C.c_void_p), ("d_xn64", C.c_void_p),
+        ("d_linv32", C.c_void_p),
+    ]
+
+
+class AcqSpec(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("maximize", C.c_int32), ("best_f", C.c_float), ("beta", C.c_float),
+        ("obj_scale", C.c_float), ("obj_shift", C.c_float), ("tau_relu", C.c_float),
+        ("tau_max", C.c_float), ("tau_pi", C.c_float),
+    ]
+
+
+class Best(C.Structure):
+    _fields_ = [("val", C.c_float), ("pad_", C.c_int32), ("idx", C.c_int64)]
+
+
+class NativeLibraryError(RuntimeError):
+    """The CUDA extension is missing or failed to load (there is no CPU fallback)."""
+
+
+_lib = None
+
+_vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+_SIGNATURES = {
+    "bb_abi_version": (C.c_int, []),
+    "bb_last_error": (C.c_char_p, []),
+    "bb_model_blob_bytes": (_sz, [_i32, _i32, _i32]),
+    "bb_model_build": (C.c_int, [C.POINTER(ModelDesc), _vp, _sz, C.POINTER(Model), _vp]),
+    "bb_kernel_matrix": (C.c_int, [C.POINTER(Model), _vp, _i32, _i64, _i64, _vp, _i64, _vp]),
+    "bb_posterior": (C.c_int, [C.POINTER(Model), _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "bb_pending_stats": (C.c_int, [C.POINTER(Model), _vp, _i32, _vp, _vp, _vp, _vp]),
+    "bb_acq_score": (C.c_int, [C.POINTER(AcqSpec), _vp, _vp, _i64, _vp, _i32, _vp, _vp]),
+    "bb_acq_score_joint": (C.c_int, [C.POINTER(AcqSpec), _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
+    "bb_score_fused": (C.c_int, [C.POINTER(Model), C.POINTER(AcqSpec), _vp, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "bb_best_init": (C.c_int, [_vp, _vp]),
+    "bb_argmax": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "bb_best_decode": (C.c_int, [_vp, _vp, _vp]),
+    "bb_topk": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "bb_debug_posterior_simt": (C.c_int, [C.POINTER(Model), _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and type its entry points."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m baybe_b200.build` "
+            "(baybe_b200 has no CPU fallback)"
+        )
+    try:
+        lib = C.CDLL(str(LIB_PATH))
+    except OSError as e:  # pragma: no cover - depends on the environment
+        raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.bb_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(
+            f"ABI mismatch: library reports {lib.bb_abi_version()}, binding expects {ABI_VERSION}"
+        )
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    """Map a bb_status to the exception types the reference's callers expect."""
+    if rc == 0:
+        return
+    msg = load().bb_last_error().decode(errors="replace")
+    text = f"{what}: {msg} (status {rc})"
+    if rc in (BB_ERR_INVALID, BB_ERR_WORKSPACE):
+        raise ValueError(text)
+    if rc == BB_ERR_UNSUPPORTED:
+        raise NotImplementedError(text)
+    if rc == BB_ERR_NOT_PD:
+        raise FloatingPointError(text)
+    raise RuntimeError(text)

@@ -1,0 +1,527 @@
+// fused.cu -- the hot path: per tile of 128 candidates
+//   K* = k(X*, X)                       CUDA cores (fp32, GEMM-form distance + Matern/RBF epilogue)
+//   mu~ = c + K* alpha                  CUDA cores (fp32, folded into the K* pass)
+//   V = K* L^-T                         tcgen05 tensor cores, fp16 hi/lo split x3, fp32 accum in TMEM,
+//                                       lower-triangular structure of L^-1 skipped tile-wise
+//   var~ = k** - |V|^2 ; un-standardise  TMEM -> registers epilogue
+//   q=1 acquisition value (MC or analytic) + running arg-max
+// K* never leaves the SM.  One persistent CTA per SM, warp-specialised:
+//   warps 0..15  compute (assembly, epilogue, MC)      warp 16  bulk-copy (TMA engine) producer
+//   warp 17      tcgen05.mma issuer (one elected lane)
+//
+// Reference path replaced: one chunk loop of botorch.optim.optimize_acqf_discrete
+// (/root/reference/baybe/recommenders/pure/bayesian/botorch/discrete.py:124-126) =
+// acqf(X[chunk].unsqueeze(-2)) -> SingleTaskGP.posterior (gaussian_process/core.py:268-269)
+// -> qLogExpectedImprovement.forward (class chosen at acquisition/base.py:162-181).
+#include "acq_math.cuh"
+#include "assemble.cuh"
+#include "common.cuh"
+
+namespace bb {
+
+constexpr int kComputeWarps = 16;
+constexpr int kComputeThreads = kComputeWarps * 32;  // 512
+constexpr int kFusedThreads = kComputeThreads + 64;  // + producer warp + MMA warp
+constexpr int kWarpProducer = 16;
+constexpr int kWarpMma = 17;
+constexpr int kMaxSlotsA = 4;
+constexpr int kMaxStagesB = 8;
+constexpr uint32_t kSlotABytes = 32768;  // [hi 16 KB | lo 16 KB], each 128 rows x 64 fp16, SW128
+constexpr uint32_t kStageBBytes = 16384; // [hi 8 KB | lo 8 KB],  each  64 rows x 64 fp16, SW128
+constexpr int kMaxTasks = 16;
+constexpr int kMaxSamples = 1024;
+
+struct FusedParams {
+  // candidates
+  const void* x;
+  int layout;
+  int64_t N, ldx;
+  int num_tiles;
+  // model
+  const float *cand_scale, *cand_shift, *train_m2, *train_sq, *alpha, *task_covar, *mean_const;
+  const int32_t* train_task;
+  const uint8_t* rimg;
+  int n_pad, d, d_pad, n_chunks, task_col, n_tasks;
+  float y_mean, y_std, prior_scale, inv_r_scale2;
+  int scaled;  // task kernel or output scale present
+  // ring sizes
+  int slots_a, stages_b;
+  uint32_t tmem_cols;
+  // acquisition (has_acq == 0: posterior only)
+  int has_acq;
+  bb_acq_spec acq;
+  const float* z;
+  int S;
+  // outputs (nullable)
+  float *mu, *var, *score;
+  const uint8_t* keep;
+  long long* best_key;
+  int64_t index_offset;
+};
+
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <int FAMILY>
+__global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  // ---- carve shared memory ----
+  uint8_t* ring_a = base;
+  uint8_t* ring_b = ring_a + (size_t)p.slots_a * kSlotABytes;
+  uint8_t* cur = ring_b + (size_t)p.stages_b * kStageBBytes;
+  const int dq = p.d_pad >> 2;
+  float4* xt4 = reinterpret_cast<float4*>(cur);
+  cur += (size_t)p.n_pad * p.d_pad * 4;
+  float* tsq = reinterpret_cast<float*>(cur);
+  cur += p.n_pad * 4;
+  float* alpha_s = reinterpret_cast<float*>(cur);
+  cur += p.n_pad * 4;
+  int32_t* ttask = reinterpret_cast<int32_t*>(cur);
+  cur += p.n_pad * 4;
+  float4* a_s = reinterpret_cast<float4*>(cur);
+  cur += (size_t)kTileM * p.d_pad * 4;
+  float* z_s = reinterpret_cast<float*>(cur);
+  cur += kMaxSamples * 4;
+  float* mean_part = reinterpret_cast<float*>(cur);  // [8][128]
+  cur += 8 * kTileM * 4;
+  float* var_part = reinterpret_cast<float*>(cur);   // [4][128]
+  cur += 4 * kTileM * 4;
+  float* mc_part = reinterpret_cast<float*>(cur);    // [4][128][2]
+  cur += 4 * kTileM * 2 * 4;
+  float* tcov = reinterpret_cast<float*>(cur);
+  cur += kMaxTasks * kMaxTasks * 4;
+  float* meanc = reinterpret_cast<float*>(cur);
+  cur += kMaxTasks * 4;
+  int32_t* cand_task = reinterpret_cast<int32_t*>(cur);
+  cur += kTileM * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cur);
+  uint64_t* a_full = bars;                       // [kMaxSlotsA]
+  uint64_t* a_empty = a_full + kMaxSlotsA;       // [kMaxSlotsA]
+  uint64_t* b_full = a_empty + kMaxSlotsA;       // [kMaxStagesB]
+  uint64_t* b_empty = b_full + kMaxStagesB;      // [kMaxStagesB]
+  uint64_t* d_full = b_empty + kMaxStagesB;      // [1]
+  uint64_t* d_empty = d_full + 1;                // [1]
+  cur += 32 * 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(cur);
+  float* zstat = reinterpret_cast<float*>(cur + 8);  // mean z, mean |z|
+  __shared__ long long best_red[4];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = p.n_chunks;
+
+  // ---- one-time setup ----
+  if (warp == kWarpMma && lane == 0) {
+    for (int i = 0; i < p.slots_a; ++i) {
+      mbar_init(&a_full[i], kComputeWarps);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < p.stages_b; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(d_full, 1);
+    mbar_init(d_empty, kComputeWarps);
+    fence_mbar_init();
+  }
+  if (warp == kWarpProducer) {
+    tmem_alloc(tmem_ptr, p.tmem_cols);
+    tmem_relinquish();
+  }
+  // model data resident in shared memory for the whole kernel
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.train_m2);
+    for (int e = tid; e < p.n_pad * dq; e += kFusedThreads) xt4[e] = __ldg(src + e);
+    for (int e = tid; e < p.n_pad; e += kFusedThreads) {
+      tsq[e] = __ldg(p.train_sq + e);
+      alpha_s[e] = __ldg(p.alpha + e);
+      ttask[e] = __ldg(p.train_task + e);
+    }
+    for (int e = tid; e < p.n_tasks * p.n_tasks; e += kFusedThreads) tcov[e] = __ldg(p.task_covar + e);
+    for (int e = tid; e < p.n_tasks; e += kFusedThreads) meanc[e] = __ldg(p.mean_const + e);
+    for (int e = tid; e < kTileM; e += kFusedThreads) cand_task[e] = 0;
+    if (p.has_acq && p.z != nullptr)
+      for (int e = tid; e < p.S; e += kFusedThreads) z_s[e] = __ldg(p.z + e);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (p.has_acq && warp == 0) {
+    float sz = 0.f, sa = 0.f;
+    for (int e = lane; e < p.S; e += 32) {
+      sz += z_s[e];
+      sa += fabsf(z_s[e]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      sz += __shfl_xor_sync(0xffffffffu, sz, o);
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    }
+    if (lane == 0) {
+      zstat[0] = sz / (float)p.S;
+      zstat[1] = sa / (float)p.S;
+    }
+  }
+
+  if (warp < kComputeWarps) {
+    // =====================================================================================
+    // compute warps
+    // =====================================================================================
+    AsmSmem sm;
+    sm.xt4 = xt4;
+    sm.tsq = tsq;
+    sm.ttask = ttask;
+    sm.tcov = tcov;
+    sm.a_s = a_s;
+    sm.cand_task = cand_task;
+    sm.dq = dq;
+    sm.T = p.n_tasks;
+    sm.scaled = p.scaled != 0;
+    const int mp = tid & 63, g = tid >> 6;       // assembly: candidates (mp, mp+64), i-octet g
+    const int row_e = tid & 127, sg = tid >> 7;  // epilogue: TMEM lane row_e, column/sample group
+    long long best = kEmptyKey;
+    uint32_t q = 0;  // running A-chunk counter (ring position)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int64_t row0 = (int64_t)tile * kTileM;
+      stage_candidates(p.x, p.layout, p.N, p.ldx, row0, p.d, p.d_pad, p.task_col, p.cand_scale,
+                       p.cand_shift, sm, tid, kComputeThreads);
+      bar_compute();
+      const float an0 = cand_sqnorm(sm, mp), an1 = cand_sqnorm(sm, mp + 64);
+      float mean0 = 0.f, mean1 = 0.f;
+      for (int c = 0; c < C; ++c, ++q) {
+        const uint32_t slot = q % (uint32_t)p.slots_a;
+        const uint32_t ph = (q / (uint32_t)p.slots_a) & 1u;
+        float k0[8], k1[8];
+        const int i0 = c * kChunk + g * 8;
+        assemble_2x8<FAMILY>(sm, mp, mp + 64, an0, an1, i0, k0, k1);
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+          const float al = alpha_s[i0 + ii];
+          mean0 = fmaf(k0[ii], al, mean0);
+          mean1 = fmaf(k1[ii], al, mean1);
+        }
+        uint4 h0, l0, h1, l1;
+        split_pair(k0[0], k0[1], h0.x, l0.x);
+        split_pair(k0[2], k0[3], h0.y, l0.y);
+        split_pair(k0[4], k0[5], h0.z, l0.z);
+        split_pair(k0[6], k0[7], h0.w, l0.w);
+        split_pair(k1[0], k1[1], h1.x, l1.x);
+        split_pair(k1[2], k1[3], h1.y, l1.y);
+        split_pair(k1[4], k1[5], h1.z, l1.z);
+        split_pair(k1[6], k1[7], h1.w, l1.w);
+        mbar_wait(&a_empty[slot], ph ^ 1u);  // MMAs that read this slot last time are done
+        uint8_t* sa = ring_a + (size_t)slot * kSlotABytes;
+        const uint32_t o0 = sw128_offset((uint32_t)mp, (uint32_t)g);
+        const uint32_t o1 = sw128_offset((uint32_t)(mp + 64), (uint32_t)g);
+        *reinterpret_cast<uint4*>(sa + o0) = h0;
+        *reinterpret_cast<uint4*>(sa + 16384 + o0) = l0;
+        *reinterpret_cast<uint4*>(sa + o1) = h1;
+        *reinterpret_cast<uint4*>(sa + 16384 + o1) = l1;
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[slot]);
+      }
+      mean_part[g * kTileM + mp] = mean0;
+      mean_part[g * kTileM + mp + 64] = mean1;
+
+      // ---- epilogue: |V|^2 per candidate from TMEM ----
+      mbar_wait(d_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      {
+        float ss = 0.f;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (int cb = sg; cb * 32 < p.n_pad; cb += 4) {
+          float v[32];
+          tmem_ld32(tmem_base + lane_base + (uint32_t)(cb * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) ss = fmaf(v[e], v[e], ss);
+        }
+        var_part[sg * kTileM + row_e] = ss;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty);
+      bar_compute();
+
+      // ---- moments in original units ----
+      const int ct = cand_task[row_e];
+      float msum = meanc[ct];
+#pragma unroll
+      for (int gg = 0; gg < 8; ++gg) msum += mean_part[gg * kTileM + row_e];
+      const float vsum = (var_part[row_e] + var_part[kTileM + row_e]) +
+                         (var_part[2 * kTileM + row_e] + var_part[3 * kTileM + row_e]);
+      const float kss = p.scaled ? tcov[ct * p.n_tasks + ct] : 1.0f;
+      float var_t = fmaxf(kss - vsum * p.inv_r_scale2, 1e-10f);
+      const float mu = fmaf(p.y_std, msum, p.y_mean);
+      const float var = p.y_std * p.y_std * var_t;
+      const int64_t row = row0 + row_e;
+      const bool in_range = row < p.N;
+      if (sg == 0 && in_range) {
+        if (p.mu) p.mu[row] = mu;
+        if (p.var) p.var[row] = var;
+      }
+      if (p.has_acq) {
+        float score;
+        const bool is_mc = p.acq.kind <= BB_ACQ_QPI;
+        if (is_mc) {
+          float s0, s1;
+          mc_partial(p.acq, mu, var, z_s, p.S, sg, 4, s0, s1);
+          mc_part[(sg * kTileM + row_e) * 2] = s0;
+          mc_part[(sg * kTileM + row_e) * 2 + 1] = s1;
+        }
+        bar_compute();
+        if (sg == 0) {
+          if (is_mc) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) {
+              s0 += mc_part[(gg * kTileM + row_e) * 2];
+              s1 += mc_part[(gg * kTileM + row_e) * 2 + 1];
+            }
+            score = mc_finalize(p.acq, mu, var, s0, s1, p.S, zstat[0], zstat[1]);
+          } else {
+            score = analytic_value(p.acq, mu, var);
+          }
+          if (in_range) {
+            if (p.score) p.score[row] = score;
+            const bool ok = (p.keep == nullptr || p.keep[row] != 0) && !(score != score);
+            if (ok) {
+              long long key = pack_key(score, (uint32_t)(row + p.index_offset));
+              best = key > best ? key : best;
+            }
+          }
+        }
+      } else {
+        bar_compute();  // a_s / partial buffers are rewritten by the next tile
+      }
+    }
+    // ---- CTA-level arg-max ----
+    if (p.best_key != nullptr && p.has_acq) {
+      if (sg == 0) {
+        for (int o = 16; o > 0; o >>= 1) {
+          long long other = __shfl_xor_sync(0xffffffffu, best, o);
+          best = other > best ? other : best;
+        }
+        if (lane == 0) best_red[warp] = best;
+      }
+      bar_compute();
+      if (tid == 0) {
+        long long b = best_red[0];
+        for (int w = 1; w < 4; ++w) b = best_red[w] > b ? best_red[w] : b;
+        if (b != kEmptyKey) atomicMax(p.best_key, b);
+      }
+    }
+  } else if (warp == kWarpProducer) {
+    // =====================================================================================
+    // producer: stream the fp16 image of L^-1 (B operand) through the TMA engine
+    // =====================================================================================
+    if (lane == 0) {
+      uint32_t qb = 0;
+      const int n_tiles_b = C * (C + 1) / 2;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tb = 0; tb < n_tiles_b; ++tb, ++qb) {
+          const uint32_t st = qb % (uint32_t)p.stages_b;
+          const uint32_t ph = (qb / (uint32_t)p.stages_b) & 1u;
+          mbar_wait(&b_empty[st], ph ^ 1u);
+          mbar_expect_tx(&b_full[st], kStageBBytes);
+          bulk_g2s(ring_b + (size_t)st * kStageBBytes, p.rimg + (size_t)tb * kStageBBytes,
+                   kStageBBytes, &b_full[st]);
+        }
+      }
+    }
+  } else {
+    // =====================================================================================
+    // MMA issuer: D[128 x n_pad] (TMEM, fp32) = K*[128 x n_pad] (smem, fp16 hi+lo) * Linv^T
+    // =====================================================================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kTileM, kChunk);
+      uint32_t qa = 0, qb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(d_empty, (uint32_t)((it & 1) ^ 1));  // epilogue of the previous tile drained TMEM
+        tc_fence_after();
+        for (int c = 0; c < C; ++c, ++qa) {
+          const uint32_t slot = qa % (uint32_t)p.slots_a;
+          mbar_wait(&a_full[slot], (qa / (uint32_t)p.slots_a) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(ring_a + (size_t)slot * kSlotABytes);
+          const uint64_t a_hi = make_sw128_desc(a_addr);
+          const uint64_t a_lo = make_sw128_desc(a_addr + 16384);
+          for (int s = c; s < C; ++s, ++qb) {
+            const uint32_t st = qb % (uint32_t)p.stages_b;
+            mbar_wait(&b_full[st], (qb / (uint32_t)p.stages_b) & 1u);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(ring_b + (size_t)st * kStageBBytes);
+            const uint64_t b_hi = make_sw128_desc(b_addr);
+            const uint64_t b_lo = make_sw128_desc(b_addr + 8192);
+            const uint32_t d_addr = tmem_base + (uint32_t)(s * kChunk);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ko = (uint64_t)(kk * 2);  // 16 fp16 = 32 bytes = 2 x 16-byte units
+              umma_f16(d_addr, a_hi + ko, b_hi + ko, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+              umma_f16(d_addr, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_f16(d_addr, a_lo + ko, b_hi + ko, idesc, 1u);
+            }
+            umma_commit(&b_empty[st]);
+          }
+          umma_commit(&a_empty[slot]);
+        }
+        umma_commit(d_full);
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpProducer) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+static size_t fused_smem_bytes(const FusedParams& p) {
+  size_t b = 1024;  // alignment slack
+  b += (size_t)p.slots_a * kSlotABytes + (size_t)p.stages_b * kStageBBytes;
+  b += (size_t)p.n_pad * p.d_pad * 4 + (size_t)p.n_pad * 12;
+  b += (size_t)kTileM * p.d_pad * 4 + kMaxSamples * 4;
+  b += 8 * kTileM * 4 + 4 * kTileM * 4 + 4 * kTileM * 2 * 4;
+  b += kMaxTasks * kMaxTasks * 4 + kMaxTasks * 4 + kTileM * 4;
+  b += 32 * 8 + 64;
+  return b;
+}
+
+template <int FAMILY>
+static int launch_family(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
+  BB_CUDA(cudaFuncSetAttribute(k_fused<FAMILY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  k_fused<FAMILY><<<grid, kFusedThreads, smem, stream>>>(p);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
+                 const bb_acq_spec* acq, const float* d_z, int32_t S, const uint8_t* d_keep,
+                 float* d_mu, float* d_var, float* d_score, int64_t* d_best_key,
+                 int64_t index_offset, cudaStream_t stream) {
+  BB_CHECK_ARG(m && m->abi_version == BB_ABI_VERSION, "model struct missing or ABI mismatch");
+  BB_CHECK_ARG(d_x != nullptr || N == 0, "candidate pointer is null");
+  BB_CHECK_ARG(layout >= 0 && layout <= 3, "unknown candidate layout %d", layout);
+  BB_CHECK_ARG(N >= 0, "negative candidate count");
+  const bool col_major = (layout == BB_COL_MAJOR_F32 || layout == BB_COL_MAJOR_F64);
+  BB_CHECK_ARG(col_major ? ldx >= N : ldx >= m->d, "leading dimension %lld too small",
+               (long long)ldx);
+  BB_CHECK_ARG(N + index_offset < 0xffffffffLL, "candidate index exceeds the 32-bit key range");
+  BB_CHECK_SUPPORTED(m->n_tasks <= kMaxTasks, "at most %d tasks supported", kMaxTasks);
+  if (acq) {
+    BB_CHECK_ARG(acq->kind >= BB_ACQ_QLOGEI && acq->kind <= BB_ACQ_PSTD, "unknown acquisition kind %d",
+                 acq->kind);
+    const bool is_mc = acq->kind <= BB_ACQ_QPI;
+    BB_CHECK_ARG(!is_mc || (d_z != nullptr && S >= 16 && S <= kMaxSamples && S % 16 == 0),
+                 "fused MC scoring needs base samples with 16 <= S <= %d, S %% 16 == 0 (got S=%d)",
+                 kMaxSamples, S);
+  }
+  if (N == 0) return BB_OK;
+
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = d_x;
+  p.layout = layout;
+  p.N = N;
+  p.ldx = ldx;
+  p.num_tiles = (int)((N + kTileM - 1) / kTileM);
+  p.cand_scale = m->d_cand_scale;
+  p.cand_shift = m->d_cand_shift;
+  p.train_m2 = m->d_train_m2;
+  p.train_sq = m->d_train_sq;
+  p.alpha = m->d_alpha;
+  p.task_covar = m->d_task_covar;
+  p.mean_const = m->d_mean_const;
+  p.train_task = m->d_train_task;
+  p.rimg = reinterpret_cast<const uint8_t*>(m->d_rimg);
+  p.n_pad = m->n_pad;
+  p.d = m->d;
+  p.d_pad = m->d_pad;
+  p.n_chunks = m->n_chunks;
+  p.task_col = m->task_col;
+  p.n_tasks = m->n_tasks;
+  p.y_mean = m->y_mean;
+  p.y_std = m->y_std;
+  p.prior_scale = m->prior_scale;
+  p.inv_r_scale2 = 1.0f / (m->r_scale * m->r_scale);
+  p.scaled = (m->task_col >= 0 || m->prior_scale != 1.0f) ? 1 : 0;
+  p.has_acq = acq ? 1 : 0;
+  if (acq) p.acq = *acq;
+  p.z = d_z;
+  p.S = S;
+  p.mu = d_mu;
+  p.var = d_var;
+  p.score = d_score;
+  p.keep = d_keep;
+  p.best_key = reinterpret_cast<long long*>(d_best_key);
+  p.index_offset = index_offset;
+  uint32_t cols = 32;
+  while ((int)cols < p.n_pad) cols <<= 1;
+  BB_CHECK_SUPPORTED(cols <= 512, "n_pad=%d exceeds the 512 TMEM columns", p.n_pad);
+  p.tmem_cols = cols;
+
+  int dev = 0, max_smem = 0, sms = 0;
+  BB_CUDA(cudaGetDevice(&dev));
+  BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // ring sizes: as many as fit, B stages first (they hide L2 latency), then A slots
+  p.slots_a = 2;
+  p.stages_b = 2;
+  while (true) {
+    FusedParams t = p;
+    if (t.stages_b < 4) t.stages_b++;
+    else if (t.slots_a < 3) t.slots_a++;
+    else if (t.stages_b < kMaxStagesB) t.stages_b++;
+    else break;
+    if (fused_smem_bytes(t) > (size_t)max_smem) break;
+    p = t;
+  }
+  const size_t smem = fused_smem_bytes(p);
+  BB_CHECK_SUPPORTED(smem <= (size_t)max_smem,
+                     "shared-memory budget exceeded: need %zu bytes, device allows %d", smem,
+                     max_smem);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  switch (m->family) {
+    case BB_KERNEL_MATERN12: return launch_family<BB_KERNEL_MATERN12>(p, grid, smem, stream);
+    case BB_KERNEL_MATERN32: return launch_family<BB_KERNEL_MATERN32>(p, grid, smem, stream);
+    case BB_KERNEL_MATERN52: return launch_family<BB_KERNEL_MATERN52>(p, grid, smem, stream);
+    default: return launch_family<BB_KERNEL_RBF>(p, grid, smem, stream);
+  }
+}
+
+}  // namespace bb
+
+using namespace bb;
+
+extern "C" int bb_score_fused(const bb_model* m, const bb_acq_spec* a, const void* d_x,
+                              int32_t layout, int64_t N, int64_t ldx, const uint8_t* d_keep,
+                              const float* d_z, int32_t S, float* d_score, int64_t* d_best_key,
+                              int64_t index_offset, void* stream) {
+  BB_CHECK_ARG(a != nullptr, "bb_score_fused: acquisition spec is null");
+  return launch_fused(m, d_x, layout, N, ldx, a, d_z, S, d_keep, nullptr, nullptr, d_score,
+                      d_best_key, index_offset, (cudaStream_t)stream);
+}
+
+namespace bb {
+int launch_cross(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
+                 const float* d_pend_x, const float* d_pend_beta, int32_t P, float* d_cross,
+                 cudaStream_t stream);
+}
+
+extern "C" int bb_posterior(const bb_model* m, const void* d_x, int32_t layout, int64_t N,
+                            int64_t ldx, float* d_mu, float* d_var, float* d_cross,
+                            const float* d_pend_x, const float* d_pend_beta, int32_t n_pending,
+                            void* stream) {
+  BB_CHECK_ARG(d_mu != nullptr && d_var != nullptr, "bb_posterior: output pointers are null");
+  int rc = launch_fused(m, d_x, layout, N, ldx, nullptr, nullptr, 0, nullptr, d_mu, d_var, nullptr,
+                        nullptr, 0, (cudaStream_t)stream);
+  if (rc != BB_OK) return rc;
+  if (d_cross != nullptr && n_pending > 0)
+    return launch_cross(m, d_x, layout, N, ldx, d_pend_x, d_pend_beta, n_pending, d_cross,
+                        (cudaStream_t)stream);
+  return BB_OK;
+}

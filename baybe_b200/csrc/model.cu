@@ -1,0 +1,575 @@
+// model.cu -- training-side caches: K(X,X)+noise, Cholesky, L^-1, alpha, and the
+// tensor-core image of L^-1.  Everything here runs once per fitted model, in float64, on the GPU.
+//
+// Replaces what gpytorch's DefaultPredictionStrategy computes lazily on the first posterior
+// call of botorch.models.SingleTaskGP (reference entry: GaussianProcessSurrogate._posterior,
+// /root/reference/baybe/surrogates/gaussian_process/core.py:268-269; model built at :331-339).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace bb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------
+// blob layout
+// ------------------------------------------------------------------------------------------
+struct BlobLayout {
+  size_t cand_scale, cand_shift, train_m2, train_sq, alpha, train_task, task_covar, mean_const,
+      rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, flags,
+      total;
+  int n_pad, d_pad, n_chunks, n_tiles;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static BlobLayout make_layout(int n, int d, int T) {
+  BlobLayout L;
+  L.n_pad = round_up(n, kChunk);
+  L.d_pad = round_up(d, 4);
+  L.n_chunks = L.n_pad / kChunk;
+  L.n_tiles = L.n_chunks * (L.n_chunks + 1) / 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  L.cand_scale = take(sizeof(float) * L.d_pad);
+  L.cand_shift = take(sizeof(float) * L.d_pad);
+  L.train_m2 = take(sizeof(float) * (size_t)L.n_pad * L.d_pad);
+  L.train_sq = take(sizeof(float) * L.n_pad);
+  L.alpha = take(sizeof(float) * L.n_pad);
+  L.train_task = take(sizeof(int32_t) * L.n_pad);
+  L.task_covar = take(sizeof(float) * T * T);
+  L.mean_const = take(sizeof(float) * T);
+  L.rimg = take((size_t)L.n_tiles * 16384);
+  L.linv = take(sizeof(double) * (size_t)n * n);
+  L.alpha64 = take(sizeof(double) * n);
+  L.xn64 = take(sizeof(double) * (size_t)n * d);
+  L.linv32 = take(sizeof(float) * (size_t)L.n_pad * L.n_pad);
+  L.kmat = take(sizeof(double) * (size_t)n * n);
+  L.resid = take(sizeof(double) * n * 2);
+  L.noise_row = take(sizeof(double) * n);
+  L.tcov64 = take(sizeof(double) * (T * T + d));
+  L.cnorm = take(sizeof(float) * 2 * d);
+  L.pend_norm = take(sizeof(double) * BB_MAX_PENDING * d);
+  L.pend_w64 = take(sizeof(double) * BB_MAX_PENDING * n);
+  L.flags = take(64);
+  L.total = off;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------
+// float64 kernel function on the normalised inputs (direct differences: exact in float64)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double kernel_f64(int family, double r2) {
+  if (family == BB_KERNEL_RBF) return exp(-0.5 * r2);
+  double r = sqrt(fmax(r2, 1e-30));
+  if (family == BB_KERNEL_MATERN12) return exp(-r);
+  if (family == BB_KERNEL_MATERN32) {
+    double s = 1.7320508075688772 * r;
+    return (1.0 + s) * exp(-s);
+  }
+  double s = 2.23606797749979 * r;
+  return (1.0 + s + (5.0 / 3.0) * r2) * exp(-s);
+}
+
+// d_aux: [T*T] task covariance (prior scale folded in; 1x1 = prior scale without tasks),
+// followed by [d] inverse lengthscales (0 for inactive columns / the task column).
+__device__ __forceinline__ double k_pair_f64(const double* __restrict__ xa,
+                                             const double* __restrict__ xb, int d,
+                                             const double* __restrict__ inv_ls, int family) {
+  double r2 = 0.0;
+  for (int j = 0; j < d; ++j) {
+    double u = (xa[j] - xb[j]) * inv_ls[j];
+    r2 += u * u;
+  }
+  return kernel_f64(family, r2);
+}
+
+__global__ void k_train_gram(const double* __restrict__ xn, const int32_t* __restrict__ task,
+                             const double* __restrict__ aux, const double* __restrict__ noise_row,
+                             int n, int d, int T, int family, double jitter,
+                             double* __restrict__ K) {
+  const double* tcov = aux;
+  const double* inv_ls = aux + T * T;
+  int i = blockIdx.y * blockDim.y + threadIdx.y;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || j >= n) return;
+  double k;
+  if (i == j) {
+    k = 1.0;  // x1 is x2: gpytorch sets the self-distance diagonal to exactly 0
+  } else {
+    k = k_pair_f64(xn + (size_t)i * d, xn + (size_t)j * d, d, inv_ls, family);
+  }
+  k *= tcov[task[i] * T + task[j]];
+  if (i == j) k += noise_row[i] + jitter;
+  K[(size_t)i * n + j] = k;
+}
+
+// In-place lower Cholesky of the n x n row-major matrix A (single CTA).  fail[0] != 0 on a
+// non-positive pivot.
+__global__ void __launch_bounds__(1024) k_cholesky(double* __restrict__ A, int n,
+                                                   int* __restrict__ fail) {
+  extern __shared__ double col[];
+  __shared__ int bad;
+  int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    if (tid == 0) {
+      double dj = A[(size_t)j * n + j];
+      if (!(dj > 0.0)) {
+        bad = 1;
+        dj = 1.0;
+      }
+      A[(size_t)j * n + j] = sqrt(dj);
+    }
+    __syncthreads();
+    double inv = 1.0 / A[(size_t)j * n + j];
+    for (int i = j + 1 + tid; i < n; i += nt) {
+      double v = A[(size_t)i * n + j] * inv;
+      A[(size_t)i * n + j] = v;
+      col[i] = v;
+    }
+    __syncthreads();
+    int m = n - j - 1;  // trailing size
+    for (int e = tid; e < m * m; e += nt) {
+      int ii = e / m, kk = e - ii * m;
+      if (kk <= ii) {
+        int i = j + 1 + ii, k = j + 1 + kk;
+        A[(size_t)i * n + k] -= col[i] * col[k];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) fail[0] = bad;
+  // zero the strict upper triangle so that A is exactly L
+  for (int e = tid; e < n * n; e += nt) {
+    int i = e / n, k = e - i * n;
+    if (k > i) A[e] = 0.0;
+  }
+}
+
+// X = L^-1 (lower triangular), one thread per column, forward substitution.
+__global__ void k_tri_inverse(const double* __restrict__ L, int n, double* __restrict__ X) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  for (int i = 0; i < c; ++i) X[(size_t)i * n + c] = 0.0;
+  X[(size_t)c * n + c] = 1.0 / L[(size_t)c * n + c];
+  for (int i = c + 1; i < n; ++i) {
+    const double* Li = L + (size_t)i * n;
+    double s0 = 0.0, s1 = 0.0;
+    int k = c;
+    for (; k + 1 < i; k += 2) {
+      s0 += Li[k] * X[(size_t)k * n + c];
+      s1 += Li[k + 1] * X[(size_t)(k + 1) * n + c];
+    }
+    if (k < i) s0 += Li[k] * X[(size_t)k * n + c];
+    X[(size_t)i * n + c] = -(s0 + s1) / Li[i];
+  }
+}
+
+// u = Linv r ; alpha = Linv^T u   (single CTA, n <= 1024 threads)
+__global__ void k_alpha(const double* __restrict__ Linv, const double* __restrict__ resid, int n,
+                        double* __restrict__ u, double* __restrict__ alpha64,
+                        float* __restrict__ alpha32) {
+  int t = threadIdx.x;
+  if (t < n) {
+    double s = 0.0;
+    for (int i = 0; i <= t; ++i) s += Linv[(size_t)t * n + i] * resid[i];
+    u[t] = s;
+  }
+  __syncthreads();
+  if (t < n) {
+    double s = 0.0;
+    for (int j = t; j < n; ++j) s += Linv[(size_t)j * n + t] * u[j];
+    alpha64[t] = s;
+    alpha32[t] = (float)s;
+  }
+}
+
+__global__ void k_absmax(const double* __restrict__ X, size_t count, double* __restrict__ out) {
+  __shared__ double red[256];
+  double m = 0.0;
+  for (size_t e = threadIdx.x; e < count; e += blockDim.x) m = fmax(m, fabs(X[e]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// fp16 hi/lo image of (scale * L^-1) laid out as the sequence of B-operand tiles the MMA warp
+// consumes: for K chunk c (training points 64c..64c+63) and N sub-block s >= c (columns
+// 64s..64s+63 of D), one 16 KB tile [hi 8 KB | lo 8 KB], each [64 n-rows][64 k] fp16, K-major,
+// 128-byte swizzled.  B[n=j][k=i] = Linv[j][i] so that D[m][j] = sum_i K*[m][i] Linv[j][i].
+__global__ void k_build_rimg(const double* __restrict__ Linv, int n, int n_chunks, double scale,
+                             uint8_t* __restrict__ rimg, float* __restrict__ linv32, int n_pad) {
+  int tile = blockIdx.x;
+  // decode (c, s) from the linear tile index: tiles are ordered c-major, s = c..C-1
+  int c = 0, rem = tile;
+  while (rem >= n_chunks - c) {
+    rem -= n_chunks - c;
+    ++c;
+  }
+  int s = c + rem;
+  uint8_t* base = rimg + (size_t)tile * 16384;
+  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    int r = e >> 6, kk = e & 63;
+    int j = s * 64 + r, i = c * 64 + kk;
+    double v = (j < n && i < n && i <= j) ? Linv[(size_t)j * n + i] * scale : 0.0;
+    float vf = (float)v;
+    __half hi = __float2half_rn(vf);
+    __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+    uint32_t off = sw128_offset((uint32_t)r, (uint32_t)(kk >> 3)) + (uint32_t)(kk & 7) * 2u;
+    *reinterpret_cast<__half*>(base + off) = hi;
+    *reinterpret_cast<__half*>(base + 8192 + off) = lo;
+  }
+  // fp32 dense copy, zero padded (the strict upper triangle stays zero from the blob memset)
+  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    int r = e >> 6, kk = e & 63;
+    int j = s * 64 + r, i = c * 64 + kk;
+    double v = (j < n && i < n && i <= j) ? Linv[(size_t)j * n + i] : 0.0;
+    linv32[(size_t)j * n_pad + i] = (float)v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pending-point statistics (float64 math, fp32 outputs)
+// ------------------------------------------------------------------------------------------
+// one CTA per pending point p: kx = k(X, p) ; w = Linv kx ; beta = Linv^T w ; mu = c + kx.alpha
+__global__ void k_pending_w(const float* __restrict__ pend_x, int P, int n, int n_pad, int d,
+                            int T, int family, int task_col, const double* __restrict__ xn,
+                            const int32_t* __restrict__ ttask, const double* __restrict__ aux,
+                            const float* __restrict__ cand_norm /* [2*d]: lo, inv_range */,
+                            const double* __restrict__ Linv, const double* __restrict__ alpha64,
+                            const float* __restrict__ mean_const, float y_mean, float y_std,
+                            float* __restrict__ beta_out, float* __restrict__ mu_out,
+                            double* __restrict__ pn_out /* [P*d] normalised pending */,
+                            double* __restrict__ w_out /* [P*n] */) {
+  extern __shared__ double sh[];
+  double* pn = sh;           // [d]
+  double* kx = sh + d;       // [n]
+  double* w = sh + d + n;    // [n]
+  __shared__ double red[256];
+  int p = blockIdx.x, tid = threadIdx.x;
+  const double* tcov = aux;
+  const double* inv_ls = aux + T * T;
+  for (int j = tid; j < d; j += blockDim.x) {
+    double x = (double)pend_x[(size_t)p * d + j];
+    double v = (j == task_col) ? x : (x - (double)cand_norm[j]) * (double)cand_norm[d + j];
+    pn[j] = v;
+    pn_out[(size_t)p * d + j] = v;
+  }
+  __syncthreads();
+  int tp = (task_col >= 0) ? min(max((int)llrint(pn[task_col]), 0), T - 1) : 0;
+  double part = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    double k = k_pair_f64(pn, xn + (size_t)i * d, d, inv_ls, family) * tcov[tp * T + ttask[i]];
+    kx[i] = k;
+    part += k * alpha64[i];
+  }
+  red[tid] = part;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] += red[tid + s];
+    __syncthreads();
+  }
+  if (tid == 0) mu_out[p] = y_mean + y_std * (float)((double)mean_const[tp] + red[0]);
+  for (int j = tid; j < n; j += blockDim.x) {
+    double s = 0.0;
+    for (int i = 0; i <= j; ++i) s += Linv[(size_t)j * n + i] * kx[i];
+    w[j] = s;
+    w_out[(size_t)p * n + j] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < n_pad; i += blockDim.x) {
+    double s = 0.0;
+    if (i < n)
+      for (int j = i; j < n; ++j) s += Linv[(size_t)j * n + i] * w[j];
+    beta_out[(size_t)p * n_pad + i] = (float)s;
+  }
+}
+
+// cov[p][q] = (k(p,q) - w_p . w_q) * y_std^2, float64
+__global__ void k_pending_cov(const double* __restrict__ pn, const double* __restrict__ w, int P,
+                              int n, int d, int T, int family, int task_col,
+                              const double* __restrict__ aux, float y_std,
+                              float* __restrict__ cov) {
+  int p = blockIdx.x, q = threadIdx.x;
+  if (q >= P) return;
+  const double* tcov = aux;
+  const double* inv_ls = aux + T * T;
+  int tp = (task_col >= 0) ? min(max((int)llrint(pn[(size_t)p * d + task_col]), 0), T - 1) : 0;
+  int tq = (task_col >= 0) ? min(max((int)llrint(pn[(size_t)q * d + task_col]), 0), T - 1) : 0;
+  double k = (p == q) ? 1.0 : k_pair_f64(pn + (size_t)p * d, pn + (size_t)q * d, d, inv_ls, family);
+  k *= tcov[tp * T + tq];
+  double s = 0.0;
+  for (int j = 0; j < n; ++j) s += w[(size_t)p * n + j] * w[(size_t)q * n + j];
+  cov[p * P + q] = (float)((k - s) * (double)y_std * (double)y_std);
+}
+
+}  // namespace bb
+
+using namespace bb;
+
+extern "C" int bb_abi_version(void) { return BB_ABI_VERSION; }
+extern "C" const char* bb_last_error(void) { return bb::last_error(); }
+
+extern "C" size_t bb_model_blob_bytes(int32_t n, int32_t d, int32_t n_tasks) {
+  if (n <= 0 || d <= 0 || n_tasks <= 0) return 0;
+  return make_layout(n, d, n_tasks).total;
+}
+
+extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t blob_bytes,
+                              bb_model* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  BB_CHECK_ARG(desc && d_blob && out, "bb_model_build: null argument");
+  const int n = desc->n, d = desc->d, T = desc->n_tasks;
+  BB_CHECK_ARG(n >= 1 && d >= 1 && T >= 1, "bb_model_build: n, d, n_tasks must be positive");
+  BB_CHECK_SUPPORTED(n <= BB_MAX_TRAIN,
+                     "bb_model_build: n=%d training points exceeds this build's limit of %d", n,
+                     BB_MAX_TRAIN);
+  BB_CHECK_ARG(desc->family >= 0 && desc->family <= 3, "bb_model_build: unknown kernel family %d",
+               desc->family);
+  BB_CHECK_ARG(desc->task_col >= -1 && desc->task_col < d, "bb_model_build: bad task_col");
+  BB_CHECK_ARG((desc->task_col >= 0) == (desc->task_covar != nullptr) || T == 1,
+               "bb_model_build: task_col and task_covar must be given together");
+  BB_CHECK_ARG(desc->train_x && desc->train_y && desc->lower && desc->upper && desc->lengthscale &&
+                   desc->noise && desc->mean_const,
+               "bb_model_build: null array in descriptor");
+  BB_CHECK_ARG(((uintptr_t)d_blob & 1023) == 0, "bb_model_build: blob must be 1024-byte aligned");
+  BlobLayout L = make_layout(n, d, T);
+  if (blob_bytes < bb_model_blob_bytes(n, d, T)) {
+    set_error("bb_model_build: blob of %zu bytes is smaller than the required %zu", blob_bytes,
+              bb_model_blob_bytes(n, d, T));
+    return BB_ERR_WORKSPACE;
+  }
+  // the scoring kernel keeps the scaled training rows resident in shared memory
+  BB_CHECK_SUPPORTED((size_t)L.n_pad * L.d_pad * 4 <= 56 * 1024,
+                     "bb_model_build: n_pad*d_pad = %d*%d floats exceeds the 56 KB shared-memory "
+                     "budget of the scoring kernel",
+                     L.n_pad, L.d_pad);
+
+  // ---- host-side parameter packing (float64): Normalize / Standardize / ARD folding ----
+  const double kfam = desc->family == BB_KERNEL_MATERN52   ? 5.0
+                      : desc->family == BB_KERNEL_MATERN32 ? 3.0
+                      : desc->family == BB_KERNEL_MATERN12 ? 1.0
+                                                           : 0.5 * 1.4426950408889634;
+  const double sq_kfam = sqrt(kfam);
+  std::vector<double> lo(d), inv_range(d), inv_ls(d), centre(d, 0.0), xn((size_t)n * d);
+  for (int j = 0; j < d; ++j) {
+    double r = desc->upper[j] - desc->lower[j];
+    if (fabs(r) < 1e-12) r = 1.0;  // botorch Normalize: degenerate range -> 1
+    lo[j] = desc->lower[j];
+    inv_range[j] = 1.0 / r;
+    double ls = desc->lengthscale[j];
+    inv_ls[j] = (j == desc->task_col || !(ls > 0.0)) ? 0.0 : 1.0 / ls;
+    if (j == desc->task_col) {
+      lo[j] = 0.0;
+      inv_range[j] = 1.0;
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < d; ++j) {
+      double v = (desc->train_x[(size_t)i * d + j] - lo[j]) * inv_range[j];
+      xn[(size_t)i * d + j] = v;
+      centre[j] += v / n;
+    }
+  std::vector<int32_t> ttask(L.n_pad, 0);
+  if (desc->task_col >= 0)
+    for (int i = 0; i < n; ++i) {
+      long t = lrint(xn[(size_t)i * d + desc->task_col]);
+      BB_CHECK_ARG(t >= 0 && t < T, "bb_model_build: training task id %ld outside [0,%d)", t, T);
+      ttask[i] = (int32_t)t;
+    }
+  double y_mean = 0.0, y_std = 1.0;
+  for (int i = 0; i < n; ++i) y_mean += desc->train_y[i] / n;
+  if (n > 1) {
+    double ss = 0.0;
+    for (int i = 0; i < n; ++i) ss += (desc->train_y[i] - y_mean) * (desc->train_y[i] - y_mean);
+    y_std = sqrt(ss / (n - 1));
+    if (!(y_std >= 1e-8)) y_std = 1.0;  // botorch Standardize min_stdv
+  }
+  const double prior_scale = desc->has_outputscale ? desc->outputscale : 1.0;
+  std::vector<double> aux(T * T + d);
+  for (int a = 0; a < T; ++a)
+    for (int b = 0; b < T; ++b)
+      aux[a * T + b] = prior_scale * (desc->task_covar ? desc->task_covar[a * T + b] : 1.0);
+  for (int j = 0; j < d; ++j) aux[T * T + j] = inv_ls[j];
+  std::vector<double> resid(n), noise_row(n);
+  for (int i = 0; i < n; ++i) {
+    double nz = desc->noise[ttask[i]];
+    noise_row[i] = nz < 1e-4 ? 1e-4 : nz;  // MIN_INFERRED_NOISE_LEVEL
+    resid[i] = (desc->train_y[i] - y_mean) / y_std - desc->mean_const[ttask[i]];
+  }
+  // fp32 candidate transform a_j = x_j*scale_j + shift_j and the (-2 x) scaled training rows
+  std::vector<float> cscale(L.d_pad, 0.f), cshift(L.d_pad, 0.f), tm2((size_t)L.n_pad * L.d_pad, 0.f),
+      tsq(L.n_pad, 0.f), tcov32(T * T), mean32(T), cnorm(2 * d);
+  for (int j = 0; j < d; ++j) {
+    double g = inv_ls[j] * sq_kfam;
+    cscale[j] = (float)(inv_range[j] * g);
+    cshift[j] = (float)(-(lo[j] * inv_range[j] + centre[j]) * g);
+    cnorm[j] = (float)lo[j];
+    cnorm[d + j] = (float)inv_range[j];
+  }
+  for (int i = 0; i < n; ++i) {
+    double sq = 0.0;
+    for (int j = 0; j < d; ++j) {
+      float b = (float)((xn[(size_t)i * d + j] - centre[j]) * inv_ls[j] * sq_kfam);
+      tm2[(size_t)i * L.d_pad + j] = -2.0f * b;
+      sq += (double)b * (double)b;
+    }
+    tsq[i] = (float)sq;
+  }
+  // padded training rows: zero kernel contribution is guaranteed by zero rows of L^-1 / alpha
+  for (int a = 0; a < T * T; ++a) tcov32[a] = (float)aux[a];
+  for (int a = 0; a < T; ++a) mean32[a] = (float)desc->mean_const[a];
+
+  uint8_t* B = (uint8_t*)d_blob;
+  BB_CUDA(cudaMemsetAsync(B, 0, L.total, stream));
+  auto up = [&](size_t off, const void* src, size_t bytes) {
+    return cudaMemcpyAsync(B + off, src, bytes, cudaMemcpyHostToDevice, stream);
+  };
+  BB_CUDA(up(L.cand_scale, cscale.data(), cscale.size() * 4));
+  BB_CUDA(up(L.cand_shift, cshift.data(), cshift.size() * 4));
+  BB_CUDA(up(L.train_m2, tm2.data(), tm2.size() * 4));
+  BB_CUDA(up(L.train_sq, tsq.data(), tsq.size() * 4));
+  BB_CUDA(up(L.train_task, ttask.data(), ttask.size() * 4));
+  BB_CUDA(up(L.task_covar, tcov32.data(), tcov32.size() * 4));
+  BB_CUDA(up(L.mean_const, mean32.data(), mean32.size() * 4));
+  BB_CUDA(up(L.xn64, xn.data(), xn.size() * 8));
+  BB_CUDA(up(L.resid, resid.data(), resid.size() * 8));
+  BB_CUDA(up(L.noise_row, noise_row.data(), noise_row.size() * 8));
+  BB_CUDA(up(L.tcov64, aux.data(), aux.size() * 8));
+  BB_CUDA(up(L.cnorm, cnorm.data(), cnorm.size() * 4));
+  BB_CUDA(cudaStreamSynchronize(stream));  // host vectors above go out of scope only after this
+
+  double* dK = (double*)(B + L.kmat);
+  double* dLinv = (double*)(B + L.linv);
+  int* dflag = (int*)(B + L.flags);
+  double* dmax = (double*)(B + L.flags + 16);
+  BB_CUDA(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(sizeof(double) * n)));
+  int tries = 0;
+  double jitter = 0.0;
+  for (;; ++tries) {
+    // linear_operator psd_safe_cholesky: plain, then 1e-8, 1e-7, 1e-6 (float64)
+    jitter = tries == 0 ? 0.0 : 1e-8 * pow(10.0, tries - 1);
+    dim3 blk(16, 16), grd((n + 15) / 16, (n + 15) / 16);
+    k_train_gram<<<grd, blk, 0, stream>>>((const double*)(B + L.xn64),
+                                          (const int32_t*)(B + L.train_task),
+                                          (const double*)(B + L.tcov64),
+                                          (const double*)(B + L.noise_row), n, d, T, desc->family,
+                                          jitter, dK);
+    BB_LAUNCH_CHECK();
+    k_cholesky<<<1, 1024, sizeof(double) * n, stream>>>(dK, n, dflag);
+    BB_LAUNCH_CHECK();
+    int flag = 0;
+    BB_CUDA(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    BB_CUDA(cudaStreamSynchronize(stream));
+    if (flag == 0) break;
+    if (tries == 3) {
+      set_error("bb_model_build: K + noise*I is not positive definite (jitter up to 1e-6 tried)");
+      return BB_ERR_NOT_PD;
+    }
+  }
+  k_tri_inverse<<<(n + 31) / 32, 32, 0, stream>>>(dK, n, dLinv);
+  BB_LAUNCH_CHECK();
+  k_alpha<<<1, 1024, 0, stream>>>(dLinv, (const double*)(B + L.resid), n,
+                                  (double*)(B + L.resid) + n, (double*)(B + L.alpha64),
+                                  (float*)(B + L.alpha));
+  BB_LAUNCH_CHECK();
+  k_absmax<<<1, 256, 0, stream>>>(dLinv, (size_t)n * n, dmax);
+  BB_LAUNCH_CHECK();
+  double amax = 0.0;
+  BB_CUDA(cudaMemcpyAsync(&amax, dmax, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  BB_CUDA(cudaStreamSynchronize(stream));
+  if (!(amax > 0.0) || !isfinite(amax)) {
+    set_error("bb_model_build: L^-1 has no finite non-zero entries (max |.| = %g)", amax);
+    return BB_ERR_NOT_PD;
+  }
+  // power-of-two scale so that max |scale * Linv| lies in [2^13, 2^14): well inside fp16 range
+  int e;
+  frexp(amax, &e);  // amax = f * 2^e, f in [0.5,1)
+  double scale = ldexp(1.0, 14 - e);
+  k_build_rimg<<<L.n_tiles, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, B + L.rimg,
+                                              (float*)(B + L.linv32), L.n_pad);
+  BB_LAUNCH_CHECK();
+
+  memset(out, 0, sizeof(*out));
+  out->abi_version = BB_ABI_VERSION;
+  out->n = n;
+  out->n_pad = L.n_pad;
+  out->d = d;
+  out->d_pad = L.d_pad;
+  out->family = desc->family;
+  out->task_col = desc->task_col;
+  out->n_tasks = T;
+  out->n_chunks = L.n_chunks;
+  out->jitter_tries = tries;
+  out->jitter = jitter;
+  out->y_mean = (float)y_mean;
+  out->y_std = (float)y_std;
+  out->prior_scale = (float)prior_scale;
+  out->r_scale = (float)scale;
+  out->d_blob = d_blob;
+  out->blob_bytes = blob_bytes;
+  out->d_cand_scale = (const float*)(B + L.cand_scale);
+  out->d_cand_shift = (const float*)(B + L.cand_shift);
+  out->d_train_m2 = (const float*)(B + L.train_m2);
+  out->d_train_sq = (const float*)(B + L.train_sq);
+  out->d_alpha = (const float*)(B + L.alpha);
+  out->d_train_task = (const int32_t*)(B + L.train_task);
+  out->d_task_covar = (const float*)(B + L.task_covar);
+  out->d_mean_const = (const float*)(B + L.mean_const);
+  out->d_rimg = B + L.rimg;
+  out->d_linv = dLinv;
+  out->d_alpha64 = (const double*)(B + L.alpha64);
+  out->d_xn64 = (const double*)(B + L.xn64);
+  out->d_linv32 = (const float*)(B + L.linv32);
+  BB_CUDA(cudaStreamSynchronize(stream));
+  return BB_OK;
+}
+
+extern "C" int bb_pending_stats(const bb_model* m, const float* d_pend_x, int32_t P,
+                                float* d_pend_beta, float* d_pend_mu, float* d_pend_cov,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  BB_CHECK_ARG(m && d_pend_x && d_pend_beta && d_pend_mu && d_pend_cov,
+               "bb_pending_stats: null argument");
+  BB_CHECK_ARG(m->abi_version == BB_ABI_VERSION, "bb_pending_stats: ABI mismatch");
+  BB_CHECK_ARG(P >= 1 && P <= BB_MAX_PENDING, "bb_pending_stats: n_pending=%d outside [1,%d]", P,
+               BB_MAX_PENDING);
+  BlobLayout L = make_layout(m->n, m->d, m->n_tasks);
+  uint8_t* B = (uint8_t*)m->d_blob;
+  double* pn = (double*)(B + L.pend_norm);  // normalised pending rows (scratch inside the blob)
+  double* w64 = (double*)(B + L.pend_w64);
+  size_t shm = sizeof(double) * (m->d + 2 * m->n);
+  k_pending_w<<<P, 256, shm, stream>>>(d_pend_x, P, m->n, m->n_pad, m->d, m->n_tasks, m->family,
+                                       m->task_col, m->d_xn64, m->d_train_task,
+                                       (const double*)(B + L.tcov64), (const float*)(B + L.cnorm),
+                                       m->d_linv, m->d_alpha64, m->d_mean_const, m->y_mean,
+                                       m->y_std, d_pend_beta, d_pend_mu, pn, w64);
+  BB_LAUNCH_CHECK();
+  k_pending_cov<<<P, 32, 0, stream>>>(pn, w64, P, m->n, m->d, m->n_tasks, m->family, m->task_col,
+                                      (const double*)(B + L.tcov64), m->y_std, d_pend_cov);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}

@@ -1,0 +1,224 @@
+/*
+ * baybe_b200.h -- C ABI of libbaybe_b200.so: the B200-native (sm_100a) replacement for the
+ * recommend-time hot path of emdgroup/baybe (GP posterior over a full discrete candidate set
+ * + acquisition scoring + arg-max / top-k).
+ *
+ * The reference has no FFI for this path: it calls into BoTorch/GPyTorch (Python).  Each entry
+ * point below cites the reference call site whose work it replaces (paths under
+ * /root/reference); INTEGRATION.md shows the ctypes binding a BayBE maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; the library never
+ *     allocates or frees device memory and keeps no global mutable state except a
+ *     thread-local error string.
+ *   - every call takes the caller's CUDA stream (a cudaStream_t passed as void*), enqueues
+ *     its kernels there and returns without synchronising, EXCEPT bb_model_build which
+ *     synchronises the stream once (Cholesky success flag / jitter escalation).
+ *   - return value: BB_OK (0) or a negative bb_status; bb_last_error() gives the message.
+ *     No partial results: on error the output buffers are unspecified.
+ */
+#ifndef BAYBE_B200_H_
+#define BAYBE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+
+typedef enum bb_status {
+  BB_OK = 0,
+  BB_ERR_INVALID = -1,     /* bad argument (shape, enum, null pointer, alignment)      */
+  BB_ERR_UNSUPPORTED = -2, /* valid request outside what this build implements         */
+  BB_ERR_CUDA = -3,        /* a CUDA runtime call or kernel launch failed              */
+  BB_ERR_NOT_PD = -4,      /* K + noise*I not positive definite after jitter escalation */
+  BB_ERR_WORKSPACE = -5    /* caller-provided buffer too small                         */
+} bb_status;
+
+/* Kernel family: baybe/kernels/basic.py:48 (MaternKernel nu), :166 (RBFKernel). */
+typedef enum bb_kernel_family {
+  BB_KERNEL_MATERN12 = 0,
+  BB_KERNEL_MATERN32 = 1,
+  BB_KERNEL_MATERN52 = 2,
+  BB_KERNEL_RBF = 3
+} bb_kernel_family;
+
+/* Candidate-matrix layouts.  COL_MAJOR_F64 is what the reference hands to BoTorch today
+ * (baybe/utils/dataframe.py:68-81 -> float64, strides (1,N)). */
+typedef enum bb_layout {
+  BB_ROW_MAJOR_F32 = 0,
+  BB_COL_MAJOR_F32 = 1,
+  BB_ROW_MAJOR_F64 = 2,
+  BB_COL_MAJOR_F64 = 3
+} bb_layout;
+
+/* Acquisition kinds, named by the reference's abbreviations (baybe/acquisition/acqfs.py). */
+typedef enum bb_acq_kind {
+  BB_ACQ_QLOGEI = 0, /* qLogExpectedImprovement   acqfs.py:220 */
+  BB_ACQ_QEI = 1,    /* qExpectedImprovement      acqfs.py:206 */
+  BB_ACQ_QUCB = 2,   /* qUpperConfidenceBound     acqfs.py:283 */
+  BB_ACQ_QSR = 3,    /* qSimpleRegret             acqfs.py:190 */
+  BB_ACQ_QPI = 4,    /* qProbabilityOfImprovement acqfs.py:256 */
+  BB_ACQ_UCB = 5,    /* UpperConfidenceBound      acqfs.py:265 */
+  BB_ACQ_EI = 6,     /* ExpectedImprovement       acqfs.py:199 */
+  BB_ACQ_LOGEI = 7,  /* LogExpectedImprovement    acqfs.py:213 */
+  BB_ACQ_PI = 8,     /* ProbabilityOfImprovement  acqfs.py:249 */
+  BB_ACQ_PM = 9,     /* PosteriorMean             acqfs.py:162 */
+  BB_ACQ_PSTD = 10   /* PosteriorStandardDeviation acqfs.py:169 */
+} bb_acq_kind;
+
+#define BB_MAX_PENDING 31 /* max pending points in a joint (q>1) evaluation */
+#define BB_MAX_TRAIN 512  /* max training points of this build (reference: exact Cholesky <= 800) */
+
+/*
+ * Description of a fitted GP, i.e. what botorch.models.SingleTaskGP holds after
+ * GaussianProcessSurrogate._fit (baybe/surrogates/gaussian_process/core.py:272-341).
+ * All pointers are HOST pointers to float64 data (these are a few KB).
+ */
+typedef struct bb_model_desc {
+  int32_t n;              /* training points                                              */
+  int32_t d;              /* comp-rep columns (searchspace.comp_rep_columns)               */
+  int32_t family;         /* bb_kernel_family                                              */
+  int32_t task_col;       /* comp-rep column of the TaskParameter, or -1 (core.py:104-111) */
+  int32_t n_tasks;        /* T (1 without a task parameter)                                */
+  int32_t has_outputscale;/* ScaleKernel present (kernels/composite.py:21)                 */
+  double outputscale;     /* s_f^2 (ignored unless has_outputscale)                        */
+  const double* train_x;  /* [n*d] row-major raw comp-rep training inputs                  */
+  const double* train_y;  /* [n]   raw targets                                             */
+  const double* lower;    /* [d]   searchspace.scaling_bounds lower row (core.py:98-102)   */
+  const double* upper;    /* [d]   upper row                                               */
+  const double* lengthscale; /* [d] ARD lengthscale per column; <=0 marks an inactive column
+                                (kernels/base.py:223-240); ignored for task_col            */
+  const double* noise;    /* [T] likelihood noise per task (floored at 1e-4)               */
+  const double* mean_const; /* [T] constant mean per task, standardised units              */
+  const double* task_covar; /* [T*T] evaluated PositiveIndexKernel matrix, or NULL         */
+} bb_model_desc;
+
+/*
+ * Device-resident model caches (what GPyTorch's prediction strategy caches: alpha, the
+ * inverse root R = L^-T, plus our fp16 hi/lo tensor-core image of it).  Filled by
+ * bb_model_build; the pointers point INTO the caller-owned blob.
+ */
+typedef struct bb_model {
+  int32_t abi_version;
+  int32_t n, n_pad, d, d_pad;
+  int32_t family, task_col, n_tasks;
+  int32_t n_chunks;          /* n_pad / 64                                               */
+  int32_t jitter_tries;      /* 0 = plain Cholesky succeeded                             */
+  float y_mean, y_std;       /* Standardize(1) statistics                                */
+  float prior_scale;         /* s_f^2 (1 without ScaleKernel)                            */
+  float r_scale;             /* power of two folded into the fp16 image of L^-1          */
+  double jitter;             /* jitter finally added to the diagonal                     */
+  void* d_blob;              /* base of the caller-owned blob                            */
+  size_t blob_bytes;
+  const float* d_cand_scale; /* [d_pad] a_j = x_j*scale_j + shift_j (normalise, centre, 1/l) */
+  const float* d_cand_shift; /* [d_pad]                                                   */
+  const float* d_train_m2;   /* [n_pad*d_pad] -2 * scaled training rows (0 in padding)    */
+  const float* d_train_sq;   /* [n_pad] squared norms of the scaled training rows         */
+  const float* d_alpha;      /* [n_pad] K^-1 (y~ - c), fp32                               */
+  const int32_t* d_train_task; /* [n_pad]                                                 */
+  const float* d_task_covar; /* [T*T] fp32, prior_scale folded in                         */
+  const float* d_mean_const; /* [T]                                                       */
+  const void* d_rimg;        /* fp16 hi/lo swizzled tiles of L^-1 (tcgen05 B operand)     */
+  const double* d_linv;      /* [n*n] row-major L^-1, float64                             */
+  const double* d_alpha64;   /* [n]                                                       */
+  const double* d_xn64;      /* [n*d] normalised training inputs, float64                 */
+  const float* d_linv32;     /* [n_pad*n_pad] row-major L^-1, fp32 (zero padded)          */
+} bb_model;
+
+/* Acquisition context built by BotorchAcquisitionFunctionBuilder.build
+ * (baybe/acquisition/_builder.py:195-265). */
+typedef struct bb_acq_spec {
+  int32_t kind;     /* bb_acq_kind                                                        */
+  int32_t maximize; /* PSTD sign (acqfs.py:169-177)                                       */
+  float best_f;     /* max_i o(mu(x_i)) over training inputs (_builder.py:256-265)        */
+  float beta;       /* UCB/qUCB (acqfs.py:270,288)                                        */
+  float obj_scale;  /* objective o = obj_scale*y + obj_shift (objectives/single.py:66-91) */
+  float obj_shift;
+  float tau_relu;   /* qLogEI fatplus temperature (botorch default 1e-6)                  */
+  float tau_max;    /* qLogEI fatmax temperature (botorch default 1e-2)                   */
+  float tau_pi;     /* qPI sigmoid temperature (botorch default 1e-3)                     */
+} bb_acq_spec;
+
+/* (value, index) of the best candidate of one shard; idx = -1 when nothing was eligible. */
+typedef struct bb_best {
+  float val;
+  int32_t pad_;
+  int64_t idx;
+} bb_best;
+
+int bb_abi_version(void);
+const char* bb_last_error(void);
+
+/* ---- training-side caches (K8): replaces the lazily cached Cholesky / alpha / inverse root
+ * of gpytorch's DefaultPredictionStrategy reached from core.py:268-269, 331-341. ---------- */
+size_t bb_model_blob_bytes(int32_t n, int32_t d, int32_t n_tasks);
+int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t blob_bytes, bb_model* out,
+                   void* stream);
+
+/* ---- K2: K(X*, X_train), fp32 row-major [N, ldk>=n].  Replaces gpytorch
+ * MaternKernel/RBFKernel/ScaleKernel/ProductKernel.forward built at
+ * baybe/kernels/base.py:173-178 and components/kernel.py:337. ---------------------------- */
+int bb_kernel_matrix(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
+                     float* d_k, int64_t ldk, void* stream);
+
+/* ---- K2-K5: marginal posterior mean / variance of every candidate, original units.
+ * Replaces SingleTaskGP.posterior(X.unsqueeze(-2)) reached from
+ * GaussianProcessSurrogate._posterior (core.py:268-269), Surrogate.posterior_stats
+ * (surrogates/base.py:308-384).  d_cross (nullable): [N, n_pending] posterior covariance with
+ * the pending points, needs d_pend_beta = K^-1 k(X, pending) [n_pending, n_pad] fp32 (from
+ * bb_pending_stats) and d_pend_x [n_pending, d] raw comp-rep rows (fp32 row-major). -------- */
+int bb_posterior(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
+                 float* d_mu, float* d_var, float* d_cross, const float* d_pend_x,
+                 const float* d_pend_beta, int32_t n_pending, void* stream);
+
+/* ---- pending-point statistics for sequential greedy (K9 prologue): for P pending rows
+ * (fp32 row-major raw comp-rep) returns beta = K^-1 k(X,P) [P, n_pad], the posterior mean [P]
+ * and covariance [P,P] in original units (float64 math, fp32 outputs). --------------------- */
+int bb_pending_stats(const bb_model* m, const float* d_pend_x, int32_t n_pending,
+                     float* d_pend_beta, float* d_pend_mu, float* d_pend_cov, void* stream);
+
+/* ---- K6: acquisition value of each candidate as its own q=1 batch from (mu, var).
+ * d_z: [S] shared Sobol-normal base samples (MC kinds; ignored for analytic kinds).
+ * Replaces qLogExpectedImprovement.forward etc. (class picked at acquisition/base.py:162-181). */
+int bb_acq_score(const bb_acq_spec* a, const float* d_mu, const float* d_var, int64_t N,
+                 const float* d_z, int32_t S, float* d_score, void* stream);
+
+/* ---- K9: joint MC acquisition value of [x*; pending] per candidate (sequential greedy,
+ * candidate first -- botorch concatenate_pending_points).  d_z: [S, 1+P] row-major. -------- */
+int bb_acq_score_joint(const bb_acq_spec* a, const float* d_mu, const float* d_var,
+                       const float* d_cross, int64_t N, const float* d_pend_mu,
+                       const float* d_pend_cov, int32_t n_pending, const float* d_z, int32_t S,
+                       float* d_score, void* stream);
+
+/* ---- K2-K7 fused: posterior + q=1 acquisition + running arg-max, K* never leaves the SM.
+ * d_keep (nullable): uint8 [N], 0 = not eligible (already recommended / excluded).
+ * d_score (nullable): per-candidate scores.  d_best_key: int64 packed (score, lowest index)
+ * key, must be initialised with bb_best_init; combine shards with max(), decode with
+ * bb_best_decode.  Replaces one round of botorch.optim.optimize_acqf_discrete
+ * (baybe/recommenders/pure/bayesian/botorch/discrete.py:124-126). ------------------------- */
+int bb_score_fused(const bb_model* m, const bb_acq_spec* a, const void* d_x, int32_t layout,
+                   int64_t N, int64_t ldx, const uint8_t* d_keep, const float* d_z, int32_t S,
+                   float* d_score, int64_t* d_best_key, int64_t index_offset, void* stream);
+
+/* ---- K7: arg-max / top-k over a score vector (ties -> lowest index, as torch.argmax). ---- */
+int bb_best_init(int64_t* d_best_key, void* stream);
+int bb_argmax(const float* d_score, const uint8_t* d_keep, int64_t N, int64_t index_offset,
+              int64_t* d_best_key, void* stream);
+int bb_best_decode(const int64_t* d_best_key, bb_best* d_out, void* stream);
+int bb_topk(const float* d_score, const uint8_t* d_keep, int64_t N, int32_t k, float* d_vals,
+            int64_t* d_idx, uint8_t* d_scratch_mask /* [N] */, int64_t* d_scratch_key, void* stream);
+
+/* ---- test-only diagnostic: plain fp32 SIMT posterior (no tensor cores), used by the GPU
+ * tests to separate tcgen05-path errors from formula errors.  Not called by the product. -- */
+int bb_debug_posterior_simt(const bb_model* m, const void* d_x, int32_t layout, int64_t N,
+                            int64_t ldx, float* d_mu, float* d_var, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYBE_B200_H_ */
