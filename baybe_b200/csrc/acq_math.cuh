@@ -51,12 +51,40 @@ __device__ __forceinline__ void mc_term(float t, float& s0, float& s1) {
 template <int KIND>
 __device__ __forceinline__ void mc_partial_kind(float c0, float c1, const float4* __restrict__ z4,
                                                 int n4, float& s0, float& s1) {
-  for (int i = 0; i < n4; ++i) {
-    const float4 z = z4[i];
-    mc_term<KIND>(fmaf(c1, z.x, c0), s0, s1);
-    mc_term<KIND>(fmaf(c1, z.y, c0), s0, s1);
-    mc_term<KIND>(fmaf(c1, z.z, c0), s0, s1);
-    mc_term<KIND>(fmaf(c1, z.w, c0), s0, s1);
+  if constexpr (KIND == BB_ACQ_QLOGEI) {
+    // fast path for all four samples, one rarely-taken correction branch per group of four
+    float s0b = 0.f, s1b = 0.f;
+#pragma unroll 2
+    for (int i = 0; i < n4; ++i) {
+      const float4 z = z4[i];
+      const float t0 = fmaf(c1, z.x, c0), t1 = fmaf(c1, z.y, c0);
+      const float t2 = fmaf(c1, z.z, c0), t3 = fmaf(c1, z.w, c0);
+      s0 += fmaxf(t0, 0.f);
+      s0b += fmaxf(t1, 0.f);
+      s0 += fmaxf(t2, 0.f);
+      s0b += fmaxf(t3, 0.f);
+      s1 += fast_rcp(fmaf(t0, t0, 1.0f));
+      s1b += fast_rcp(fmaf(t1, t1, 1.0f));
+      s1 += fast_rcp(fmaf(t2, t2, 1.0f));
+      s1b += fast_rcp(fmaf(t3, t3, 1.0f));
+      const float tmin = fminf(fminf(fabsf(t0), fabsf(t1)), fminf(fabsf(t2), fabsf(t3)));
+      if (tmin < 30.f) {
+        if (fabsf(t0) < 30.f) s0 += softplus_tail(fabsf(t0));
+        if (fabsf(t1) < 30.f) s0 += softplus_tail(fabsf(t1));
+        if (fabsf(t2) < 30.f) s0 += softplus_tail(fabsf(t2));
+        if (fabsf(t3) < 30.f) s0 += softplus_tail(fabsf(t3));
+      }
+    }
+    s0 += s0b;
+    s1 += s1b;
+  } else {
+    for (int i = 0; i < n4; ++i) {
+      const float4 z = z4[i];
+      mc_term<KIND>(fmaf(c1, z.x, c0), s0, s1);
+      mc_term<KIND>(fmaf(c1, z.y, c0), s0, s1);
+      mc_term<KIND>(fmaf(c1, z.z, c0), s0, s1);
+      mc_term<KIND>(fmaf(c1, z.w, c0), s0, s1);
+    }
   }
 }
 

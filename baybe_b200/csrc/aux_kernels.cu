@@ -34,6 +34,7 @@ struct AuxParams {
 
 struct AuxSmem {
   AsmSmem sm;
+  StageCtx sc;
   float* extra;
 };
 
@@ -49,14 +50,21 @@ __device__ __forceinline__ AuxSmem aux_carve(uint8_t* base, const AuxParams& p, 
   int32_t* ttask = reinterpret_cast<int32_t*>(cur);
   cur += p.n_pad * 4;
   float4* a_s = reinterpret_cast<float4*>(cur);
-  cur += (size_t)kTileM * p.d_pad * 4;
+  cur += (size_t)kTileM * p.d_pad * 8;  // duplicated candidate values
   float* tcov = reinterpret_cast<float*>(cur);
   cur += 256 * 4;
   int32_t* cand_task = reinterpret_cast<int32_t*>(cur);
   cur += kTileM * 4;
+  float* cscale_s = reinterpret_cast<float*>(cur);
+  cur += ((p.d_pad * 4 + 15) / 16) * 16;
+  float* cshift_s = reinterpret_cast<float*>(cur);
+  cur += ((p.d_pad * 4 + 15) / 16) * 16;
   r.extra = reinterpret_cast<float*>(cur);
-  const float4* src = reinterpret_cast<const float4*>(p.train_m2);
-  for (int e = tid; e < p.n_pad * dq; e += nthreads) xt4[e] = __ldg(src + e);
+  load_train_rows(xt4, p.train_m2, p.n_pad, dq, tid, nthreads);
+  for (int e = tid; e < p.d_pad; e += nthreads) {
+    cscale_s[e] = __ldg(p.cand_scale + e);
+    cshift_s[e] = __ldg(p.cand_shift + e);
+  }
   for (int e = tid; e < p.n_pad; e += nthreads) {
     tsq[e] = __ldg(p.train_sq + e);
     ttask[e] = __ldg(p.train_task + e);
@@ -70,14 +78,24 @@ __device__ __forceinline__ AuxSmem aux_carve(uint8_t* base, const AuxParams& p, 
   r.sm.a_s = a_s;
   r.sm.cand_task = cand_task;
   r.sm.dq = dq;
+  r.sm.np = p.n_pad;
   r.sm.T = p.n_tasks;
   r.sm.scaled = p.scaled != 0;
+  r.sc.x = p.x;
+  r.sc.layout = p.layout;
+  r.sc.N = p.N;
+  r.sc.ldx = p.ldx;
+  r.sc.d = p.d;
+  r.sc.task_col = p.task_col;
+  r.sc.cscale = cscale_s;
+  r.sc.cshift = cshift_s;
+  r.sc.groups = nthreads / kTileM;
   return r;
 }
 
 static size_t aux_base_bytes(const AuxParams& p) {
-  return (size_t)p.n_pad * p.d_pad * 4 + (size_t)p.n_pad * 8 + (size_t)kTileM * p.d_pad * 4 +
-         256 * 4 + kTileM * 4;
+  return (size_t)p.n_pad * p.d_pad * 4 + (size_t)p.n_pad * 8 + (size_t)kTileM * p.d_pad * 8 +
+         256 * 4 + kTileM * 4 + 2 * (size_t)(((p.d_pad * 4 + 15) / 16) * 16);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -93,11 +111,14 @@ __global__ void __launch_bounds__(kAuxThreads, 1) k_kmat(const AuxParams p) {
   __syncthreads();
   const int mp = tid & 63, g = tid >> 6;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.kout) & 15) == 0) && ((p.ldk & 3) == 0);
+  StageRegs regs;
+  if ((int)blockIdx.x < p.num_tiles) stage_prefetch(as.sc, as.sm.dq, (int64_t)blockIdx.x * kTileM, tid, regs);
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const int64_t row0 = (int64_t)tile * kTileM;
-    stage_candidates(p.x, p.layout, p.N, p.ldx, row0, p.d, p.d_pad, p.task_col, p.cand_scale,
-                     p.cand_shift, as.sm, tid, kAuxThreads);
+    stage_commit(as.sc, as.sm.a_s, as.sm.cand_task, as.sm.T, as.sm.dq, row0, tid, regs);
     __syncthreads();
+    if (tile + (int)gridDim.x < p.num_tiles)
+      stage_prefetch(as.sc, as.sm.dq, (int64_t)(tile + gridDim.x) * kTileM, tid, regs);
     const float an0 = cand_sqnorm(as.sm, mp), an1 = cand_sqnorm(as.sm, mp + 64);
     for (int c = 0; c < p.n_chunks; ++c) {
       float k0[8], k1[8];
@@ -143,22 +164,22 @@ __global__ void __launch_bounds__(256, 1) k_cross(const AuxParams p) {
   AuxSmem as = aux_carve(smem_aux, p, tid, 256);
   const int dq = p.d_pad >> 2;
   float* cross_s = as.extra;                               // [128][32]
-  float4* pxt4 = reinterpret_cast<float4*>(cross_s + kTileM * 32);  // [32][dq]
+  float4* pxt4 = reinterpret_cast<float4*>(cross_s + kTileM * 32);  // [dq][32], pair-interleaved
   float* psq = reinterpret_cast<float*>(pxt4 + 32 * dq);   // [32]
   int32_t* ptask = reinterpret_cast<int32_t*>(psq + 32);   // [32]
-  // scaled pending rows, laid out like the training rows (-2 b) + squared norms
+  // scaled pending rows, laid out like the training rows (-2 b, quad-major) + squared norms
   for (int e = tid; e < 32 * p.d_pad; e += 256) {
     int pp = e / p.d_pad, j = e - pp * p.d_pad;
     float b = 0.f;
     if (pp < p.P && j < p.d)
       b = fmaf(__ldg(p.pend_x + (size_t)pp * p.d + j), __ldg(p.cand_scale + j), __ldg(p.cand_shift + j));
-    reinterpret_cast<float*>(pxt4)[pp * p.d_pad + j] = -2.0f * b;
+    reinterpret_cast<float*>(pxt4)[xt_float_index(32, pp, j)] = -2.0f * b;
   }
   __syncthreads();
   if (tid < 32) {
     float s = 0.f;
     for (int j = 0; j < p.d_pad; ++j) {
-      float b = -0.5f * reinterpret_cast<float*>(pxt4)[tid * p.d_pad + j];
+      float b = -0.5f * reinterpret_cast<float*>(pxt4)[xt_float_index(32, tid, j)];
       s = fmaf(b, b, s);
     }
     psq[tid] = s;
@@ -171,8 +192,11 @@ __global__ void __launch_bounds__(256, 1) k_cross(const AuxParams p) {
   const int mp = tid & 63, g = tid >> 6;  // g in 0..3: quarter of the training points
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const int64_t row0 = (int64_t)tile * kTileM;
-    stage_candidates(p.x, p.layout, p.N, p.ldx, row0, p.d, p.d_pad, p.task_col, p.cand_scale,
-                     p.cand_shift, as.sm, tid, 256);
+    {
+      StageRegs regs;
+      stage_prefetch(as.sc, as.sm.dq, row0, tid, regs);
+      stage_commit(as.sc, as.sm.a_s, as.sm.cand_task, as.sm.T, as.sm.dq, row0, tid, regs);
+    }
     for (int e = tid; e < kTileM * 32; e += 256) cross_s[e] = 0.f;
     __syncthreads();
     const float an0 = cand_sqnorm(as.sm, mp), an1 = cand_sqnorm(as.sm, mp + 64);
@@ -202,6 +226,7 @@ __global__ void __launch_bounds__(256, 1) k_cross(const AuxParams p) {
     {
       AsmSmem ps = as.sm;
       ps.xt4 = pxt4;
+      ps.np = 32;
       ps.tsq = psq;
       ps.ttask = ptask;
       float k0[8], k1[8];
@@ -440,8 +465,8 @@ extern "C" int bb_debug_posterior_simt(const bb_model* m, const void* d_x, int32
   AuxParams p;
   int rc = fill_params(p, m, d_x, layout, N, ldx);
   if (rc != BB_OK) return rc;
-  BB_CHECK_ARG(d_mu && d_var, "bb_debug_posterior_simt: output pointers are null");
   if (N == 0) return BB_OK;
+  BB_CHECK_ARG(d_mu && d_var, "bb_debug_posterior_simt: output pointers are null");
   p.mu = d_mu;
   p.var = d_var;
   size_t smem = (size_t)32 * (p.n_pad + 1) * 4 + 32 * p.d_pad * 4 + 32 * 4 + 8 * 32 * 2 * 4;

@@ -61,105 +61,154 @@ struct FusedParams {
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-template <int FAMILY>
-__global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
-  // ---- carve shared memory ----
-  uint8_t* ring_a = base;
-  uint8_t* ring_b = ring_a + (size_t)p.slots_a * kSlotABytes;
-  uint8_t* cur = ring_b + (size_t)p.stages_b * kStageBBytes;
-  const int dq = p.d_pad >> 2;
-  float4* xt4 = reinterpret_cast<float4*>(cur);
-  cur += (size_t)p.n_pad * p.d_pad * 4;
-  float* tsq = reinterpret_cast<float*>(cur);
-  cur += p.n_pad * 4;
-  float* alpha_s = reinterpret_cast<float*>(cur);
-  cur += p.n_pad * 4;
-  int32_t* ttask = reinterpret_cast<int32_t*>(cur);
-  cur += p.n_pad * 4;
-  float4* a_s = reinterpret_cast<float4*>(cur);
-  cur += (size_t)kTileM * p.d_pad * 4;
-  float* z_s = reinterpret_cast<float*>(cur);
-  cur += kMaxSamples * 4;
-  float* mean_part = reinterpret_cast<float*>(cur);  // [8][128]
-  cur += 8 * kTileM * 4;
-  float* var_part = reinterpret_cast<float*>(cur);   // [4][128]
-  cur += 4 * kTileM * 4;
-  float* mc_part = reinterpret_cast<float*>(cur);    // [4][128][2]
-  cur += 4 * kTileM * 2 * 4;
-  float* tcov = reinterpret_cast<float*>(cur);
-  cur += kMaxTasks * kMaxTasks * 4;
-  float* meanc = reinterpret_cast<float*>(cur);
-  cur += kMaxTasks * 4;
-  int32_t* cand_task = reinterpret_cast<int32_t*>(cur);
-  cur += kTileM * 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cur);
-  uint64_t* a_full = bars;                       // [kMaxSlotsA]
-  uint64_t* a_empty = a_full + kMaxSlotsA;       // [kMaxSlotsA]
-  uint64_t* b_full = a_empty + kMaxSlotsA;       // [kMaxStagesB]
-  uint64_t* b_empty = b_full + kMaxStagesB;      // [kMaxStagesB]
-  uint64_t* d_full = b_empty + kMaxStagesB;      // [1]
-  uint64_t* d_empty = d_full + 1;                // [1]
-  cur += 32 * 8;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(cur);
-  float* zstat = reinterpret_cast<float*>(cur + 8);  // mean z, mean |z|
-  __shared__ long long best_red[4];
+// Everything the compute warps keep in shared memory, carved from the dynamic allocation.
+struct FusedSmem {
+  uint8_t *ring_a, *ring_b;
+  float4* xt4;
+  float *tsq, *alpha_s;
+  int32_t* ttask;
+  float4* a_s;
+  float *z_s, *mean_part, *var_part, *mc_part, *tcov, *meanc;
+  int32_t* cand_task;
+  float *cscale_s, *cshift_s;
+  uint64_t *a_full, *a_empty, *b_full, *b_empty, *d_full, *d_empty;
+  uint32_t* tmem_ptr;
+  float* zstat;
+  long long* best_red;
+};
 
+__device__ __forceinline__ FusedSmem carve_fused(uint8_t* base, const FusedParams& p) {
+  FusedSmem s;
+  uint8_t* cur = base;
+  s.ring_a = cur;
+  cur += (size_t)p.slots_a * kSlotABytes;
+  s.ring_b = cur;
+  cur += (size_t)p.stages_b * kStageBBytes;
+  s.xt4 = reinterpret_cast<float4*>(cur);
+  cur += (size_t)p.n_pad * p.d_pad * 4;
+  s.tsq = reinterpret_cast<float*>(cur);
+  cur += p.n_pad * 4;
+  s.alpha_s = reinterpret_cast<float*>(cur);
+  cur += p.n_pad * 4;
+  s.ttask = reinterpret_cast<int32_t*>(cur);
+  cur += p.n_pad * 4;
+  s.a_s = reinterpret_cast<float4*>(cur);
+  cur += (size_t)kTileM * p.d_pad * 8;  // duplicated candidate values
+  s.z_s = reinterpret_cast<float*>(cur);
+  cur += kMaxSamples * 4;
+  s.mean_part = reinterpret_cast<float*>(cur);  // [2][8][128]
+  cur += 2 * 8 * kTileM * 4;
+  s.var_part = reinterpret_cast<float*>(cur);   // [4][128]
+  cur += 4 * kTileM * 4;
+  s.mc_part = reinterpret_cast<float*>(cur);    // [4][128][2]
+  cur += 4 * kTileM * 2 * 4;
+  s.tcov = reinterpret_cast<float*>(cur);
+  cur += kMaxTasks * kMaxTasks * 4;
+  s.meanc = reinterpret_cast<float*>(cur);
+  cur += kMaxTasks * 4;
+  s.cand_task = reinterpret_cast<int32_t*>(cur);  // [2][128]
+  cur += 2 * kTileM * 4;
+  s.cscale_s = reinterpret_cast<float*>(cur);
+  cur += ((p.d_pad * 4 + 15) / 16) * 16;
+  s.cshift_s = reinterpret_cast<float*>(cur);
+  cur += ((p.d_pad * 4 + 15) / 16) * 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cur);
+  s.a_full = bars;                          // [kMaxSlotsA]
+  s.a_empty = s.a_full + kMaxSlotsA;        // [kMaxSlotsA]
+  s.b_full = s.a_empty + kMaxSlotsA;        // [kMaxStagesB]
+  s.b_empty = s.b_full + kMaxStagesB;       // [kMaxStagesB]
+  s.d_full = s.b_empty + kMaxStagesB;       // [2]
+  s.d_empty = s.d_full + 2;                 // [2]
+  cur += 32 * 8;
+  s.best_red = reinterpret_cast<long long*>(cur);  // [4]
+  cur += 32;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(cur);
+  s.zstat = reinterpret_cast<float*>(cur + 8);  // mean z, mean |z|
+  return s;
+}
+
+static size_t fused_smem_bytes(const FusedParams& p) {
+  size_t b = 0;
+  b += (size_t)p.slots_a * kSlotABytes + (size_t)p.stages_b * kStageBBytes;
+  b += (size_t)p.n_pad * p.d_pad * 4 + (size_t)p.n_pad * 12;
+  b += (size_t)kTileM * p.d_pad * 8 + kMaxSamples * 4;
+  b += 2 * 8 * kTileM * 4 + 4 * kTileM * 4 + 4 * kTileM * 2 * 4;
+  b += kMaxTasks * kMaxTasks * 4 + kMaxTasks * 4 + 2 * kTileM * 4;
+  b += 2 * (size_t)(((p.d_pad * 4 + 15) / 16) * 16);
+  b += 32 * 8 + 32 + 32;
+  return b;
+}
+
+// Spin with back-off: used by the two single-lane helper warps so that their polling does not
+// eat issue slots of the compute warps sharing their scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
+
+// LAG = 1: the epilogue of tile t runs after the assembly of tile t+1, so the tensor-core tail of
+// tile t is never waited for; needs two accumulators in TMEM (2 * n_pad <= 512 columns).
+template <int FAMILY, int LAG>
+__global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const FusedSmem s = carve_fused(smem_raw, p);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = p.n_chunks;
+  const int dq = p.d_pad >> 2;
+  if (tid == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();  // swizzled tiles need 1024-B alignment
 
   // ---- one-time setup ----
   if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < p.slots_a; ++i) {
-      mbar_init(&a_full[i], kComputeWarps);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&s.a_full[i], kComputeWarps);
+      mbar_init(&s.a_empty[i], 1);
     }
     for (int i = 0; i < p.stages_b; ++i) {
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&s.b_full[i], 1);
+      mbar_init(&s.b_empty[i], 1);
     }
-    mbar_init(d_full, 1);
-    mbar_init(d_empty, kComputeWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.d_full[i], 1);
+      mbar_init(&s.d_empty[i], kComputeWarps);
+    }
     fence_mbar_init();
   }
   if (warp == kWarpProducer) {
-    tmem_alloc(tmem_ptr, p.tmem_cols);
+    tmem_alloc(s.tmem_ptr, p.tmem_cols);
     tmem_relinquish();
   }
   // model data resident in shared memory for the whole kernel
-  {
-    const float4* src = reinterpret_cast<const float4*>(p.train_m2);
-    for (int e = tid; e < p.n_pad * dq; e += kFusedThreads) xt4[e] = __ldg(src + e);
-    for (int e = tid; e < p.n_pad; e += kFusedThreads) {
-      tsq[e] = __ldg(p.train_sq + e);
-      alpha_s[e] = __ldg(p.alpha + e);
-      ttask[e] = __ldg(p.train_task + e);
-    }
-    for (int e = tid; e < p.n_tasks * p.n_tasks; e += kFusedThreads) tcov[e] = __ldg(p.task_covar + e);
-    for (int e = tid; e < p.n_tasks; e += kFusedThreads) meanc[e] = __ldg(p.mean_const + e);
-    for (int e = tid; e < kTileM; e += kFusedThreads) cand_task[e] = 0;
-    if (p.has_acq && p.z != nullptr)
-      for (int e = tid; e < p.S; e += kFusedThreads) z_s[e] = __ldg(p.z + e);
+  load_train_rows(s.xt4, p.train_m2, p.n_pad, dq, tid, kFusedThreads);
+  for (int e = tid; e < p.d_pad; e += kFusedThreads) {
+    s.cscale_s[e] = __ldg(p.cand_scale + e);
+    s.cshift_s[e] = __ldg(p.cand_shift + e);
   }
+  for (int e = tid; e < p.n_pad; e += kFusedThreads) {
+    s.tsq[e] = __ldg(p.train_sq + e);
+    s.alpha_s[e] = __ldg(p.alpha + e);
+    s.ttask[e] = __ldg(p.train_task + e);
+  }
+  for (int e = tid; e < p.n_tasks * p.n_tasks; e += kFusedThreads) s.tcov[e] = __ldg(p.task_covar + e);
+  for (int e = tid; e < p.n_tasks; e += kFusedThreads) s.meanc[e] = __ldg(p.mean_const + e);
+  for (int e = tid; e < 2 * kTileM; e += kFusedThreads) s.cand_task[e] = 0;
+  if (p.has_acq && p.z != nullptr)
+    for (int e = tid; e < p.S; e += kFusedThreads) s.z_s[e] = __ldg(p.z + e);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = *s.tmem_ptr;
   if (p.has_acq && warp == 0) {
     float sz = 0.f, sa = 0.f;
     for (int e = lane; e < p.S; e += 32) {
-      sz += z_s[e];
-      sa += fabsf(z_s[e]);
+      sz += s.z_s[e];
+      sa += fabsf(s.z_s[e]);
     }
     for (int o = 16; o > 0; o >>= 1) {
       sz += __shfl_xor_sync(0xffffffffu, sz, o);
       sa += __shfl_xor_sync(0xffffffffu, sa, o);
     }
     if (lane == 0) {
-      zstat[0] = sz / (float)p.S;
-      zstat[1] = sa / (float)p.S;
+      s.zstat[0] = sz / (float)p.S;
+      s.zstat[1] = sa / (float)p.S;
     }
   }
 
@@ -168,38 +217,133 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
     // compute warps
     // =====================================================================================
     AsmSmem sm;
-    sm.xt4 = xt4;
-    sm.tsq = tsq;
-    sm.ttask = ttask;
-    sm.tcov = tcov;
-    sm.a_s = a_s;
-    sm.cand_task = cand_task;
+    sm.xt4 = s.xt4;
+    sm.tsq = s.tsq;
+    sm.ttask = s.ttask;
+    sm.tcov = s.tcov;
+    sm.a_s = s.a_s;
+    sm.cand_task = s.cand_task;
     sm.dq = dq;
+    sm.np = p.n_pad;
     sm.T = p.n_tasks;
     sm.scaled = p.scaled != 0;
+    StageCtx sc;
+    sc.x = p.x;
+    sc.layout = p.layout;
+    sc.N = p.N;
+    sc.ldx = p.ldx;
+    sc.d = p.d;
+    sc.task_col = p.task_col;
+    sc.cscale = s.cscale_s;
+    sc.cshift = s.cshift_s;
+    sc.groups = kComputeThreads / kTileM;
+    StageRegs regs;
+    if ((int)blockIdx.x < p.num_tiles) stage_prefetch(sc, dq, (int64_t)blockIdx.x * kTileM, tid, regs);
     const int mp = tid & 63, g = tid >> 6;       // assembly: candidates (mp, mp+64), i-octet g
     const int row_e = tid & 127, sg = tid >> 7;  // epilogue: TMEM lane row_e, column/sample group
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     long long best = kEmptyKey;
-    uint32_t q = 0;  // running A-chunk counter (ring position)
+
+    // ---- epilogue of tile number e_it (rows e_row0..): |V|^2 from TMEM, moments, acquisition ----
+    auto epilogue = [&](int e_it, int64_t e_row0) {
+      const int buf = LAG ? (e_it & 1) : 0;
+      const int use = LAG ? (e_it >> 1) : e_it;
+      mbar_wait(&s.d_full[buf], (uint32_t)(use & 1));
+      tc_fence_after();
+      {
+        float ss = 0.f;
+        const uint32_t col0 = tmem_base + lane_base + (uint32_t)(buf * p.n_pad);
+        for (int cb = sg; cb * 32 < p.n_pad; cb += 4) {
+          float v[32];
+          tmem_ld32(col0 + (uint32_t)(cb * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) ss = fmaf(v[e], v[e], ss);
+        }
+        s.var_part[sg * kTileM + row_e] = ss;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.d_empty[buf]);
+      bar_compute();
+      // moments in original units
+      const float* mpart = s.mean_part + buf * 8 * kTileM;
+      const int ct = s.cand_task[buf * kTileM + row_e];
+      float msum = s.meanc[ct];
+#pragma unroll
+      for (int gg = 0; gg < 8; ++gg) msum += mpart[gg * kTileM + row_e];
+      const float vsum = (s.var_part[row_e] + s.var_part[kTileM + row_e]) +
+                         (s.var_part[2 * kTileM + row_e] + s.var_part[3 * kTileM + row_e]);
+      const float kss = p.scaled ? s.tcov[ct * p.n_tasks + ct] : 1.0f;
+      const float var_t = fmaxf(kss - vsum * p.inv_r_scale2, 1e-10f);
+      const float mu = fmaf(p.y_std, msum, p.y_mean);
+      const float var = p.y_std * p.y_std * var_t;
+      const int64_t row = e_row0 + row_e;
+      const bool in_range = row < p.N;
+      if (sg == 0 && in_range) {
+        if (p.mu) p.mu[row] = mu;
+        if (p.var) p.var[row] = var;
+      }
+      if (p.has_acq) {
+        const bool is_mc = p.acq.kind <= BB_ACQ_QPI;
+        if (is_mc) {
+          float s0, s1;
+          mc_partial(p.acq, mu, var, s.z_s, p.S, sg, 4, s0, s1);
+          *reinterpret_cast<float2*>(s.mc_part + (sg * kTileM + row_e) * 2) = make_float2(s0, s1);
+        }
+        bar_compute();
+        if (sg == 0) {
+          float score;
+          if (is_mc) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) {
+              const float2 pr = *reinterpret_cast<const float2*>(s.mc_part + (gg * kTileM + row_e) * 2);
+              s0 += pr.x;
+              s1 += pr.y;
+            }
+            score = mc_finalize(p.acq, mu, var, s0, s1, p.S, s.zstat[0], s.zstat[1]);
+          } else {
+            score = analytic_value(p.acq, mu, var);
+          }
+          if (in_range) {
+            if (p.score) p.score[row] = score;
+            const bool ok = (p.keep == nullptr || p.keep[row] != 0) && !(score != score);
+            if (ok) {
+              const long long key = pack_key(score, (uint32_t)(row + p.index_offset));
+              best = key > best ? key : best;
+            }
+          }
+        }
+      } else {
+        bar_compute();  // partial buffers are rewritten by the next epilogue
+      }
+    };
+
+    uint32_t slot = 0, ph = 0;  // A-ring position and phase
     int it = 0;
+    int64_t prev_row0 = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = LAG ? (it & 1) : 0;
       const int64_t row0 = (int64_t)tile * kTileM;
-      stage_candidates(p.x, p.layout, p.N, p.ldx, row0, p.d, p.d_pad, p.task_col, p.cand_scale,
-                       p.cand_shift, sm, tid, kComputeThreads);
+      sm.cand_task = s.cand_task + buf * kTileM;
+      stage_commit(sc, s.a_s, sm.cand_task, p.n_tasks, dq, row0, tid, regs);
       bar_compute();
       const float an0 = cand_sqnorm(sm, mp), an1 = cand_sqnorm(sm, mp + 64);
       float mean0 = 0.f, mean1 = 0.f;
-      for (int c = 0; c < C; ++c, ++q) {
-        const uint32_t slot = q % (uint32_t)p.slots_a;
-        const uint32_t ph = (q / (uint32_t)p.slots_a) & 1u;
+      for (int c = 0; c < C; ++c) {
         float k0[8], k1[8];
         const int i0 = c * kChunk + g * 8;
         assemble_2x8<FAMILY>(sm, mp, mp + 64, an0, an1, i0, k0, k1);
+        {
+          const float4 al0 = *reinterpret_cast<const float4*>(s.alpha_s + i0);
+          const float4 al1 = *reinterpret_cast<const float4*>(s.alpha_s + i0 + 4);
+          const float al[8] = {al0.x, al0.y, al0.z, al0.w, al1.x, al1.y, al1.z, al1.w};
 #pragma unroll
-        for (int ii = 0; ii < 8; ++ii) {
-          const float al = alpha_s[i0 + ii];
-          mean0 = fmaf(k0[ii], al, mean0);
-          mean1 = fmaf(k1[ii], al, mean1);
+          for (int ii = 0; ii < 8; ++ii) {
+            mean0 = fmaf(k0[ii], al[ii], mean0);
+            mean1 = fmaf(k1[ii], al[ii], mean1);
+          }
         }
         uint4 h0, l0, h1, l1;
         split_pair(k0[0], k0[1], h0.x, l0.x);
@@ -210,8 +354,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
         split_pair(k1[2], k1[3], h1.y, l1.y);
         split_pair(k1[4], k1[5], h1.z, l1.z);
         split_pair(k1[6], k1[7], h1.w, l1.w);
-        mbar_wait(&a_empty[slot], ph ^ 1u);  // MMAs that read this slot last time are done
-        uint8_t* sa = ring_a + (size_t)slot * kSlotABytes;
+        mbar_wait(&s.a_empty[slot], ph ^ 1u);  // MMAs that read this slot last time are done
+        uint8_t* sa = s.ring_a + (size_t)slot * kSlotABytes;
         const uint32_t o0 = sw128_offset((uint32_t)mp, (uint32_t)g);
         const uint32_t o1 = sw128_offset((uint32_t)(mp + 64), (uint32_t)g);
         *reinterpret_cast<uint4*>(sa + o0) = h0;
@@ -220,96 +364,40 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
         *reinterpret_cast<uint4*>(sa + 16384 + o1) = l1;
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[slot]);
-      }
-      mean_part[g * kTileM + mp] = mean0;
-      mean_part[g * kTileM + mp + 64] = mean1;
-
-      // ---- epilogue: |V|^2 per candidate from TMEM ----
-      mbar_wait(d_full, (uint32_t)(it & 1));
-      tc_fence_after();
-      {
-        float ss = 0.f;
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        for (int cb = sg; cb * 32 < p.n_pad; cb += 4) {
-          float v[32];
-          tmem_ld32(tmem_base + lane_base + (uint32_t)(cb * 32), v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) ss = fmaf(v[e], v[e], ss);
+        if (lane == 0) mbar_arrive(&s.a_full[slot]);
+        if (++slot == (uint32_t)p.slots_a) {
+          slot = 0;
+          ph ^= 1u;
         }
-        var_part[sg * kTileM + row_e] = ss;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d_empty);
-      bar_compute();
-
-      // ---- moments in original units ----
-      const int ct = cand_task[row_e];
-      float msum = meanc[ct];
-#pragma unroll
-      for (int gg = 0; gg < 8; ++gg) msum += mean_part[gg * kTileM + row_e];
-      const float vsum = (var_part[row_e] + var_part[kTileM + row_e]) +
-                         (var_part[2 * kTileM + row_e] + var_part[3 * kTileM + row_e]);
-      const float kss = p.scaled ? tcov[ct * p.n_tasks + ct] : 1.0f;
-      float var_t = fmaxf(kss - vsum * p.inv_r_scale2, 1e-10f);
-      const float mu = fmaf(p.y_std, msum, p.y_mean);
-      const float var = p.y_std * p.y_std * var_t;
-      const int64_t row = row0 + row_e;
-      const bool in_range = row < p.N;
-      if (sg == 0 && in_range) {
-        if (p.mu) p.mu[row] = mu;
-        if (p.var) p.var[row] = var;
-      }
-      if (p.has_acq) {
-        float score;
-        const bool is_mc = p.acq.kind <= BB_ACQ_QPI;
-        if (is_mc) {
-          float s0, s1;
-          mc_partial(p.acq, mu, var, z_s, p.S, sg, 4, s0, s1);
-          mc_part[(sg * kTileM + row_e) * 2] = s0;
-          mc_part[(sg * kTileM + row_e) * 2 + 1] = s1;
-        }
-        bar_compute();
-        if (sg == 0) {
-          if (is_mc) {
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int gg = 0; gg < 4; ++gg) {
-              s0 += mc_part[(gg * kTileM + row_e) * 2];
-              s1 += mc_part[(gg * kTileM + row_e) * 2 + 1];
-            }
-            score = mc_finalize(p.acq, mu, var, s0, s1, p.S, zstat[0], zstat[1]);
-          } else {
-            score = analytic_value(p.acq, mu, var);
-          }
-          if (in_range) {
-            if (p.score) p.score[row] = score;
-            const bool ok = (p.keep == nullptr || p.keep[row] != 0) && !(score != score);
-            if (ok) {
-              long long key = pack_key(score, (uint32_t)(row + p.index_offset));
-              best = key > best ? key : best;
-            }
-          }
-        }
+      float* mpart = s.mean_part + buf * 8 * kTileM;
+      mpart[g * kTileM + mp] = mean0;
+      mpart[g * kTileM + mp + 64] = mean1;
+      // global loads of the next tile fly while an epilogue and its MC run
+      if (tile + (int)gridDim.x < p.num_tiles)
+        stage_prefetch(sc, dq, (int64_t)(tile + gridDim.x) * kTileM, tid, regs);
+      if (LAG) {
+        if (it > 0) epilogue(it - 1, prev_row0);
       } else {
-        bar_compute();  // a_s / partial buffers are rewritten by the next tile
+        epilogue(it, row0);
       }
+      prev_row0 = row0;
     }
+    if (LAG && it > 0) epilogue(it - 1, prev_row0);
+
     // ---- CTA-level arg-max ----
     if (p.best_key != nullptr && p.has_acq) {
       if (sg == 0) {
         for (int o = 16; o > 0; o >>= 1) {
-          long long other = __shfl_xor_sync(0xffffffffu, best, o);
+          const long long other = __shfl_xor_sync(0xffffffffu, best, o);
           best = other > best ? other : best;
         }
-        if (lane == 0) best_red[warp] = best;
+        if (lane == 0) s.best_red[warp] = best;
       }
       bar_compute();
       if (tid == 0) {
-        long long b = best_red[0];
-        for (int w = 1; w < 4; ++w) b = best_red[w] > b ? best_red[w] : b;
+        long long b = s.best_red[0];
+        for (int w = 1; w < 4; ++w) b = s.best_red[w] > b ? s.best_red[w] : b;
         if (b != kEmptyKey) atomicMax(p.best_key, b);
       }
     }
@@ -318,16 +406,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
     // producer: stream the fp16 image of L^-1 (B operand) through the TMA engine
     // =====================================================================================
     if (lane == 0) {
-      uint32_t qb = 0;
+      uint32_t st = 0, ph = 0;
       const int n_tiles_b = C * (C + 1) / 2;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int tb = 0; tb < n_tiles_b; ++tb, ++qb) {
-          const uint32_t st = qb % (uint32_t)p.stages_b;
-          const uint32_t ph = (qb / (uint32_t)p.stages_b) & 1u;
-          mbar_wait(&b_empty[st], ph ^ 1u);
-          mbar_expect_tx(&b_full[st], kStageBBytes);
-          bulk_g2s(ring_b + (size_t)st * kStageBBytes, p.rimg + (size_t)tb * kStageBBytes,
-                   kStageBBytes, &b_full[st]);
+        for (int tb = 0; tb < n_tiles_b; ++tb) {
+          mbar_wait_relaxed(&s.b_empty[st], ph ^ 1u);
+          mbar_expect_tx(&s.b_full[st], kStageBBytes);
+          bulk_g2s(s.ring_b + (size_t)st * kStageBBytes, p.rimg + (size_t)tb * kStageBBytes,
+                   kStageBBytes, &s.b_full[st]);
+          if (++st == (uint32_t)p.stages_b) {
+            st = 0;
+            ph ^= 1u;
+          }
         }
       }
     }
@@ -337,26 +427,28 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
     // =====================================================================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kTileM, kChunk);
-      uint32_t qa = 0, qb = 0;
+      uint32_t slot = 0, pha = 0, st = 0, phb = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(d_empty, (uint32_t)((it & 1) ^ 1));  // epilogue of the previous tile drained TMEM
+        const int buf = LAG ? (it & 1) : 0;
+        const int use = LAG ? (it >> 1) : it;
+        // the epilogue that last read this accumulator has drained it
+        mbar_wait_relaxed(&s.d_empty[buf], (uint32_t)((use & 1) ^ 1));
         tc_fence_after();
-        for (int c = 0; c < C; ++c, ++qa) {
-          const uint32_t slot = qa % (uint32_t)p.slots_a;
-          mbar_wait(&a_full[slot], (qa / (uint32_t)p.slots_a) & 1u);
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * p.n_pad);
+        for (int c = 0; c < C; ++c) {
+          mbar_wait_relaxed(&s.a_full[slot], pha);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(ring_a + (size_t)slot * kSlotABytes);
+          const uint32_t a_addr = smem_u32(s.ring_a + (size_t)slot * kSlotABytes);
           const uint64_t a_hi = make_sw128_desc(a_addr);
           const uint64_t a_lo = make_sw128_desc(a_addr + 16384);
-          for (int s = c; s < C; ++s, ++qb) {
-            const uint32_t st = qb % (uint32_t)p.stages_b;
-            mbar_wait(&b_full[st], (qb / (uint32_t)p.stages_b) & 1u);
+          for (int sb = c; sb < C; ++sb) {
+            mbar_wait_relaxed(&s.b_full[st], phb);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(ring_b + (size_t)st * kStageBBytes);
+            const uint32_t b_addr = smem_u32(s.ring_b + (size_t)st * kStageBBytes);
             const uint64_t b_hi = make_sw128_desc(b_addr);
             const uint64_t b_lo = make_sw128_desc(b_addr + 8192);
-            const uint32_t d_addr = tmem_base + (uint32_t)(s * kChunk);
+            const uint32_t d_addr = d_base + (uint32_t)(sb * kChunk);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t ko = (uint64_t)(kk * 2);  // 16 fp16 = 32 bytes = 2 x 16-byte units
@@ -364,11 +456,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
               umma_f16(d_addr, a_hi + ko, b_lo + ko, idesc, 1u);
               umma_f16(d_addr, a_lo + ko, b_hi + ko, idesc, 1u);
             }
-            umma_commit(&b_empty[st]);
+            umma_commit(&s.b_empty[st]);
+            if (++st == (uint32_t)p.stages_b) {
+              st = 0;
+              phb ^= 1u;
+            }
           }
-          umma_commit(&a_empty[slot]);
+          umma_commit(&s.a_empty[slot]);
+          if (++slot == (uint32_t)p.slots_a) {
+            slot = 0;
+            pha ^= 1u;
+          }
         }
-        umma_commit(d_full);
+        umma_commit(&s.d_full[buf]);
       }
     }
   }
@@ -379,24 +479,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
   if (warp == kWarpProducer) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-static size_t fused_smem_bytes(const FusedParams& p) {
-  size_t b = 1024;  // alignment slack
-  b += (size_t)p.slots_a * kSlotABytes + (size_t)p.stages_b * kStageBBytes;
-  b += (size_t)p.n_pad * p.d_pad * 4 + (size_t)p.n_pad * 12;
-  b += (size_t)kTileM * p.d_pad * 4 + kMaxSamples * 4;
-  b += 8 * kTileM * 4 + 4 * kTileM * 4 + 4 * kTileM * 2 * 4;
-  b += kMaxTasks * kMaxTasks * 4 + kMaxTasks * 4 + kTileM * 4;
-  b += 32 * 8 + 64;
-  return b;
+template <int FAMILY, int LAG>
+static int launch_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
+  BB_CUDA(cudaFuncSetAttribute(k_fused<FAMILY, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  k_fused<FAMILY, LAG><<<grid, kFusedThreads, smem, stream>>>(p);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
 }
 
 template <int FAMILY>
-static int launch_family(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
-  BB_CUDA(cudaFuncSetAttribute(k_fused<FAMILY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
-  k_fused<FAMILY><<<grid, kFusedThreads, smem, stream>>>(p);
-  BB_LAUNCH_CHECK();
-  return BB_OK;
+static int launch_family(FusedParams& p, int lag, int grid, size_t smem, cudaStream_t stream) {
+  return lag ? launch_one<FAMILY, 1>(p, grid, smem, stream) : launch_one<FAMILY, 0>(p, grid, smem, stream);
 }
 
 int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
@@ -459,9 +553,10 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   p.keep = d_keep;
   p.best_key = reinterpret_cast<long long*>(d_best_key);
   p.index_offset = index_offset;
+  BB_CHECK_SUPPORTED(p.n_pad <= 512, "n_pad=%d exceeds the 512 TMEM columns", p.n_pad);
+  const int lag = (2 * p.n_pad <= 512) ? 1 : 0;  // two accumulators fit: defer the epilogue
   uint32_t cols = 32;
-  while ((int)cols < p.n_pad) cols <<= 1;
-  BB_CHECK_SUPPORTED(cols <= 512, "n_pad=%d exceeds the 512 TMEM columns", p.n_pad);
+  while ((int)cols < (lag ? 2 : 1) * p.n_pad) cols <<= 1;
   p.tmem_cols = cols;
 
   int dev = 0, max_smem = 0, sms = 0;
@@ -486,10 +581,10 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
                      max_smem);
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   switch (m->family) {
-    case BB_KERNEL_MATERN12: return launch_family<BB_KERNEL_MATERN12>(p, grid, smem, stream);
-    case BB_KERNEL_MATERN32: return launch_family<BB_KERNEL_MATERN32>(p, grid, smem, stream);
-    case BB_KERNEL_MATERN52: return launch_family<BB_KERNEL_MATERN52>(p, grid, smem, stream);
-    default: return launch_family<BB_KERNEL_RBF>(p, grid, smem, stream);
+    case BB_KERNEL_MATERN12: return launch_family<BB_KERNEL_MATERN12>(p, lag, grid, smem, stream);
+    case BB_KERNEL_MATERN32: return launch_family<BB_KERNEL_MATERN32>(p, lag, grid, smem, stream);
+    case BB_KERNEL_MATERN52: return launch_family<BB_KERNEL_MATERN52>(p, lag, grid, smem, stream);
+    default: return launch_family<BB_KERNEL_RBF>(p, lag, grid, smem, stream);
   }
 }
 
@@ -516,7 +611,7 @@ extern "C" int bb_posterior(const bb_model* m, const void* d_x, int32_t layout, 
                             int64_t ldx, float* d_mu, float* d_var, float* d_cross,
                             const float* d_pend_x, const float* d_pend_beta, int32_t n_pending,
                             void* stream) {
-  BB_CHECK_ARG(d_mu != nullptr && d_var != nullptr, "bb_posterior: output pointers are null");
+  BB_CHECK_ARG(N == 0 || (d_mu != nullptr && d_var != nullptr), "bb_posterior: output pointers are null");
   int rc = launch_fused(m, d_x, layout, N, ldx, nullptr, nullptr, 0, nullptr, d_mu, d_var, nullptr,
                         nullptr, 0, (cudaStream_t)stream);
   if (rc != BB_OK) return rc;

@@ -21,7 +21,7 @@ import torch
 
 from baybe_b200 import _lib
 
-__all__ = ["AcqConfig", "DeviceGP", "sobol_normal_samples", "DEFAULT_MC_SAMPLES"]
+__all__ = ["AcqConfig", "DeviceGP", "sobol_normal_samples", "unpack_best", "decode_best", "DEFAULT_MC_SAMPLES"]
 
 DEFAULT_MC_SAMPLES = 512  # botorch MC acquisition default sample shape
 _registry: dict[int, "DeviceGP"] = {}
@@ -259,6 +259,20 @@ def decode_best(key: torch.Tensor) -> tuple[float, int]:
     val = float(out[0].item())
     idx = int(out[1].item())
     return val, idx
+
+
+def unpack_best(key: int) -> tuple[float, int]:
+    """Host-side decode of a packed (score, lowest index) key -- same bit layout as
+    ``pack_key`` in csrc/common.cuh; (-inf, -1) for the empty key."""
+    import struct
+
+    if key == -(1 << 63):
+        return float("-inf"), -1
+    hi = (key >> 32) & 0xFFFFFFFF
+    s = hi - (1 << 32) if hi & 0x80000000 else hi
+    s ^= (s >> 31) & 0x7FFFFFFF
+    val = struct.unpack("<f", struct.pack("<i", s))[0]
+    return val, 0xFFFFFFFF - (key & 0xFFFFFFFF)
 
 
 # ------------------------------------------------------------------------------------------
