@@ -1,0 +1,218 @@
+"""``B200Recommender``: the drop-in for ``BotorchRecommender`` on purely discrete search spaces.
+
+Mirrors the reference's call chain
+  BayesianRecommender.recommend            /root/reference/baybe/recommenders/pure/bayesian/base.py:129-197
+  PureRecommender._recommend_with_discrete_parts          recommenders/pure/base.py:248-307
+  recommend_discrete_without_subsets       recommenders/pure/bayesian/botorch/discrete.py:78-142
+with ``botorch.optim.optimize_acqf_discrete`` (sequential greedy, ``unique=True``, first maximum
+wins) replaced by the CUDA engine: round 1 is one fused pass (posterior + acquisition + arg-max),
+later rounds score [candidate; pending] jointly.  The candidate matrix is cached on the device per
+discrete subspace and recommendations come back as row *positions*, so neither
+the per-call re-encoding (discrete.py:123) nor the float-equality merge (discrete.py:133-140) of
+the reference is needed.
+
+Multi-GPU: when ``torch.distributed`` is initialised with the NCCL backend, every rank scores a
+contiguous row shard and one 8-byte MAX all-reduce of the packed (score, lowest index) key
+selects the global winner per greedy round.
+"""
+
+from __future__ import annotations
+
+import weakref
+from typing import ClassVar
+
+import numpy as np
+import pandas as pd
+import torch
+from attrs import define, field
+from attrs.converters import optional
+
+from baybe_b200.acquisition import (AcquisitionFunction, IncompatibleAcquisitionFunctionError,
+                                    convert_acqf, qLogExpectedImprovement)
+from baybe_b200.engine import DEFAULT_MC_SAMPLES, AcqConfig, DeviceGP, sobol_normal_samples, unpack_best
+from baybe_b200.surrogates import GaussianProcessSurrogate
+
+__all__ = ["B200Recommender", "NotEnoughPointsLeftError", "shard_bounds", "greedy_select"]
+
+
+class NotEnoughPointsLeftError(Exception):
+    """Same name/meaning as baybe.exceptions.NotEnoughPointsLeftError (pure/base.py:294-298)."""
+
+
+def _draw_sampler_seed() -> int:
+    """botorch's MC samplers draw their seed from torch's global RNG at construction
+    (SURVEY.md A.6), which is how ``Settings(random_seed=...)`` makes recommendations
+    reproducible (baybe/utils/random.py:124-130)."""
+    return int(torch.randint(0, 1_000_000, (1,)).item())
+
+
+def shard_bounds(n_rows: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous row block [lo, hi) of shard `rank` out of `world` (ceil-sized blocks)."""
+    per = -(-n_rows // world)
+    lo = min(rank * per, n_rows)
+    return lo, min(lo + per, n_rows)
+
+
+def _dist_info() -> tuple[int, int]:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _allreduce_key(key: torch.Tensor) -> torch.Tensor:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(key, op=dist.ReduceOp.MAX)
+    return key
+
+
+def _scores_for(gp: DeviceGP, cfg: AcqConfig, x: torch.Tensor, pending: np.ndarray | None, seed: int,
+                n_samples: int) -> torch.Tensor:
+    """Per-candidate acquisition values (q=1 batches, optionally joint with pending points)."""
+    if pending is not None and len(pending) > 0:
+        z = sobol_normal_samples(n_samples, 1 + len(pending), seed)
+        return gp.score_joint(cfg, x, pending, z)
+    z = sobol_normal_samples(n_samples, 1, seed)[:, 0] if cfg.is_mc else None
+    scores, _ = gp.score(cfg, x, z)
+    return scores
+
+
+def greedy_select(gp: DeviceGP, cfg: AcqConfig, x_shard: torch.Tensor, x_all_host: np.ndarray, q: int,
+                  base_pending: np.ndarray | None, seed: int, n_samples: int = DEFAULT_MC_SAMPLES,
+                  offset: int = 0, keep_init: torch.Tensor | None = None) -> tuple[list[int], list[float]]:
+    """Sequential greedy selection of q rows (global positions) -- ``optimize_acqf_discrete`` with
+    ``unique=True``.  `x_shard` holds this rank's rows [offset, offset+len) on the device;
+    `x_all_host` is the full comp-rep matrix (every rank has it) used to read winners' features."""
+    chosen: list[int] = []
+    values: list[float] = []
+    keep = (torch.ones(x_shard.shape[0], dtype=torch.uint8, device=x_shard.device)
+            if keep_init is None else keep_init.to(device=x_shard.device, dtype=torch.uint8).clone())
+    d = x_all_host.shape[1]
+    base = np.zeros((0, d)) if base_pending is None else np.asarray(base_pending, dtype=np.float64).reshape(-1, d)
+    for _ in range(q):
+        pend = np.concatenate([base, x_all_host[chosen].reshape(-1, d)], axis=0)
+        if len(pend) == 0:
+            z = sobol_normal_samples(n_samples, 1, seed)[:, 0] if cfg.is_mc else None
+            _, key = gp.score(cfg, x_shard, z, keep=keep, index_offset=offset, want_scores=False)
+        else:
+            z = sobol_normal_samples(n_samples, 1 + len(pend), seed)
+            scores = gp.score_joint(cfg, x_shard, pend, z)
+            key = torch.ops.baybe_b200.argmax(scores, keep, offset)
+        key = _allreduce_key(key)
+        val, idx = unpack_best(int(key.item()))
+        if idx < 0:
+            raise NotEnoughPointsLeftError("no eligible candidate left to recommend")
+        chosen.append(idx)
+        values.append(val)
+        if offset <= idx < offset + x_shard.shape[0]:
+            keep[idx - offset] = 0
+    return chosen, values
+
+
+class _DeviceCache:
+    """comp-rep matrices resident on the GPU, keyed by the subspace object (weakly)."""
+
+    def __init__(self):
+        self._store: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+    def get(self, subspace, device, lo: int, hi: int) -> tuple[torch.Tensor, np.ndarray]:
+        entry = self._store.get(subspace)
+        comp_df = subspace.comp_rep
+        if entry is None or entry[0] is not comp_df or entry[1] != (str(device), lo, hi):
+            host = np.ascontiguousarray(comp_df.to_numpy(dtype=np.float64))
+            dev = torch.from_numpy(host[lo:hi]).to(device=device, dtype=torch.float32)
+            entry = (comp_df, (str(device), lo, hi), dev, host)
+            try:
+                self._store[subspace] = entry
+            except TypeError:  # unhashable / non-weakrefable subspace: skip caching
+                pass
+        return entry[2], entry[3]
+
+
+_cache = _DeviceCache()
+
+
+@define
+class B200Recommender:
+    """Bayesian recommender for discrete search spaces running on the B200 engine."""
+
+    compatibility: ClassVar[str] = "DISCRETE"
+    supports_discrete_subset_generating_constraints: ClassVar[bool] = False
+
+    surrogate_model: GaussianProcessSurrogate = field(factory=GaussianProcessSurrogate)
+    acquisition_function: AcquisitionFunction | None = field(default=None, converter=optional(convert_acqf))
+    n_mc_samples: int = field(default=DEFAULT_MC_SAMPLES)
+
+    _objective = field(init=False, default=None, eq=False, repr=False)
+    _last_acq_values: list = field(init=False, factory=list, eq=False, repr=False)
+
+    def _get_acquisition_function(self, objective) -> AcquisitionFunction:
+        """Default acquisition function: qLogEI (bayesian/base.py:70-74)."""
+        return qLogExpectedImprovement() if self.acquisition_function is None else self.acquisition_function
+
+    def get_surrogate(self, searchspace, objective, measurements) -> GaussianProcessSurrogate:
+        self.surrogate_model.fit(searchspace, objective, measurements)
+        return self.surrogate_model
+
+    def recommend(self, batch_size: int, searchspace, objective=None, measurements: pd.DataFrame | None = None,
+                  pending_experiments: pd.DataFrame | None = None) -> pd.DataFrame:
+        """Rows of ``searchspace.discrete.exp_rep`` with their original index
+        (RecommenderProtocol, recommenders/base.py:11-48)."""
+        if objective is None:
+            raise NotImplementedError(
+                f"Recommenders of type '{type(self).__name__}' require that an objective is specified.")
+        if measurements is None or measurements.empty:
+            raise NotImplementedError(
+                f"Recommenders of type '{type(self).__name__}' do not support empty training data.")
+        acqf = self._get_acquisition_function(objective)
+        if batch_size > 1 and not acqf.supports_batching:
+            raise IncompatibleAcquisitionFunctionError(
+                f"The '{type(self).__name__}' only works with Monte Carlo acquisition functions "
+                f"for batch sizes > 1.")
+        self._objective = objective
+        surrogate = self.get_surrogate(searchspace, objective, measurements)
+        cfg = acqf.to_engine(surrogate, searchspace, objective, measurements, pending_experiments)
+        subspace = searchspace.discrete
+        candidates_exp, _ = subspace.get_candidates()
+        if len(candidates_exp) < batch_size:
+            raise NotEnoughPointsLeftError(
+                f"Using the current settings, there are fewer than {batch_size} possible data points "
+                f"left to recommend.")
+        idxs = self._recommend_discrete(subspace, candidates_exp, batch_size, cfg, searchspace,
+                                        pending_experiments)
+        return subspace.exp_rep.loc[idxs, :]
+
+    def _recommend_discrete(self, subspace_discrete, candidates_exp: pd.DataFrame, batch_size: int,
+                            cfg: AcqConfig, searchspace, pending_experiments) -> pd.Index:
+        gp = self.surrogate_model.device_gp
+        rank, world = _dist_info()
+        n_rows = len(subspace_discrete.comp_rep)
+        lo, hi = shard_bounds(n_rows, rank, world)
+        x_dev, x_host = _cache.get(subspace_discrete, gp.device, lo, hi)
+        keep_init = None
+        if len(candidates_exp) != n_rows or not candidates_exp.index.equals(subspace_discrete.comp_rep.index):
+            # a filtered candidate set (e.g. FilteredSubspaceDiscrete): mask rows by position
+            pos = subspace_discrete.comp_rep.index.get_indexer(candidates_exp.index)
+            mask = np.zeros(n_rows, dtype=np.uint8)
+            mask[pos[pos >= 0]] = 1
+            keep_init = torch.from_numpy(mask[lo:hi])
+        pend = None
+        if pending_experiments is not None and len(pending_experiments) > 0:
+            pend = searchspace.transform(pending_experiments, allow_extra=True).to_numpy(dtype=np.float64)
+        seed = _draw_sampler_seed()
+        positions, vals = greedy_select(gp, cfg, x_dev, x_host, batch_size, pend, seed,
+                                        self.n_mc_samples, offset=lo, keep_init=keep_init)
+        self._last_acq_values = vals
+        return subspace_discrete.comp_rep.index[np.asarray(positions, dtype=np.int64)]
+
+    def acquisition_values(self, candidates: pd.DataFrame, searchspace, objective, measurements,
+                           pending_experiments: pd.DataFrame | None = None,
+                           acquisition_function: AcquisitionFunction | None = None) -> pd.Series:
+        """Acquisition value of every candidate (bayesian/base.py:199-237)."""
+        surrogate = self.get_surrogate(searchspace, objective, measurements)
+        acqf = acquisition_function or self._get_acquisition_function(objective)
+        return acqf.evaluate(candidates, surrogate, searchspace, objective, measurements,
+                             pending_experiments, jointly=False)
