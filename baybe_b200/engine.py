@@ -21,7 +21,7 @@ import torch
 
 from baybe_b200 import _lib
 
-__all__ = ["AcqConfig", "DeviceGP", "sobol_normal_samples", "unpack_best", "decode_best", "DEFAULT_MC_SAMPLES"]
+__all__ = ["AcqConfig", "DeviceGP", "sobol_normal_samples", "pack_best", "unpack_best", "decode_best", "DEFAULT_MC_SAMPLES"]
 
 DEFAULT_MC_SAMPLES = 512  # botorch MC acquisition default sample shape
 _registry: dict[int, "DeviceGP"] = {}
@@ -259,6 +259,17 @@ def decode_best(key: torch.Tensor) -> tuple[float, int]:
     val = float(out[0].item())
     idx = int(out[1].item())
     return val, idx
+
+
+def pack_best(score: float, idx: int) -> int:
+    """Host-side twin of ``pack_key`` (csrc/common.cuh): signed-int64 order == (score, then lowest
+    index).  Used by the CPU tests of the sharded arg-max protocol."""
+    import struct
+
+    u = struct.unpack("<i", struct.pack("<f", score))[0]
+    s = u ^ ((u >> 31) & 0x7FFFFFFF)
+    v = ((s & 0xFFFFFFFF) << 32) | (0xFFFFFFFF - idx)
+    return v - (1 << 64) if v >= (1 << 63) else v
 
 
 def unpack_best(key: int) -> tuple[float, int]:

@@ -113,22 +113,23 @@ def greedy_select(gp: DeviceGP, cfg: AcqConfig, x_shard: torch.Tensor, x_all_hos
 
 
 class _DeviceCache:
-    """comp-rep matrices resident on the GPU, keyed by the subspace object (weakly)."""
+    """comp-rep matrices resident on the GPU, keyed by the identity of the subspace's cached
+    ``comp_rep`` dataframe (attrs classes with ``eq=True`` are unhashable, dataframes are
+    weak-referenceable); an entry dies with its dataframe."""
 
     def __init__(self):
-        self._store: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+        self._store: dict[int, tuple] = {}
 
     def get(self, subspace, device, lo: int, hi: int) -> tuple[torch.Tensor, np.ndarray]:
-        entry = self._store.get(subspace)
         comp_df = subspace.comp_rep
-        if entry is None or entry[0] is not comp_df or entry[1] != (str(device), lo, hi):
+        key = id(comp_df)
+        entry = self._store.get(key)
+        if entry is None or entry[0]() is not comp_df or entry[1] != (str(device), lo, hi):
             host = np.ascontiguousarray(comp_df.to_numpy(dtype=np.float64))
             dev = torch.from_numpy(host[lo:hi]).to(device=device, dtype=torch.float32)
-            entry = (comp_df, (str(device), lo, hi), dev, host)
-            try:
-                self._store[subspace] = entry
-            except TypeError:  # unhashable / non-weakrefable subspace: skip caching
-                pass
+            ref = weakref.ref(comp_df, lambda _r, k=key: self._store.pop(k, None))
+            entry = (ref, (str(device), lo, hi), dev, host)
+            self._store[key] = entry
         return entry[2], entry[3]
 
 

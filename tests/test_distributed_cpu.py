@@ -1,0 +1,70 @@
+"""world_size-2 gloo test (CPU) of the sharded arg-max protocol used with N>1 GPUs: every rank
+scores a contiguous row shard, packs (score, global index) into one int64 key, a MAX all-reduce
+picks the winner, ties go to the lowest global index; sequential greedy rounds mask the winner on
+its owning rank only.  Scores come from the CPU oracle here -- the protocol is what is tested."""
+from __future__ import annotations
+
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from baybe_b200.engine import pack_best, unpack_best
+from baybe_b200.recommenders import shard_bounds
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, scores: np.ndarray, q: int, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_bounds(len(scores), rank, world)
+    local = scores[lo:hi].copy()
+    keep = np.ones(hi - lo, dtype=bool)
+    chosen = []
+    for _ in range(q):
+        best = -(1 << 63)
+        for i in np.nonzero(keep)[0]:
+            if not np.isnan(local[i]):
+                best = max(best, pack_best(float(local[i]), lo + int(i)))
+        key = torch.tensor([best], dtype=torch.int64)
+        dist.all_reduce(key, op=dist.ReduceOp.MAX)
+        val, idx = unpack_best(int(key.item()))
+        chosen.append(idx)
+        if lo <= idx < hi:
+            keep[idx - lo] = False
+    if rank == 0:
+        out.put(chosen)
+    dist.destroy_process_group()
+
+
+def test_sharded_argmax_matches_single_process_greedy():
+    rng = np.random.default_rng(0)
+    scores = rng.standard_normal(1001).astype(np.float32)
+    scores[[5, 700]] = scores.max() + 1.0  # tie across shards -> lowest global index first
+    scores[17] = np.nan
+    q = 4
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, scores, q, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = out.get()
+    ref = []
+    s = torch.from_numpy(np.nan_to_num(scores, nan=-np.inf)).clone()
+    for _ in range(q):
+        j = int(torch.argmax(s))  # first maximum
+        ref.append(j)
+        s[j] = -float("inf")
+    assert got == ref and got[:2] == [5, 700]
