@@ -49,7 +49,8 @@ class Model(C.Structure):
         ("d_train_sq", C.c_void_p), ("d_alpha", C.c_void_p), ("d_train_task", C.c_void_p),
         ("d_task_covar", C.c_void_p), ("d_mean_const", C.c_void_p), ("d_rimg", C.c_void_p),
         ("d_linv", C.c_void_p), ("d_alpha64", C.c_void_p), ("d_xn64", C.c_void_p),
-        ("d_linv32", C.c_void_p),
+        ("d_linv32", C.c_void_p), ("d_bimg", C.c_void_p),
+        ("dist_scale_a", C.c_float), ("dist_scale_b", C.c_float),
     ]
 
 

@@ -13,53 +13,10 @@
 // (/root/reference/baybe/recommenders/pure/bayesian/botorch/discrete.py:124-126) =
 // acqf(X[chunk].unsqueeze(-2)) -> SingleTaskGP.posterior (gaussian_process/core.py:268-269)
 // -> qLogExpectedImprovement.forward (class chosen at acquisition/base.py:162-181).
-#include "acq_math.cuh"
 #include "assemble.cuh"
-#include "common.cuh"
+#include "fused_common.cuh"
 
 namespace bb {
-
-constexpr int kComputeWarps = 16;
-constexpr int kComputeThreads = kComputeWarps * 32;  // 512
-constexpr int kFusedThreads = kComputeThreads + 64;  // + producer warp + MMA warp
-constexpr int kWarpProducer = 16;
-constexpr int kWarpMma = 17;
-constexpr int kMaxSlotsA = 4;
-constexpr int kMaxStagesB = 8;
-constexpr uint32_t kSlotABytes = 32768;  // [hi 16 KB | lo 16 KB], each 128 rows x 64 fp16, SW128
-constexpr uint32_t kStageBBytes = 16384; // [hi 8 KB | lo 8 KB],  each  64 rows x 64 fp16, SW128
-constexpr int kMaxTasks = 16;
-constexpr int kMaxSamples = 1024;
-
-struct FusedParams {
-  // candidates
-  const void* x;
-  int layout;
-  int64_t N, ldx;
-  int num_tiles;
-  // model
-  const float *cand_scale, *cand_shift, *train_m2, *train_sq, *alpha, *task_covar, *mean_const;
-  const int32_t* train_task;
-  const uint8_t* rimg;
-  int n_pad, d, d_pad, n_chunks, task_col, n_tasks;
-  float y_mean, y_std, prior_scale, inv_r_scale2;
-  int scaled;  // task kernel or output scale present
-  // ring sizes
-  int slots_a, stages_b;
-  uint32_t tmem_cols;
-  // acquisition (has_acq == 0: posterior only)
-  int has_acq;
-  bb_acq_spec acq;
-  const float* z;
-  int S;
-  // outputs (nullable)
-  float *mu, *var, *score;
-  const uint8_t* keep;
-  long long* best_key;
-  int64_t index_offset;
-};
-
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // Everything the compute warps keep in shared memory, carved from the dynamic allocation.
 struct FusedSmem {
@@ -137,12 +94,6 @@ static size_t fused_smem_bytes(const FusedParams& p) {
   b += 2 * (size_t)(((p.d_pad * 4 + 15) / 16) * 16);
   b += 32 * 8 + 32 + 32;
   return b;
-}
-
-// Spin with back-off: used by the two single-lane helper warps so that their polling does not
-// eat issue slots of the compute warps sharing their scheduler.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
 }
 
 // LAG = 1: the epilogue of tile t runs after the assembly of tile t+1, so the tensor-core tail of
@@ -532,6 +483,10 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   p.mean_const = m->d_mean_const;
   p.train_task = m->d_train_task;
   p.rimg = reinterpret_cast<const uint8_t*>(m->d_rimg);
+  p.bimg = reinterpret_cast<const uint8_t*>(m->d_bimg);
+  p.dist_scale_a = m->dist_scale_a;
+  p.inv_dist_scale = 1.0f / (m->dist_scale_a * m->dist_scale_b);
+  p.family = m->family;
   p.n_pad = m->n_pad;
   p.d = m->d;
   p.d_pad = m->d_pad;
@@ -563,6 +518,10 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   BB_CUDA(cudaGetDevice(&dev));
   BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (fused_tc_supported(p, max_smem)) {
+    const int grid_tc = p.num_tiles < sms ? p.num_tiles : sms;
+    return launch_fused_tc(p, grid_tc, stream);
+  }
   // ring sizes: as many as fit, B stages first (they hide L2 latency), then A slots
   p.slots_a = 2;
   p.stages_b = 2;

@@ -28,7 +28,7 @@ const char* last_error() { return g_err; }
 // ------------------------------------------------------------------------------------------
 struct BlobLayout {
   size_t cand_scale, cand_shift, train_m2, train_sq, alpha, train_task, task_covar, mean_const,
-      rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, flags,
+      rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, bimg, flags,
       total;
   int n_pad, d_pad, n_chunks, n_tiles;
 };
@@ -67,6 +67,7 @@ static BlobLayout make_layout(int n, int d, int T) {
   L.cnorm = take(sizeof(float) * 2 * d);
   L.pend_norm = take(sizeof(double) * BB_MAX_PENDING * d);
   L.pend_w64 = take(sizeof(double) * BB_MAX_PENDING * n);
+  L.bimg = take((size_t)L.n_chunks * 24576);
   L.flags = take(64);
   L.total = off;
   return L;
@@ -247,6 +248,28 @@ __global__ void k_build_rimg(const double* __restrict__ Linv, int n, int n_chunk
     int j = s * 64 + r, i = c * 64 + kk;
     double v = (j < n && i < n && i <= j) ? Linv[(size_t)j * n + i] : 0.0;
     linv32[(size_t)j * n_pad + i] = (float)v;
+  }
+}
+
+// fp16 hi/mid/lo image of (scale * -2b) for the tensor-core distance GEMM: per K chunk c one
+// 24 KB block [hi 8 KB | mid 8 KB | lo 8 KB], each [64 training rows][64 dims] fp16, K-major,
+// 128-byte swizzled; dims >= d are zero.  D2[m][i] = sum_j a[m][j] * (-2 b[i][j]).
+__global__ void k_build_bimg(const float* __restrict__ train_m2, int n_pad, int d_pad, float scale,
+                             uint8_t* __restrict__ bimg) {
+  const int c = blockIdx.x;
+  uint8_t* base = bimg + (size_t)c * 24576;
+  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    const int r = e >> 6, j = e & 63;
+    const int i = c * 64 + r;
+    const float v = (j < d_pad && i < n_pad) ? train_m2[(size_t)i * d_pad + j] * scale : 0.f;
+    const __half h = __float2half_rn(v);
+    const float r1 = v - __half2float(h);
+    const __half m = __float2half_rn(r1);
+    const __half l = __float2half_rn(r1 - __half2float(m));
+    const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)(j >> 3)) + (uint32_t)(j & 7) * 2u;
+    *reinterpret_cast<__half*>(base + off) = h;
+    *reinterpret_cast<__half*>(base + 8192 + off) = m;
+    *reinterpret_cast<__half*>(base + 16384 + off) = l;
   }
 }
 
@@ -438,6 +461,17 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
     }
     tsq[i] = (float)sq;
   }
+  // power-of-two scales for the fp16 split images of the distance GEMM (only used for d_pad <= 64)
+  float a_abs_max = 1e-30f, b_abs_max = 1e-30f;
+  for (int j = 0; j < d; ++j) {
+    a_abs_max = fmaxf(a_abs_max, fmaxf(fabsf((float)desc->lower[j] * cscale[j] + cshift[j]),
+                                       fabsf((float)desc->upper[j] * cscale[j] + cshift[j])));
+  }
+  for (size_t e = 0; e < tm2.size(); ++e) b_abs_max = fmaxf(b_abs_max, fabsf(tm2[e]));
+  if (!(a_abs_max > 1e-6f)) a_abs_max = 1.0f;
+  if (!(b_abs_max > 1e-6f)) b_abs_max = 1.0f;
+  const float dist_scale_a = ldexpf(1.0f, (int)floorf(log2f(4000.0f / a_abs_max)));   // 16x head-room
+  const float dist_scale_b = ldexpf(1.0f, (int)floorf(log2f(30000.0f / b_abs_max)));
   // padded training rows: zero kernel contribution is guaranteed by zero rows of L^-1 / alpha
   for (int a = 0; a < T * T; ++a) tcov32[a] = (float)aux[a];
   for (int a = 0; a < T; ++a) mean32[a] = (float)desc->mean_const[a];
@@ -512,6 +546,11 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
   k_build_rimg<<<L.n_tiles, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, B + L.rimg,
                                               (float*)(B + L.linv32), L.n_pad);
   BB_LAUNCH_CHECK();
+  if (L.d_pad <= 64) {
+    k_build_bimg<<<L.n_chunks, 256, 0, stream>>>((const float*)(B + L.train_m2), L.n_pad, L.d_pad,
+                                                 dist_scale_b, B + L.bimg);
+    BB_LAUNCH_CHECK();
+  }
 
   memset(out, 0, sizeof(*out));
   out->abi_version = BB_ABI_VERSION;
@@ -544,6 +583,9 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
   out->d_alpha64 = (const double*)(B + L.alpha64);
   out->d_xn64 = (const double*)(B + L.xn64);
   out->d_linv32 = (const float*)(B + L.linv32);
+  out->d_bimg = B + L.bimg;
+  out->dist_scale_a = dist_scale_a;
+  out->dist_scale_b = dist_scale_b;
   BB_CUDA(cudaStreamSynchronize(stream));
   return BB_OK;
 }

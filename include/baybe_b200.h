@@ -128,6 +128,10 @@ typedef struct bb_model {
   const double* d_alpha64;   /* [n]                                                       */
   const double* d_xn64;      /* [n*d] normalised training inputs, float64                 */
   const float* d_linv32;     /* [n_pad*n_pad] row-major L^-1, fp32 (zero padded)          */
+  const void* d_bimg;        /* fp16 hi/mid/lo swizzled tiles of the (-2 x) scaled training
+                                rows: B operand of the tensor-core distance GEMM            */
+  float dist_scale_a;        /* power-of-two scales folded into the fp16 images of the      */
+  float dist_scale_b;        /* candidate rows (a) and training rows (b)                    */
 } bb_model;
 
 /* Acquisition context built by BotorchAcquisitionFunctionBuilder.build
