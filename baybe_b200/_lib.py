@@ -51,6 +51,7 @@ class Model(C.Structure):
         ("d_linv", C.c_void_p), ("d_alpha64", C.c_void_p), ("d_xn64", C.c_void_p),
         ("d_linv32", C.c_void_p), ("d_bimg", C.c_void_p),
         ("dist_scale_a", C.c_float), ("dist_scale_b", C.c_float),
+        ("dist_k", C.c_int32), ("pad_", C.c_int32), ("d_rimg2", C.c_void_p),
     ]
 
 
@@ -89,6 +90,7 @@ _SIGNATURES = {
     "bb_best_decode": (C.c_int, [_vp, _vp, _vp]),
     "bb_topk": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "bb_debug_posterior_simt": (C.c_int, [C.POINTER(Model), _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
+    "bb_debug_set_trace": (C.c_int, [_vp, _i64]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

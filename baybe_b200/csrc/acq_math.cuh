@@ -105,6 +105,15 @@ __device__ __forceinline__ void mc_partial(const bb_acq_spec& a, float mu, float
   else if (a.kind == BB_ACQ_QPI) mc_partial_kind<BB_ACQ_QPI>(c0, c1, z4, n4, s0, s1);
 }
 
+// Accumulate the samples z4[0..n4) (4 per element) into (s0, s1) for pre-computed coefficients;
+// lets a caller spread one candidate's Monte-Carlo work over several program phases.
+__device__ __forceinline__ void mc_accumulate(int kind, float c0, float c1, const float4* __restrict__ z4,
+                                              int n4, float& s0, float& s1) {
+  if (kind == BB_ACQ_QLOGEI) mc_partial_kind<BB_ACQ_QLOGEI>(c0, c1, z4, n4, s0, s1);
+  else if (kind == BB_ACQ_QEI) mc_partial_kind<BB_ACQ_QEI>(c0, c1, z4, n4, s0, s1);
+  else if (kind == BB_ACQ_QPI) mc_partial_kind<BB_ACQ_QPI>(c0, c1, z4, n4, s0, s1);
+}
+
 __device__ __forceinline__ float mc_finalize(const bb_acq_spec& a, float mu, float var, float s0,
                                              float s1, int S, float z_mean, float zabs_mean) {
   const float sd = sqrtf(var);

@@ -259,6 +259,23 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c
   return r * 128u + ((c16 ^ (r & 7u)) << 4);
 }
 
+// K-major tiles whose rows hold K2 fp16 (K2 = 64 -> 128-byte rows / SWIZZLE_128B, K2 = 32 ->
+// 64-byte rows / SWIZZLE_64B).  8-row groups are contiguous (SBO = 8 * row bytes).
+template <int K2>
+__host__ __device__ __forceinline__ uint32_t swk_offset(uint32_t r, uint32_t c16) {
+  if constexpr (K2 == 64) return r * 128u + ((c16 ^ (r & 7u)) << 4);
+  else return r * 64u + ((c16 ^ ((r >> 1) & 3u)) << 4);  // Swizzle<2,4,3>: bits[5:4] ^= bits[8:7]
+}
+template <int K2>
+__device__ __forceinline__ uint64_t make_swk_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+  d |= (uint64_t)((K2 == 64 ? 1024 : 512) >> 4) << 32;  // stride between 8-row groups
+  d |= (uint64_t)1 << 46;                                // descriptor version 1
+  d |= (uint64_t)(K2 == 64 ? 2 : 4) << 61;               // SWIZZLE_128B : SWIZZLE_64B
+  return d;
+}
+
 // fp16 hi/lo split of a non-negative-or-signed fp32 value: x ~= hi + lo, relative error 2^-22.
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   __half2 h = __floats2half2_rn(x0, x1);

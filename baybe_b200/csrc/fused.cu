@@ -444,6 +444,9 @@ static int launch_family(FusedParams& p, int lag, int grid, size_t smem, cudaStr
   return lag ? launch_one<FAMILY, 1>(p, grid, smem, stream) : launch_one<FAMILY, 0>(p, grid, smem, stream);
 }
 
+static long long* g_trace_buf = nullptr;
+static int g_trace_cap = 0;
+
 int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
                  const bb_acq_spec* acq, const float* d_z, int32_t S, const uint8_t* d_keep,
                  float* d_mu, float* d_var, float* d_score, int64_t* d_best_key,
@@ -487,6 +490,8 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   p.dist_scale_a = m->dist_scale_a;
   p.inv_dist_scale = 1.0f / (m->dist_scale_a * m->dist_scale_b);
   p.family = m->family;
+  p.dist_k = m->dist_k;
+  p.rimg2 = reinterpret_cast<const uint8_t*>(m->d_rimg2);
   p.n_pad = m->n_pad;
   p.d = m->d;
   p.d_pad = m->d_pad;
@@ -508,6 +513,8 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   p.keep = d_keep;
   p.best_key = reinterpret_cast<long long*>(d_best_key);
   p.index_offset = index_offset;
+  p.trace = g_trace_buf;
+  p.trace_cap = g_trace_cap;
   BB_CHECK_SUPPORTED(p.n_pad <= 512, "n_pad=%d exceeds the 512 TMEM columns", p.n_pad);
   const int lag = (2 * p.n_pad <= 512) ? 1 : 0;  // two accumulators fit: defer the epilogue
   uint32_t cols = 32;
@@ -550,6 +557,14 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
 }  // namespace bb
 
 using namespace bb;
+
+// test-only: route the next fused launches' pipeline events of CTA 0 into d_buf
+// ([0] = count, then (tile*1000+event, SM clock) pairs); pass null to switch tracing off.
+extern "C" int bb_debug_set_trace(int64_t* d_buf, int64_t capacity_pairs) {
+  bb::g_trace_buf = reinterpret_cast<long long*>(d_buf);
+  bb::g_trace_cap = (int)capacity_pairs;
+  return BB_OK;
+}
 
 extern "C" int bb_score_fused(const bb_model* m, const bb_acq_spec* a, const void* d_x,
                               int32_t layout, int64_t N, int64_t ldx, const uint8_t* d_keep,

@@ -31,8 +31,10 @@ struct FusedParams {
   const int32_t* train_task;
   const uint8_t* rimg;
   const uint8_t* bimg;           // distance-GEMM B operand (fused_tc only)
+  const uint8_t* rimg2;          // pair-grouped L^-1 image (fused_tc only)
   float dist_scale_a, inv_dist_scale;  // a is scaled by dist_scale_a; D2 * inv_dist_scale = -2 a.b
   int family;
+  int dist_k;                    // 32 or 64: K extent of the distance-GEMM tiles (0: none)
   int n_pad, d, d_pad, n_chunks, task_col, n_tasks;
   float y_mean, y_std, prior_scale, inv_r_scale2;
   int scaled;  // task kernel or output scale present
@@ -49,15 +51,40 @@ struct FusedParams {
   const uint8_t* keep;
   long long* best_key;
   int64_t index_offset;
+  long long* trace;  // test-only event trace (bb_debug_set_trace); null in normal operation
+  int trace_cap;
 };
+
+// test-only: (event id, SM clock) pairs of CTA 0 for a few tiles, to reconstruct the pipeline timeline
+__device__ __forceinline__ void trace_ev(const FusedParams& p, int it, int ev) {
+  if (p.trace != nullptr && blockIdx.x == 0 && it >= 6 && it < 9) {
+    const long long c = clock64();
+    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ull);
+    if ((long long)i < p.trace_cap) {
+      p.trace[1 + 2 * i] = (long long)it * 1000 + ev;
+      p.trace[2 + 2 * i] = c;
+    }
+  }
+}
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 
-// Spin with back-off: used by the two single-lane helper warps so that their polling does not
-// eat issue slots of the compute warps sharing their scheduler.
+// Wait used by the single-lane helper warps: mbarrier.try_wait with a suspend-time hint parks the
+// thread in hardware until the phase completes (wake-up ~60 cycles after the arrive) instead of
+// polling, so the helpers neither burn issue slots nor add sleep-granularity latency.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(1000000u)
+        : "memory");
+  }
 }
 
 int launch_fused_tc(FusedParams& p, int grid, cudaStream_t stream);

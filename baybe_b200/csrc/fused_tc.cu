@@ -19,20 +19,21 @@ namespace bb {
 
 constexpr int kTcSlotsA = 2;
 constexpr int kTcMaxStagesR = 4;  // runtime p.stages_b in [2, 4]
-constexpr int kTcStagesBt = 2;
-constexpr uint32_t kBtBytes = 24576;  // [hi | mid | lo] x 8 KB: 64 training rows x 64 dims fp16
-constexpr uint32_t kA2Bytes = 49152;  // [hi | mid | lo] x 16 KB: 128 candidates x 64 dims fp16
+constexpr uint32_t kRStageBytes = 32768;  // one pair block of the L^-1 image: [hi 16 KB | lo 16 KB]
+// [hi | mid | lo] split panels; K2 = p.dist_k fp16 per row
+__host__ __device__ constexpr uint32_t bt_split_bytes(int k2, int n_pad) { return (uint32_t)n_pad * (uint32_t)k2 * 2u; }
+__host__ __device__ constexpr uint32_t a2_split_bytes(int k2) { return 128u * (uint32_t)k2 * 2u; }  // 128 candidates
 constexpr int kTcMaxSamples = 512;
 constexpr uint32_t kD2Col0 = 256;
 
 struct TcSmem {
-  uint8_t *ring_a, *ring_r, *ring_bt, *a2;
+  uint8_t *ring_a, *ring_r, *bt, *a2;
   float *tsq, *alpha_s;
   int32_t* ttask;
   float *z_s, *an_part, *mean_part, *var_part, *mc_part, *tcov, *meanc, *cscale_s, *cshift_s;
   int32_t* cand_task;
-  uint64_t *a_full, *a_empty, *r_full, *r_empty, *bt_full, *bt_empty, *d2_full, *d2_empty, *dsub_full,
-      *d_empty, *a2_full, *a2_empty;
+  uint64_t *a_full, *a_empty, *r_full, *r_empty, *d2_full, *d2_empty, *dsub_full, *d_empty, *a2_full,
+      *a2_empty;
   long long* best_red;
   uint32_t* tmem_ptr;
   float* zstat;
@@ -46,9 +47,9 @@ __host__ __device__ inline size_t tc_carve(uint8_t* base, const FusedParams& p, 
     return o;
   };
   const size_t o_ra = take((size_t)kTcSlotsA * kSlotABytes);
-  const size_t o_rr = take((size_t)p.stages_b * kStageBBytes);
-  const size_t o_bt = take((size_t)kTcStagesBt * kBtBytes);
-  const size_t o_a2 = take(kA2Bytes);
+  const size_t o_rr = take((size_t)p.stages_b * kRStageBytes);
+  const size_t o_bt = take((size_t)3 * bt_split_bytes(p.dist_k, p.n_pad));  // resident Bt panels
+  const size_t o_a2 = take((size_t)3 * a2_split_bytes(p.dist_k));
   const size_t o_tsq = take(p.n_pad * 4), o_al = take(p.n_pad * 4), o_tt = take(p.scaled ? p.n_pad * 4 : 16);
   const size_t o_z = take(kTcMaxSamples * 4);
   const size_t o_an = take(2 * 4 * kTileM * 4), o_mp = take(4 * kTileM * 4), o_vp = take(4 * kTileM * 4);
@@ -61,7 +62,7 @@ __host__ __device__ inline size_t tc_carve(uint8_t* base, const FusedParams& p, 
   if (s) {
     s->ring_a = base + o_ra;
     s->ring_r = base + o_rr;
-    s->ring_bt = base + o_bt;
+    s->bt = base + o_bt;
     s->a2 = base + o_a2;
     s->tsq = reinterpret_cast<float*>(base + o_tsq);
     s->alpha_s = reinterpret_cast<float*>(base + o_al);
@@ -77,18 +78,16 @@ __host__ __device__ inline size_t tc_carve(uint8_t* base, const FusedParams& p, 
     s->cshift_s = reinterpret_cast<float*>(base + o_sh);
     s->cand_task = reinterpret_cast<int32_t*>(base + o_ct);
     uint64_t* b = reinterpret_cast<uint64_t*>(base + o_bar);
-    s->a_full = b;            // [2]
-    s->a_empty = b + 2;       // [2]
-    s->r_full = b + 4;        // [<=4]
-    s->r_empty = b + 8;       // [<=4]
-    s->bt_full = b + 12;      // [2]
-    s->bt_empty = b + 14;     // [2]
-    s->d2_full = b + 16;      // [4]
-    s->d2_empty = b + 20;     // [4]
-    s->dsub_full = b + 24;    // [4]
-    s->d_empty = b + 28;      // [1]
-    s->a2_full = b + 29;      // [1]
-    s->a2_empty = b + 30;     // [1]
+    s->a_full = b;            // [<=4]
+    s->a_empty = b + 4;       // [<=4]
+    s->r_full = b + 8;        // [<=6]
+    s->r_empty = b + 14;      // [<=6]
+    s->d2_full = b + 24;      // [1]
+    s->d2_empty = b + 28;     // [1]
+    s->dsub_full = b + 32;    // [4]
+    s->d_empty = b + 36;      // [1]
+    s->a2_full = b + 37;      // [1]
+    s->a2_empty = b + 38;     // [1]
     s->best_red = reinterpret_cast<long long*>(base + o_best);
     s->tmem_ptr = reinterpret_cast<uint32_t*>(base + o_misc);
     s->zstat = reinterpret_cast<float*>(base + o_misc + 8);
@@ -163,8 +162,11 @@ __device__ __forceinline__ float4 tc_load_quad(const FusedParams& p, int64_t row
   }
 }
 
-template <int FAMILY>
+template <int FAMILY, int K2>
 __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams p) {
+  constexpr uint32_t kA2Split = a2_split_bytes(K2);
+  constexpr uint32_t kA2Bytes = 3 * kA2Split;
+  const uint32_t kBtSplit = bt_split_bytes(K2, p.n_pad);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TcSmem s;
   tc_carve(smem_raw, p, &s);
@@ -184,15 +186,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
       mbar_init(&s.r_full[i], 1);
       mbar_init(&s.r_empty[i], 1);
     }
-    for (int i = 0; i < kTcStagesBt; ++i) {
-      mbar_init(&s.bt_full[i], 1);
-      mbar_init(&s.bt_empty[i], 1);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s.d2_full[i], 1);
-      mbar_init(&s.d2_empty[i], kComputeWarps);
-      mbar_init(&s.dsub_full[i], 1);
-    }
+    for (int i = 0; i < 4; ++i) mbar_init(&s.dsub_full[i], 1);
+    mbar_init(s.d2_full, 1);
+    mbar_init(s.d2_empty, kComputeWarps);
     mbar_init(s.d_empty, kComputeWarps);
     mbar_init(s.a2_full, kComputeWarps);
     mbar_init(s.a2_empty, 1);
@@ -204,6 +200,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
   }
   for (int e = tid; e < (int)(kA2Bytes / 16); e += kFusedThreads)  // dims >= d stay zero for good
     reinterpret_cast<uint4*>(s.a2)[e] = make_uint4(0u, 0u, 0u, 0u);
+  for (int e = tid; e < (int)(3 * kBtSplit / 16); e += kFusedThreads)  // resident Bt panels
+    reinterpret_cast<uint4*>(s.bt)[e] = __ldg(reinterpret_cast<const uint4*>(p.bimg) + e);
   for (int e = tid; e < 64; e += kFusedThreads) {
     s.cscale_s[e] = e < p.d_pad ? __ldg(p.cand_scale + e) : 0.f;
     s.cshift_s[e] = e < p.d_pad ? __ldg(p.cand_shift + e) : 0.f;
@@ -282,16 +280,65 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
           for (int e = 0; e < 4; ++e) a[e] *= p.dist_scale_a;  // exact: power of two
           uint2 hi, mid, lo;
           split3_quad(a, hi, mid, lo);
-          const uint32_t off = sw128_offset((uint32_t)row_e, (uint32_t)(jq >> 1)) + (uint32_t)(jq & 1) * 8u;
+          const uint32_t off = swk_offset<K2>((uint32_t)row_e, (uint32_t)(jq >> 1)) + (uint32_t)(jq & 1) * 8u;
           *reinterpret_cast<uint2*>(s.a2 + off) = hi;
-          *reinterpret_cast<uint2*>(s.a2 + 16384 + off) = mid;
-          *reinterpret_cast<uint2*>(s.a2 + 32768 + off) = lo;
+          *reinterpret_cast<uint2*>(s.a2 + kA2Split + off) = mid;
+          *reinterpret_cast<uint2*>(s.a2 + 2 * kA2Split + off) = lo;
         }
       }
       s.an_part[(buf * 4 + jg) * kTileM + row_e] = an;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(s.a2_full);
+    };
+
+    // Monte-Carlo work of the PREVIOUS tile is interleaved into the chunk loop of the current one:
+    // it fills the time the tensor cores need to drain the A-operand ring and keeps MUFU/FMA busy
+    // while this tile's distance tiles are converted.
+    const bool is_mc = p.has_acq && p.acq.kind <= BB_ACQ_QPI;
+    const int per = is_mc ? p.S / 4 : 0;            // samples of this thread's group
+    const float4* zq = reinterpret_cast<const float4*>(s.z_s + cg * per);
+    const int n4_total = per >> 2;
+    bool have_prev = false;
+    float mu_p = 0.f, var_p = 0.f, c0_p = 0.f, c1_p = 0.f, s0_p = 0.f, s1_p = 0.f;
+    int64_t row0_p = 0;
+    int mc_done = 0;  // float4 groups of the previous tile's samples already accumulated
+
+    auto mc_slice = [&](int part, int nparts) {  // accumulate slice `part` of `nparts`
+      if (!have_prev || !is_mc) return;
+      const int lo = (n4_total * part) / nparts, hi = (n4_total * (part + 1)) / nparts;
+      mc_accumulate(p.acq.kind, c0_p, c1_p, zq + lo, hi - lo, s0_p, s1_p);
+      mc_done = hi;
+    };
+    // combine the four sample groups of the previous tile, score, arg-max
+    auto finish_prev = [&]() {
+      if (!p.has_acq) return;
+      if (is_mc) *reinterpret_cast<float2*>(s.mc_part + (cg * kTileM + row_e) * 2) = make_float2(s0_p, s1_p);
+      bar_compute();
+      if (cg == 0 && have_prev) {
+        float score;
+        if (is_mc) {
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            const float2 pr = *reinterpret_cast<const float2*>(s.mc_part + (gg * kTileM + row_e) * 2);
+            s0 += pr.x;
+            s1 += pr.y;
+          }
+          score = mc_finalize(p.acq, mu_p, var_p, s0, s1, p.S, s.zstat[0], s.zstat[1]);
+        } else {
+          score = analytic_value(p.acq, mu_p, var_p);
+        }
+        const int64_t row = row0_p + row_e;
+        if (row < p.N) {
+          if (p.score) p.score[row] = score;
+          const bool ok = (p.keep == nullptr || p.keep[row] != 0) && !(score != score);
+          if (ok) {
+            const long long key = pack_key(score, (uint32_t)(row + p.index_offset));
+            best = key > best ? key : best;
+          }
+        }
+      }
     };
 
     uint32_t slot = 0, ph = 0;
@@ -315,13 +362,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
       // ---- K* chunk by chunk: D2 (TMEM) -> kernel values -> fp16 hi/lo A operand ----
       for (int c = 0; c < C; ++c) {
         float v[16];
-        mbar_wait(&s.d2_full[c], par);
-        tc_fence_after();
+        if (tid == 0) trace_ev(p, it, 100 + c);
+        if (c == 0) {
+          mbar_wait(s.d2_full, par);
+          tc_fence_after();
+        }
         tmem_ld16(tmem_base + lane_base + kD2Col0 + (uint32_t)(c * kChunk + cg * 16), v);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.d2_empty[c]);
+        if (c == C - 1) {  // all of D2 is in registers now: the next tile's distance GEMM may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s.d2_empty);
+        }
+        if (tid == 0) trace_ev(p, it, 110 + c);
         const int i0 = c * kChunk + cg * 16;
         float k[16];
 #pragma unroll
@@ -348,7 +401,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
         split_pair(k[10], k[11], h1.y, l1.y);
         split_pair(k[12], k[13], h1.z, l1.z);
         split_pair(k[14], k[15], h1.w, l1.w);
+        if (tid == 0) trace_ev(p, it, 120 + c);
+        mc_slice(c, C);  // previous tile's MC slice: overlaps the MMA drain of the A ring
+        if (tid == 0) trace_ev(p, it, 130 + c);
         mbar_wait(&s.a_empty[slot], ph ^ 1u);
+        if (tid == 0) trace_ev(p, it, 140 + c);
         uint8_t* sa = s.ring_a + (size_t)slot * kSlotABytes;
         const uint32_t o0 = sw128_offset((uint32_t)row_e, (uint32_t)(2 * cg));
         const uint32_t o1 = sw128_offset((uint32_t)row_e, (uint32_t)(2 * cg + 1));
@@ -359,12 +416,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s.a_full[slot]);
+        if (tid == 0) trace_ev(p, it, 150 + c);
         if (++slot == (uint32_t)kTcSlotsA) {
           slot = 0;
           ph ^= 1u;
         }
       }
       s.mean_part[cg * kTileM + row_e] = mean;
+
+      // ---- finish the previous tile (its partial buffers are free again afterwards) ----
+      finish_prev();
+      if (tid == 0) trace_ev(p, it, 160);
 
       // ---- stage the next tile's A2 so that its distance GEMM runs under this epilogue ----
       const int next = tile + (int)gridDim.x;
@@ -374,12 +436,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
         if (next + (int)gridDim.x < p.num_tiles) prefetch(next + gridDim.x);
       }
 
+      if (tid == 0) trace_ev(p, it, 161);
       // ---- |V|^2: every 64-column sub-block is final as soon as its diagonal chunk is done ----
       {
         float ss = 0.f;
         for (int sb = 0; sb < C; ++sb) {
           float v[16];
           mbar_wait(&s.dsub_full[sb], par);
+          if (tid == 0) trace_ev(p, it, 170 + sb);
           tc_fence_after();
           tmem_ld16(tmem_base + lane_base + (uint32_t)(sb * kChunk + cg * 16), v);
           tmem_ld_wait();
@@ -392,8 +456,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
         s.var_part[cg * kTileM + row_e] = ss;
       }
       bar_compute();
+      if (tid == 0) trace_ev(p, it, 180);
 
-      // ---- moments in original units, acquisition ----
+      // ---- moments of this tile in original units; its acquisition work runs next iteration ----
       float msum = s.meanc[ct];
 #pragma unroll
       for (int gg = 0; gg < 4; ++gg) msum += s.mean_part[gg * kTileM + row_e];
@@ -401,48 +466,23 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
                          (s.var_part[2 * kTileM + row_e] + s.var_part[3 * kTileM + row_e]);
       const float kss = scaled ? s.tcov[ct * p.n_tasks + ct] : 1.0f;
       const float var_t = fmaxf(kss - vsum * p.inv_r_scale2, 1e-10f);
-      const float mu = fmaf(p.y_std, msum, p.y_mean);
-      const float var = p.y_std * p.y_std * var_t;
-      const int64_t row = row0 + row_e;
-      const bool in_range = row < p.N;
-      if (cg == 0 && in_range) {
-        if (p.mu) p.mu[row] = mu;
-        if (p.var) p.var[row] = var;
+      mu_p = fmaf(p.y_std, msum, p.y_mean);
+      var_p = p.y_std * p.y_std * var_t;
+      row0_p = row0;
+      have_prev = true;
+      s0_p = 0.f;
+      s1_p = 0.f;
+      mc_done = 0;
+      if (is_mc) mc_coef(p.acq, mu_p, var_p, c0_p, c1_p);
+      if (cg == 0 && row0 + row_e < p.N) {
+        if (p.mu) p.mu[row0 + row_e] = mu_p;
+        if (p.var) p.var[row0 + row_e] = var_p;
       }
-      if (p.has_acq) {
-        const bool is_mc = p.acq.kind <= BB_ACQ_QPI;
-        if (is_mc) {
-          float s0, s1;
-          mc_partial(p.acq, mu, var, s.z_s, p.S, cg, 4, s0, s1);
-          *reinterpret_cast<float2*>(s.mc_part + (cg * kTileM + row_e) * 2) = make_float2(s0, s1);
-        }
-        bar_compute();
-        if (cg == 0) {
-          float score;
-          if (is_mc) {
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int gg = 0; gg < 4; ++gg) {
-              const float2 pr = *reinterpret_cast<const float2*>(s.mc_part + (gg * kTileM + row_e) * 2);
-              s0 += pr.x;
-              s1 += pr.y;
-            }
-            score = mc_finalize(p.acq, mu, var, s0, s1, p.S, s.zstat[0], s.zstat[1]);
-          } else {
-            score = analytic_value(p.acq, mu, var);
-          }
-          if (in_range) {
-            if (p.score) p.score[row] = score;
-            const bool ok = (p.keep == nullptr || p.keep[row] != 0) && !(score != score);
-            if (ok) {
-              const long long key = pack_key(score, (uint32_t)(row + p.index_offset));
-              best = key > best ? key : best;
-            }
-          }
-        }
-      } else {
-        bar_compute();
-      }
+    }
+    // ---- drain: acquisition work of the last tile ----
+    if (have_prev) {
+      if (is_mc) mc_accumulate(p.acq.kind, c0_p, c1_p, zq, n4_total, s0_p, s1_p);
+      finish_prev();
     }
     if (p.best_key != nullptr && p.has_acq) {
       if (cg == 0) {
@@ -461,37 +501,30 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
     }
   } else if (warp == kWarpProducer) {
     // =====================================================================================
-    // producer (TMA engine): Bt chunks of tile 0, then per tile the L^-1 tiles of this tile
-    // followed by the Bt chunks of the next tile -- the order in which the MMA warp consumes them
+    // producer (TMA engine): streams the L^-1 tiles (same sequence for every candidate tile)
     // =====================================================================================
     if (lane == 0) {
-      uint32_t rs = 0, rph = 0, bs = 0, bph = 0;
-      const int n_tiles_r = C * (C + 1) / 2;
-      auto load_bt = [&]() {
+      uint32_t rs = 0, rph = 0;
+      int pit = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++pit) {
+        size_t off = 0;
+        int tb = 0;
         for (int c = 0; c < C; ++c) {
-          mbar_wait_relaxed(&s.bt_empty[bs], bph ^ 1u);
-          mbar_expect_tx(&s.bt_full[bs], kBtBytes);
-          bulk_g2s(s.ring_bt + (size_t)bs * kBtBytes, p.bimg + (size_t)c * kBtBytes, kBtBytes, &s.bt_full[bs]);
-          if (++bs == (uint32_t)kTcStagesBt) {
-            bs = 0;
-            bph ^= 1u;
+          for (int sb = c; sb < C; ++tb) {
+            const int g = ((sb & 1) == 0 && sb + 1 < C) ? 2 : 1;
+            const uint32_t bytes = (uint32_t)g * 16384u;
+            mbar_wait_relaxed(&s.r_empty[rs], rph ^ 1u);
+            trace_ev(p, pit, 300 + tb);
+            mbar_expect_tx(&s.r_full[rs], bytes);
+            bulk_g2s(s.ring_r + (size_t)rs * kRStageBytes, p.rimg2 + off, bytes, &s.r_full[rs]);
+            off += bytes;
+            sb += g;
+            if (++rs == (uint32_t)p.stages_b) {
+              rs = 0;
+              rph ^= 1u;
+            }
           }
         }
-      };
-      int tile = blockIdx.x;
-      if (tile < p.num_tiles) load_bt();
-      for (; tile < p.num_tiles; tile += gridDim.x) {
-        for (int tb = 0; tb < n_tiles_r; ++tb) {
-          mbar_wait_relaxed(&s.r_empty[rs], rph ^ 1u);
-          mbar_expect_tx(&s.r_full[rs], kStageBBytes);
-          bulk_g2s(s.ring_r + (size_t)rs * kStageBBytes, p.rimg + (size_t)tb * kStageBBytes, kStageBBytes,
-                   &s.r_full[rs]);
-          if (++rs == (uint32_t)p.stages_b) {
-            rs = 0;
-            rph ^= 1u;
-          }
-        }
-        if (tile + (int)gridDim.x < p.num_tiles) load_bt();
       }
     }
   } else {
@@ -499,74 +532,79 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
     // MMA issuer
     // =====================================================================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kTileM, kChunk);
-      uint32_t slot = 0, pha = 0, rs = 0, rph = 0, bs = 0, bph = 0;
-      const uint32_t a2_addr = smem_u32(s.a2);
-      const uint64_t a2_h = make_sw128_desc(a2_addr), a2_m = make_sw128_desc(a2_addr + 16384),
-                     a2_l = make_sw128_desc(a2_addr + 32768);
-      // distance GEMM of tile number j: D2[c] = A2 * Bt[c]^T, six split products
+      const uint32_t idesc = make_idesc_f16(kTileM, kChunk), idesc128 = make_idesc_f16(kTileM, 2 * kChunk);
+      const uint32_t idesc_d2 = make_idesc_f16(kTileM, p.n_pad);  // one MMA spans all training columns
+      uint32_t slot = 0, pha = 0, rs = 0, rph = 0;
+      const uint32_t a2_addr = smem_u32(s.a2), bt_addr = smem_u32(s.bt);
+      const uint64_t a2_h = make_swk_desc<K2>(a2_addr), a2_m = make_swk_desc<K2>(a2_addr + kA2Split),
+                     a2_l = make_swk_desc<K2>(a2_addr + 2 * kA2Split);
+      const uint64_t b_h = make_swk_desc<K2>(bt_addr), b_m = make_swk_desc<K2>(bt_addr + kBtSplit),
+                     b_l = make_swk_desc<K2>(bt_addr + 2 * kBtSplit);
+      // distance GEMM of tile number j: D2 = A2 * Bt^T, six split products, N = n_pad per MMA
       auto issue_distance = [&](int j) {
         const uint32_t par = (uint32_t)(j & 1);
+        trace_ev(p, j, 250);
         mbar_wait_relaxed(s.a2_full, par);
+        trace_ev(p, j, 251);
+        mbar_wait_relaxed(s.d2_empty, par ^ 1u);  // D2 drained by the previous tile's chunk loop
+        trace_ev(p, j, 252);
         tc_fence_after();
-        for (int c = 0; c < C; ++c) {
-          mbar_wait_relaxed(&s.bt_full[bs], bph);
-          mbar_wait_relaxed(&s.d2_empty[c], par ^ 1u);  // slot drained by the previous tile
-          tc_fence_after();
-          const uint32_t bt_addr = smem_u32(s.ring_bt + (size_t)bs * kBtBytes);
-          const uint64_t b_h = make_sw128_desc(bt_addr), b_m = make_sw128_desc(bt_addr + 8192),
-                         b_l = make_sw128_desc(bt_addr + 16384);
-          const uint32_t d_addr = tmem_base + kD2Col0 + (uint32_t)(c * kChunk);
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t ko = (uint64_t)(kk * 2);
-            umma_f16(d_addr, a2_h + ko, b_h + ko, idesc, kk > 0 ? 1u : 0u);
-            umma_f16(d_addr, a2_h + ko, b_m + ko, idesc, 1u);
-            umma_f16(d_addr, a2_m + ko, b_h + ko, idesc, 1u);
-            umma_f16(d_addr, a2_h + ko, b_l + ko, idesc, 1u);
-            umma_f16(d_addr, a2_l + ko, b_h + ko, idesc, 1u);
-            umma_f16(d_addr, a2_m + ko, b_m + ko, idesc, 1u);
-          }
-          umma_commit(&s.bt_empty[bs]);
-          umma_commit(&s.d2_full[c]);
-          if (++bs == (uint32_t)kTcStagesBt) {
-            bs = 0;
-            bph ^= 1u;
-          }
+        const uint32_t d_addr = tmem_base + kD2Col0;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t ko = (uint64_t)(kk * 2);
+          umma_f16(d_addr, a2_h + ko, b_h + ko, idesc_d2, kk > 0 ? 1u : 0u);
+          umma_f16(d_addr, a2_h + ko, b_m + ko, idesc_d2, 1u);
+          umma_f16(d_addr, a2_m + ko, b_h + ko, idesc_d2, 1u);
+          umma_f16(d_addr, a2_h + ko, b_l + ko, idesc_d2, 1u);
+          umma_f16(d_addr, a2_l + ko, b_h + ko, idesc_d2, 1u);
+          umma_f16(d_addr, a2_m + ko, b_m + ko, idesc_d2, 1u);
         }
+        umma_commit(s.d2_full);
         umma_commit(s.a2_empty);
+        trace_ev(p, j, 253);
       };
       int j = 0;
       int tile = blockIdx.x;
       if (tile < p.num_tiles) issue_distance(0);
       for (; tile < p.num_tiles; tile += gridDim.x, ++j) {
         mbar_wait_relaxed(s.d_empty, (uint32_t)((j & 1) ^ 1));  // previous epilogue drained V
+        trace_ev(p, j, 200);
         tc_fence_after();
         for (int c = 0; c < C; ++c) {
           mbar_wait_relaxed(&s.a_full[slot], pha);
+          trace_ev(p, j, 210 + c);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(s.ring_a + (size_t)slot * kSlotABytes);
           const uint64_t a_hi = make_sw128_desc(a_addr), a_lo = make_sw128_desc(a_addr + 16384);
-          for (int sb = c; sb < C; ++sb) {
+          // Every SS-form tcgen05.mma re-reads its 128x16 A slice from shared memory (~130 cycles,
+          // four times the math of a 64-column MMA), so adjacent column sub-blocks are issued as one
+          // 128-column MMA wherever the lower-triangular structure allows a pair.
+          for (int sb = c; sb < C;) {
+            const int g = ((sb & 1) == 0 && sb + 1 < C) ? 2 : 1;
             mbar_wait_relaxed(&s.r_full[rs], rph);
+            trace_ev(p, j, 220 + c * 4 + sb);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(s.ring_r + (size_t)rs * kStageBBytes);
-            const uint64_t b_hi = make_sw128_desc(b_addr), b_lo = make_sw128_desc(b_addr + 8192);
+            const uint32_t b_addr = smem_u32(s.ring_r + (size_t)rs * kRStageBytes);
+            const uint64_t b_hi = make_sw128_desc(b_addr), b_lo = make_sw128_desc(b_addr + (uint32_t)g * 8192u);
             const uint32_t d_addr = tmem_base + (uint32_t)(sb * kChunk);
+            const uint32_t id = (g == 2) ? idesc128 : idesc;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t ko = (uint64_t)(kk * 2);
-              umma_f16(d_addr, a_hi + ko, b_hi + ko, idesc, (c > 0 || kk > 0) ? 1u : 0u);
-              umma_f16(d_addr, a_hi + ko, b_lo + ko, idesc, 1u);
-              umma_f16(d_addr, a_lo + ko, b_hi + ko, idesc, 1u);
+              umma_f16(d_addr, a_hi + ko, b_hi + ko, id, (c > 0 || kk > 0) ? 1u : 0u);
+              umma_f16(d_addr, a_hi + ko, b_lo + ko, id, 1u);
+              umma_f16(d_addr, a_lo + ko, b_hi + ko, id, 1u);
             }
             umma_commit(&s.r_empty[rs]);
             if (++rs == (uint32_t)p.stages_b) {
               rs = 0;
               rph ^= 1u;
             }
+            sb += g;
           }
           umma_commit(&s.a_empty[slot]);
           umma_commit(&s.dsub_full[c]);  // sub-block c of V has received its last contribution
+          trace_ev(p, j, 240 + c);
           if (++slot == (uint32_t)kTcSlotsA) {
             slot = 0;
             pha ^= 1u;
@@ -587,7 +625,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
 bool fused_tc_supported(FusedParams& p, int max_smem) {
   if (p.n_pad > 256 || p.d_pad > 64 || p.family == BB_KERNEL_MATERN12) return false;
   if (p.has_acq && p.S > kTcMaxSamples) return false;
-  if (p.bimg == nullptr) return false;
+  if (p.bimg == nullptr || p.rimg2 == nullptr || (p.dist_k != 32 && p.dist_k != 64) || p.d_pad > p.dist_k) return false;
   for (int st = kTcMaxStagesR; st >= 2; --st) {
     p.stages_b = st;
     if (tc_carve(nullptr, p, nullptr) + 2048 <= (size_t)max_smem) return true;
@@ -595,12 +633,18 @@ bool fused_tc_supported(FusedParams& p, int max_smem) {
   return false;
 }
 
-template <int FAMILY>
-static int launch_tc_family(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
-  BB_CUDA(cudaFuncSetAttribute(k_fused_tc<FAMILY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_fused_tc<FAMILY><<<grid, kFusedThreads, smem, stream>>>(p);
+template <int FAMILY, int K2>
+static int launch_tc_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
+  BB_CUDA(cudaFuncSetAttribute(k_fused_tc<FAMILY, K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_fused_tc<FAMILY, K2><<<grid, kFusedThreads, smem, stream>>>(p);
   BB_LAUNCH_CHECK();
   return BB_OK;
+}
+
+template <int FAMILY>
+static int launch_tc_family(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
+  return p.dist_k == 32 ? launch_tc_one<FAMILY, 32>(p, grid, smem, stream)
+                        : launch_tc_one<FAMILY, 64>(p, grid, smem, stream);
 }
 
 int launch_fused_tc(FusedParams& p, int grid, cudaStream_t stream) {

@@ -28,7 +28,7 @@ const char* last_error() { return g_err; }
 // ------------------------------------------------------------------------------------------
 struct BlobLayout {
   size_t cand_scale, cand_shift, train_m2, train_sq, alpha, train_task, task_covar, mean_const,
-      rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, bimg, flags,
+      rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, bimg, rimg2, flags,
       total;
   int n_pad, d_pad, n_chunks, n_tiles;
 };
@@ -68,6 +68,7 @@ static BlobLayout make_layout(int n, int d, int T) {
   L.pend_norm = take(sizeof(double) * BB_MAX_PENDING * d);
   L.pend_w64 = take(sizeof(double) * BB_MAX_PENDING * n);
   L.bimg = take((size_t)L.n_chunks * 24576);
+  L.rimg2 = take((size_t)L.n_tiles * 16384);
   L.flags = take(64);
   L.total = off;
   return L;
@@ -251,25 +252,70 @@ __global__ void k_build_rimg(const double* __restrict__ Linv, int n, int n_chunk
   }
 }
 
-// fp16 hi/mid/lo image of (scale * -2b) for the tensor-core distance GEMM: per K chunk c one
-// 24 KB block [hi 8 KB | mid 8 KB | lo 8 KB], each [64 training rows][64 dims] fp16, K-major,
-// 128-byte swizzled; dims >= d are zero.  D2[m][i] = sum_j a[m][j] * (-2 b[i][j]).
+// Second layout of the (scale * L^-1) image for the fused_tc kernel: per K chunk c the column
+// sub-blocks s >= c are grouped so that one tcgen05.mma covers up to 128 output columns -- a
+// leading single tile if c is odd, then pairs (s, s+1) with s even, then a trailing single.
+// A pair block is [hi: 128 rows x 64 k | lo: same] = 32 KB, a single block [hi 8 KB | lo 8 KB];
+// blocks follow each other in consumption order.  One CTA per block (blockIdx.x = group index).
+__global__ void k_build_rimg2(const double* __restrict__ Linv, int n, int n_chunks, double scale,
+                              uint8_t* __restrict__ rimg2) {
+  // decode group -> (c, first sub-block s, size g) and byte offset
+  int grp = blockIdx.x, c = 0, s0 = 0, g = 1;
+  size_t off = 0;
+  bool found = false;
+  int idx = 0;
+  for (c = 0; c < n_chunks && !found; ++c) {
+    int s = c;
+    while (s < n_chunks) {
+      const int gg = ((s & 1) == 0 && s + 1 < n_chunks) ? 2 : 1;
+      if (idx == grp) {
+        s0 = s;
+        g = gg;
+        found = true;
+        break;
+      }
+      off += (size_t)gg * 16384;
+      s += gg;
+      ++idx;
+    }
+    if (found) break;
+  }
+  if (!found) return;
+  uint8_t* base = rimg2 + off;
+  const uint32_t lo_off = (uint32_t)g * 8192u;
+  const int rows = 64 * g;
+  for (int e = threadIdx.x; e < rows * 64; e += blockDim.x) {
+    const int r = e >> 6, kk = e & 63;
+    const int j = s0 * 64 + r, i = c * 64 + kk;
+    const double v = (j < n && i < n && i <= j) ? Linv[(size_t)j * n + i] * scale : 0.0;
+    const float vf = (float)v;
+    const __half hi = __float2half_rn(vf);
+    const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+    const uint32_t o = sw128_offset((uint32_t)r, (uint32_t)(kk >> 3)) + (uint32_t)(kk & 7) * 2u;
+    *reinterpret_cast<__half*>(base + o) = hi;
+    *reinterpret_cast<__half*>(base + lo_off + o) = lo;
+  }
+}
+
+// fp16 hi/mid/lo image of (scale * -2b) for the tensor-core distance GEMM: three panels
+// [hi | mid | lo], each [n_pad training rows][K2 dims] fp16, K-major, swizzled (K2 = 32: 64-byte
+// rows / SWIZZLE_64B; K2 = 64: 128-byte rows / SWIZZLE_128B); 8-row groups contiguous; dims >= d
+// are zero.  D2[m][i] = sum_j a[m][j] * (-2 b[i][j]).
+template <int K2>
 __global__ void k_build_bimg(const float* __restrict__ train_m2, int n_pad, int d_pad, float scale,
                              uint8_t* __restrict__ bimg) {
-  const int c = blockIdx.x;
-  uint8_t* base = bimg + (size_t)c * 24576;
-  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
-    const int r = e >> 6, j = e & 63;
-    const int i = c * 64 + r;
-    const float v = (j < d_pad && i < n_pad) ? train_m2[(size_t)i * d_pad + j] * scale : 0.f;
+  const uint32_t split = (uint32_t)n_pad * K2 * 2u;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_pad * K2; e += gridDim.x * blockDim.x) {
+    const int i = e / K2, j = e - i * K2;
+    const float v = (j < d_pad) ? train_m2[(size_t)i * d_pad + j] * scale : 0.f;
     const __half h = __float2half_rn(v);
     const float r1 = v - __half2float(h);
     const __half m = __float2half_rn(r1);
     const __half l = __float2half_rn(r1 - __half2float(m));
-    const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)(j >> 3)) + (uint32_t)(j & 7) * 2u;
-    *reinterpret_cast<__half*>(base + off) = h;
-    *reinterpret_cast<__half*>(base + 8192 + off) = m;
-    *reinterpret_cast<__half*>(base + 16384 + off) = l;
+    const uint32_t off = swk_offset<K2>((uint32_t)i, (uint32_t)(j >> 3)) + (uint32_t)(j & 7) * 2u;
+    *reinterpret_cast<__half*>(bimg + off) = h;
+    *reinterpret_cast<__half*>(bimg + split + off) = m;
+    *reinterpret_cast<__half*>(bimg + 2 * split + off) = l;
   }
 }
 
@@ -546,9 +592,27 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
   k_build_rimg<<<L.n_tiles, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, B + L.rimg,
                                               (float*)(B + L.linv32), L.n_pad);
   BB_LAUNCH_CHECK();
-  if (L.d_pad <= 64) {
-    k_build_bimg<<<L.n_chunks, 256, 0, stream>>>((const float*)(B + L.train_m2), L.n_pad, L.d_pad,
-                                                 dist_scale_b, B + L.bimg);
+  {
+    int n_groups = 0;
+    for (int c = 0; c < L.n_chunks; ++c)
+      for (int sb = c; sb < L.n_chunks;) {
+        const int g = ((sb & 1) == 0 && sb + 1 < L.n_chunks) ? 2 : 1;
+        sb += g;
+        ++n_groups;
+      }
+    k_build_rimg2<<<n_groups, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, B + L.rimg2);
+    BB_LAUNCH_CHECK();
+  }
+  int dist_k = 0;
+  if (L.d_pad <= 32) {
+    dist_k = 32;
+    k_build_bimg<32><<<L.n_chunks, 256, 0, stream>>>((const float*)(B + L.train_m2), L.n_pad,
+                                                     L.d_pad, dist_scale_b, B + L.bimg);
+    BB_LAUNCH_CHECK();
+  } else if (L.d_pad <= 64) {
+    dist_k = 64;
+    k_build_bimg<64><<<L.n_chunks, 256, 0, stream>>>((const float*)(B + L.train_m2), L.n_pad,
+                                                     L.d_pad, dist_scale_b, B + L.bimg);
     BB_LAUNCH_CHECK();
   }
 
@@ -586,6 +650,8 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
   out->d_bimg = B + L.bimg;
   out->dist_scale_a = dist_scale_a;
   out->dist_scale_b = dist_scale_b;
+  out->dist_k = dist_k;
+  out->d_rimg2 = B + L.rimg2;
   BB_CUDA(cudaStreamSynchronize(stream));
   return BB_OK;
 }

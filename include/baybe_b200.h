@@ -132,6 +132,9 @@ typedef struct bb_model {
                                 rows: B operand of the tensor-core distance GEMM            */
   float dist_scale_a;        /* power-of-two scales folded into the fp16 images of the      */
   float dist_scale_b;        /* candidate rows (a) and training rows (b)                    */
+  int32_t dist_k;            /* K extent of the d_bimg tiles: 32 (d_pad<=32), 64, or 0 = none */
+  int32_t pad_;
+  const void* d_rimg2;       /* L^-1 image grouped in 128-column pair tiles (fused_tc kernel)   */
 } bb_model;
 
 /* Acquisition context built by BotorchAcquisitionFunctionBuilder.build
@@ -221,6 +224,9 @@ int bb_topk(const float* d_score, const uint8_t* d_keep, int64_t N, int32_t k, f
  * tests to separate tcgen05-path errors from formula errors.  Not called by the product. -- */
 int bb_debug_posterior_simt(const bb_model* m, const void* d_x, int32_t layout, int64_t N,
                             int64_t ldx, float* d_mu, float* d_var, void* stream);
+/* test-only: record pipeline events of CTA 0 of the following fused launches into d_buf
+ * ([0] = count, then (tile*1000 + event id, SM clock) int64 pairs); NULL switches it off. */
+int bb_debug_set_trace(int64_t* d_buf, int64_t capacity_pairs);
 
 #ifdef __cplusplus
 }
