@@ -1,0 +1,84 @@
+"""Full-size GPU tests (BASELINE config 2: 1,000,000 x 20 candidates, n = 256) through
+size-independent properties, plus an oracle spot-check on a random row sample:
+  * scores of a 4096-row random sample agree with the float64 oracle,
+  * the fused arg-max equals the first maximum of the returned score vector,
+  * sharding invariance: max over per-shard keys (with global offsets) == key of the whole set,
+  * idempotence / determinism: two passes give bit-identical scores,
+  * layout invariance at scale (fp32 row-major vs the reference's fp64 column-major),
+  * the keep mask removes exactly the masked rows from contention.
+BASELINE config 5 (4 tasks x 250k, ICM kernel) is checked the same way."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from baybe_b200 import AcqConfig, DeviceGP, sobol_normal_samples
+from baybe_b200.engine import decode_best, unpack_best
+from baybe_b200.synthetic import numeric_grid_workload, task_workload
+from tests.helpers import oracle_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_fullsize(w, dev, n_shards=3):
+    om = oracle_model(w)
+    gp = DeviceGP(device=dev, **w.gp_kwargs())
+    N = len(w.candidates)
+    z = sobol_normal_samples(512, 1, seed=1234)
+    oacq = oracle.AcqSpec("qLogEI")
+    oacq.best_f = oracle.best_f_from_training(om, w.train_x, oacq)
+    acq = AcqConfig(kind="qLogEI", best_f=gp.best_f(AcqConfig(kind="qLogEI")))
+    x32 = torch.from_numpy(w.candidates).to(dev, torch.float32)
+    scores, key = gp.score(acq, x32, z[:, 0])
+    val, idx = decode_best(key)
+    # (1) oracle spot-check
+    rows = np.random.default_rng(0).choice(N, size=4096, replace=False)
+    ref = oracle.acq_values(om, oacq, w.candidates[rows], z[:, 0])
+    got = scores[torch.from_numpy(rows).to(dev)].double().cpu()
+    err = (got - ref).abs()
+    assert float((err > 5e-3 + 2e-3 * ref.abs()).double().mean()) <= 0.002, float(err.max())
+    # (2) arg-max == first maximum of the score vector
+    assert idx == int(torch.argmax(scores)) and val == float(scores[idx])
+    # (3) sharding invariance with global offsets
+    bounds = np.linspace(0, N, n_shards + 1).astype(int)
+    keys = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        _, k = gp.score(acq, x32[lo:hi], z[:, 0], index_offset=int(lo), want_scores=False)
+        keys.append(int(k.item()))
+    assert unpack_best(max(keys)) == (val, idx)
+    # (4) determinism
+    scores2, key2 = gp.score(acq, x32, z[:, 0])
+    assert torch.equal(scores, scores2) and int(key2.item()) == int(key.item())
+    # (5) layout invariance: the reference's float64 column-major matrix, no conversion pass
+    x64c = torch.from_numpy(w.candidates).to(dev).t().contiguous().t()
+    scores3, key3 = gp.score(acq, x64c, z[:, 0])
+    assert torch.equal(scores, scores3) and int(key3.item()) == int(key.item())
+    # (6) keep mask
+    keep = torch.ones(N, dtype=torch.uint8, device=dev)
+    top = torch.topk(scores, 3).indices
+    keep[top[:2]] = 0
+    _, key4 = gp.score(acq, x32, z[:, 0], keep=keep, want_scores=False)
+    masked = scores.clone()
+    masked[top[:2]] = -float("inf")
+    assert decode_best(key4)[1] == int(torch.argmax(masked))
+    return gp, scores
+
+
+def test_config2_one_million_candidates(cuda_device):
+    w = numeric_grid_workload(N=1_000_000, d=20, n=256)
+    gp, scores = _check_fullsize(w, cuda_device)
+    # posterior at the training rows: variance collapses to ~noise level, mean interpolates
+    mu, var = gp.posterior(torch.from_numpy(w.train_x))
+    assert float(var.max()) < 0.05 * float(np.var(w.train_y)) and float(var.min()) > 0
+    assert float((mu.cpu().double() - torch.from_numpy(w.train_y)).abs().max()) < 0.2 * float(np.std(w.train_y))
+    # top-k consistency
+    vals, idx = torch.ops.baybe_b200.topk(scores, None, 8)
+    ref_vals, _ = torch.topk(scores, 8)
+    assert torch.equal(vals, ref_vals)
+
+
+def test_config5_four_tasks_one_million_candidates(cuda_device):
+    w = task_workload(N_per_task=250_000, n_tasks=4, d_num=20, n_per_task=64, seed=0)
+    _check_fullsize(w, cuda_device, n_shards=4)
