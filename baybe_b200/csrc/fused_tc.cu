@@ -481,8 +481,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
     }
     // ---- drain: acquisition work of the last tile ----
     if (have_prev) {
-      if (is_mc) mc_accumulate(p.acq.kind, c0_p, c1_p, zq, n4_total, s0_p, s1_p);
-      finish_prev();
+      for (int c = 0; c < C; ++c) mc_slice(c, C);  // same slices and order as the interleaved path:
+      finish_prev();                               // a row's score must not depend on its tile's position
     }
     if (p.best_key != nullptr && p.has_acq) {
       if (cg == 0) {

@@ -228,15 +228,67 @@ class DeviceGP:
     def score(self, acq: AcqConfig, x, z: torch.Tensor | None, keep: torch.Tensor | None = None,
               index_offset: int = 0, want_scores: bool = True):
         """One fused pass: posterior + q=1 acquisition + arg-max.  Returns (scores or None,
-        packed best key (int64 device tensor of shape [1]))."""
-        xd = self.prepare(x)
+        packed best key (int64 device tensor of shape [1])).
+
+        A large candidate matrix living in (ideally pinned) HOST memory is streamed: row blocks are
+        copied on a side stream while the previous block is being scored, so the pass costs about
+        max(H2D, compute) instead of their sum."""
         zf = None
         if acq.is_mc:
             if z is None:
                 raise ValueError("Monte Carlo acquisition functions need base samples")
             zf = z.reshape(-1).to(self.device, torch.float32)
+        if torch.is_tensor(x) and x.device.type == "cpu" and x.dim() == 2 and x.shape[0] >= self.STREAM_MIN_ROWS \
+                and x.dtype in (torch.float32, torch.float64) and x.is_contiguous():
+            return self._score_streamed(acq, x, zf, keep, index_offset, want_scores)
+        xd = self.prepare(x)
         return torch.ops.baybe_b200.score_fused(xd, keep, zf, self.handle, _lib.ACQ_KIND[acq.kind],
                                                 acq.params(), int(index_offset), bool(want_scores))
+
+    STREAM_MIN_ROWS = 262_144
+    STREAM_BLOCKS = 8
+
+    def _score_streamed(self, acq: AcqConfig, x: torch.Tensor, zf, keep, index_offset: int, want_scores: bool):
+        if x.shape[1] != self.d:
+            raise ValueError(f"expected a (N, {self.d}) candidate matrix, got {tuple(x.shape)}")
+        lib = _lib.load()
+        N = x.shape[0]
+        nblk = self.STREAM_BLOCKS
+        rows = -(-N // nblk)
+        rows = -(-rows // 128) * 128  # whole tiles per block
+        c_acq = acq.to_c()
+        lay = _lib.LAYOUT["row_f64" if x.dtype == torch.float64 else "row_f32"]
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream()
+            if not hasattr(self, "_copy_stream"):
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            copy = self._copy_stream
+            bufs = [torch.empty((rows, self.d), dtype=x.dtype, device=self.device) for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            freed = [torch.cuda.Event() for _ in range(2)]
+            score = torch.empty(N if want_scores else 0, dtype=torch.float32, device=self.device)
+            key = torch.empty(1, dtype=torch.int64, device=self.device)
+            _lib.check(lib.bb_best_init(_ptr(key), _stream_ptr()), "bb_best_init")
+            copy.wait_stream(main)
+            S = 0 if zf is None else zf.numel()
+            for b, lo in enumerate(range(0, N, rows)):
+                hi = min(lo + rows, N)
+                slot = b & 1
+                with torch.cuda.stream(copy):
+                    if b >= 2:
+                        copy.wait_event(freed[slot])
+                    bufs[slot][: hi - lo].copy_(x[lo:hi], non_blocking=True)
+                    ready[slot].record(copy)
+                main.wait_event(ready[slot])
+                kp = None if keep is None else keep[lo:hi]
+                _lib.check(lib.bb_score_fused(
+                    C.byref(self.model), C.byref(c_acq), _ptr(bufs[slot]), lay, hi - lo, self.d, _ptr(kp), _ptr(zf), S,
+                    C.c_void_p(score.data_ptr() + 4 * lo) if want_scores else None, _ptr(key),
+                    int(index_offset) + lo, _stream_ptr()), "bb_score_fused")
+                freed[slot].record(main)
+            for t in bufs:
+                t.record_stream(main)
+        return score, key
 
     def score_joint(self, acq: AcqConfig, x, pending, z: torch.Tensor) -> torch.Tensor:
         """MC acquisition value of [x*; pending] for every row x* (sequential-greedy round)."""

@@ -79,6 +79,22 @@ def test_config2_one_million_candidates(cuda_device):
     assert torch.equal(vals, ref_vals)
 
 
+def test_streamed_host_matrix_equals_resident_scoring(cuda_device):
+    """The e2e path (host matrix streamed in row blocks) must be bit-identical to the resident one."""
+    w = numeric_grid_workload(N=600_001, d=20, n=256, seed=3)  # ragged last block
+    gp = DeviceGP(device=cuda_device, **w.gp_kwargs())
+    z = sobol_normal_samples(512, 1, seed=5)
+    acq = AcqConfig(kind="qLogEI", best_f=gp.best_f(AcqConfig(kind="qLogEI")))
+    x_host = torch.from_numpy(w.candidates).to(torch.float32).pin_memory()
+    keep = torch.ones(len(x_host), dtype=torch.uint8, device=cuda_device)
+    keep[::7] = 0
+    s_res, k_res = gp.score(acq, x_host.to(cuda_device), z[:, 0], keep=keep, index_offset=1000)
+    s_str, k_str = gp.score(acq, x_host, z[:, 0], keep=keep, index_offset=1000)
+    assert torch.equal(s_res, s_str) and int(k_res.item()) == int(k_str.item())
+    s64, k64 = gp.score(acq, torch.from_numpy(w.candidates), z[:, 0], keep=keep, index_offset=1000)  # pageable fp64
+    assert torch.equal(s_res, s64) and int(k_res.item()) == int(k64.item())
+
+
 def test_config5_four_tasks_one_million_candidates(cuda_device):
     w = task_workload(N_per_task=250_000, n_tasks=4, d_num=20, n_per_task=64, seed=0)
     _check_fullsize(w, cuda_device, n_shards=4)
