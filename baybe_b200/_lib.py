@@ -13,7 +13,7 @@ ABI_VERSION = 1
 
 # enums (mirror include/baybe_b200.h)
 KERNEL_FAMILY = {"matern12": 0, "matern32": 1, "matern52": 2, "rbf": 3}
-LAYOUT = {"row_f32": 0, "col_f32": 1, "row_f64": 2, "col_f64": 3}
+LAYOUT = {"row_f32": 0, "col_f32": 1, "row_f64": 2, "col_f64": 3, "bits_u8": 4}
 ACQ_KIND = {
     "qLogEI": 0, "qEI": 1, "qUCB": 2, "qSR": 3, "qPI": 4,
     "UCB": 5, "EI": 6, "LogEI": 7, "PI": 8, "PM": 9, "PSTD": 10,
@@ -52,6 +52,10 @@ class Model(C.Structure):
         ("d_linv32", C.c_void_p), ("d_bimg", C.c_void_p),
         ("dist_scale_a", C.c_float), ("dist_scale_b", C.c_float),
         ("dist_k", C.c_int32), ("pad_", C.c_int32), ("d_rimg2", C.c_void_p),
+        ("wide", C.c_int32), ("d_wide", C.c_int32), ("d_wimg", C.c_void_p),
+        ("d_wimg_bits", C.c_void_p), ("d_wnorm_bits", C.c_void_p), ("d_wide_ws", C.c_void_p),
+        ("wide_ws_rows", C.c_int64), ("dist_scale_w", C.c_float), ("pad2_", C.c_int32),
+        ("d_rimg4", C.c_void_p),
     ]
 
 

@@ -3,6 +3,7 @@
 //   k_cross  : posterior covariance of every candidate with the pending points (K9 prologue)
 //   k_simt   : test-only fp32 SIMT posterior (direct-difference distances, no tensor cores)
 #include "assemble.cuh"
+#include "fused_common.cuh"
 #include "common.cuh"
 
 namespace bb {
@@ -438,6 +439,18 @@ using namespace bb;
 extern "C" int bb_kernel_matrix(const bb_model* m, const void* d_x, int32_t layout, int64_t N,
                                 int64_t ldx, float* d_k, int64_t ldk, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (m && m->abi_version == BB_ABI_VERSION && m->wide) {  // K-chunked tensor-core path (wide.cu)
+    BB_CHECK_ARG(d_x != nullptr || N == 0, "candidate pointer is null");
+    BB_CHECK_ARG(layout >= 0 && layout <= BB_BITS_U8, "unknown candidate layout %d", layout);
+    BB_CHECK_ARG(N >= 0, "negative candidate count");
+    const bool cm = (layout == BB_COL_MAJOR_F32 || layout == BB_COL_MAJOR_F64);
+    BB_CHECK_ARG(layout == BB_BITS_U8 ? ldx >= (m->d + 7) / 8 : (cm ? ldx >= N : ldx >= m->d),
+                 "leading dimension %lld too small", (long long)ldx);
+    BB_CHECK_ARG(d_k != nullptr || N == 0, "bb_kernel_matrix: output pointer is null");
+    BB_CHECK_ARG(ldk >= m->n, "bb_kernel_matrix: ldk=%lld smaller than n=%d", (long long)ldk, m->n);
+    if (N == 0) return BB_OK;
+    return launch_kmat_wide(m, d_x, layout, N, ldx, d_k, ldk, N, m->n, stream);
+  }
   AuxParams p;
   int rc = fill_params(p, m, d_x, layout, N, ldx);
   if (rc != BB_OK) return rc;

@@ -40,7 +40,7 @@ __device__ __forceinline__ FusedSmem carve_fused(uint8_t* base, const FusedParam
   s.ring_a = cur;
   cur += (size_t)p.slots_a * kSlotABytes;
   s.ring_b = cur;
-  cur += (size_t)p.stages_b * kStageBBytes;
+  cur += (size_t)p.stages_b * p.stage_b_bytes;
   s.xt4 = reinterpret_cast<float4*>(cur);
   cur += (size_t)p.n_pad * p.d_pad * 4;
   s.tsq = reinterpret_cast<float*>(cur);
@@ -86,7 +86,7 @@ __device__ __forceinline__ FusedSmem carve_fused(uint8_t* base, const FusedParam
 
 static size_t fused_smem_bytes(const FusedParams& p) {
   size_t b = 0;
-  b += (size_t)p.slots_a * kSlotABytes + (size_t)p.stages_b * kStageBBytes;
+  b += (size_t)p.slots_a * kSlotABytes + (size_t)p.stages_b * p.stage_b_bytes;
   b += (size_t)p.n_pad * p.d_pad * 4 + (size_t)p.n_pad * 12;
   b += (size_t)kTileM * p.d_pad * 8 + kMaxSamples * 4;
   b += 2 * 8 * kTileM * 4 + 4 * kTileM * 4 + 4 * kTileM * 2 * 4;
@@ -98,7 +98,11 @@ static size_t fused_smem_bytes(const FusedParams& p) {
 
 // LAG = 1: the epilogue of tile t runs after the assembly of tile t+1, so the tensor-core tail of
 // tile t is never waited for; needs two accumulators in TMEM (2 * n_pad <= 512 columns).
-template <int FAMILY, int LAG>
+// PRE = true (wide-feature path): the K* block was materialised by k_kmat_tc (wide.cu) and is read from
+// p.kpre instead of being assembled here; FAMILY is then irrelevant.
+// GMAX: L^-1 sub-blocks (64 output columns each) per ring stage / per MMA (N = 64 * group): every SS-form
+// tcgen05.mma re-reads its A slice from shared memory whatever N is, so wider groups cut the MMA time.
+template <int FAMILY, int LAG, bool PRE, int GMAX>
 __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const FusedSmem s = carve_fused(smem_raw, p);
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
     tmem_relinquish();
   }
   // model data resident in shared memory for the whole kernel
-  load_train_rows(s.xt4, p.train_m2, p.n_pad, dq, tid, kFusedThreads);
+  if constexpr (!PRE) load_train_rows(s.xt4, p.train_m2, p.n_pad, dq, tid, kFusedThreads);
   for (int e = tid; e < p.d_pad; e += kFusedThreads) {
     s.cscale_s[e] = __ldg(p.cand_scale + e);
     s.cshift_s[e] = __ldg(p.cand_shift + e);
@@ -189,7 +193,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
     sc.cshift = s.cshift_s;
     sc.groups = kComputeThreads / kTileM;
     StageRegs regs;
-    if ((int)blockIdx.x < p.num_tiles) stage_prefetch(sc, dq, (int64_t)blockIdx.x * kTileM, tid, regs);
+    if constexpr (!PRE)
+      if ((int)blockIdx.x < p.num_tiles) stage_prefetch(sc, dq, (int64_t)blockIdx.x * kTileM, tid, regs);
     const int mp = tid & 63, g = tid >> 6;       // assembly: candidates (mp, mp+64), i-octet g
     const int row_e = tid & 127, sg = tid >> 7;  // epilogue: TMEM lane row_e, column/sample group
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -278,14 +283,57 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
       const int buf = LAG ? (it & 1) : 0;
       const int64_t row0 = (int64_t)tile * kTileM;
       sm.cand_task = s.cand_task + buf * kTileM;
-      stage_commit(sc, s.a_s, sm.cand_task, p.n_tasks, dq, row0, tid, regs);
-      bar_compute();
-      const float an0 = cand_sqnorm(sm, mp), an1 = cand_sqnorm(sm, mp + 64);
+      float an0 = 0.f, an1 = 0.f;
+      const float* kr0 = nullptr;
+      const float* kr1 = nullptr;
+      float4 nx[4];
+      if constexpr (PRE) {
+        if (p.task_col >= 0 && tid < kTileM) {  // task id of each candidate row (mean constant, prior variance)
+          const int64_t row = row0 + tid;
+          float tv = 0.f;
+          if (row < p.N) {
+            switch (p.layout) {
+              case BB_ROW_MAJOR_F32: tv = load_x<BB_ROW_MAJOR_F32>(p.x, row, p.task_col, p.ldx); break;
+              case BB_COL_MAJOR_F32: tv = load_x<BB_COL_MAJOR_F32>(p.x, row, p.task_col, p.ldx); break;
+              case BB_ROW_MAJOR_F64: tv = load_x<BB_ROW_MAJOR_F64>(p.x, row, p.task_col, p.ldx); break;
+              default: tv = load_x<BB_COL_MAJOR_F64>(p.x, row, p.task_col, p.ldx); break;
+            }
+          }
+          sm.cand_task[tid] = min(max(__float2int_rn(tv), 0), p.n_tasks - 1);
+        }
+        kr0 = p.kpre + (row0 + mp) * p.ldk + g * 8;
+        kr1 = kr0 + 64 * p.ldk;
+        nx[0] = __ldg(reinterpret_cast<const float4*>(kr0));
+        nx[1] = __ldg(reinterpret_cast<const float4*>(kr0) + 1);
+        nx[2] = __ldg(reinterpret_cast<const float4*>(kr1));
+        nx[3] = __ldg(reinterpret_cast<const float4*>(kr1) + 1);
+        bar_compute();
+      } else {
+        stage_commit(sc, s.a_s, sm.cand_task, p.n_tasks, dq, row0, tid, regs);
+        bar_compute();
+        an0 = cand_sqnorm(sm, mp);
+        an1 = cand_sqnorm(sm, mp + 64);
+      }
       float mean0 = 0.f, mean1 = 0.f;
       for (int c = 0; c < C; ++c) {
         float k0[8], k1[8];
         const int i0 = c * kChunk + g * 8;
-        assemble_2x8<FAMILY>(sm, mp, mp + 64, an0, an1, i0, k0, k1);
+        if constexpr (PRE) {
+          k0[0] = nx[0].x; k0[1] = nx[0].y; k0[2] = nx[0].z; k0[3] = nx[0].w;
+          k0[4] = nx[1].x; k0[5] = nx[1].y; k0[6] = nx[1].z; k0[7] = nx[1].w;
+          k1[0] = nx[2].x; k1[1] = nx[2].y; k1[2] = nx[2].z; k1[3] = nx[2].w;
+          k1[4] = nx[3].x; k1[5] = nx[3].y; k1[6] = nx[3].z; k1[7] = nx[3].w;
+          if (c + 1 < C) {  // next chunk's K* values fly under this chunk's split / ring wait
+            const float4* q0 = reinterpret_cast<const float4*>(kr0 + (c + 1) * kChunk);
+            const float4* q1 = reinterpret_cast<const float4*>(kr1 + (c + 1) * kChunk);
+            nx[0] = __ldg(q0);
+            nx[1] = __ldg(q0 + 1);
+            nx[2] = __ldg(q1);
+            nx[3] = __ldg(q1 + 1);
+          }
+        } else {
+          assemble_2x8<FAMILY>(sm, mp, mp + 64, an0, an1, i0, k0, k1);
+        }
         {
           const float4 al0 = *reinterpret_cast<const float4*>(s.alpha_s + i0);
           const float4 al1 = *reinterpret_cast<const float4*>(s.alpha_s + i0 + 4);
@@ -325,8 +373,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
       mpart[g * kTileM + mp] = mean0;
       mpart[g * kTileM + mp + 64] = mean1;
       // global loads of the next tile fly while an epilogue and its MC run
-      if (tile + (int)gridDim.x < p.num_tiles)
-        stage_prefetch(sc, dq, (int64_t)(tile + gridDim.x) * kTileM, tid, regs);
+      if constexpr (!PRE)
+        if (tile + (int)gridDim.x < p.num_tiles)
+          stage_prefetch(sc, dq, (int64_t)(tile + gridDim.x) * kTileM, tid, regs);
       if (LAG) {
         if (it > 0) epilogue(it - 1, prev_row0);
       } else {
@@ -358,16 +407,21 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
     // =====================================================================================
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
-      const int n_tiles_b = C * (C + 1) / 2;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int tb = 0; tb < n_tiles_b; ++tb) {
-          mbar_wait_relaxed(&s.b_empty[st], ph ^ 1u);
-          mbar_expect_tx(&s.b_full[st], kStageBBytes);
-          bulk_g2s(s.ring_b + (size_t)st * kStageBBytes, p.rimg + (size_t)tb * kStageBBytes,
-                   kStageBBytes, &s.b_full[st]);
-          if (++st == (uint32_t)p.stages_b) {
-            st = 0;
-            ph ^= 1u;
+        size_t off = 0;
+        for (int c = 0; c < C; ++c) {
+          for (int sb = c; sb < C;) {
+            const int gsz = (C - sb) < GMAX ? (C - sb) : GMAX;
+            const uint32_t bytes = (uint32_t)gsz * kStageBBytes;
+            mbar_wait_relaxed(&s.b_empty[st], ph ^ 1u);
+            mbar_expect_tx(&s.b_full[st], bytes);
+            bulk_g2s(s.ring_b + (size_t)st * p.stage_b_bytes, p.rimg + off, bytes, &s.b_full[st]);
+            off += bytes;
+            sb += gsz;
+            if (++st == (uint32_t)p.stages_b) {
+              st = 0;
+              ph ^= 1u;
+            }
           }
         }
       }
@@ -377,7 +431,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
     // MMA issuer: D[128 x n_pad] (TMEM, fp32) = K*[128 x n_pad] (smem, fp16 hi+lo) * Linv^T
     // =====================================================================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kTileM, kChunk);
       uint32_t slot = 0, pha = 0, st = 0, phb = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -393,13 +446,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
           const uint32_t a_addr = smem_u32(s.ring_a + (size_t)slot * kSlotABytes);
           const uint64_t a_hi = make_sw128_desc(a_addr);
           const uint64_t a_lo = make_sw128_desc(a_addr + 16384);
-          for (int sb = c; sb < C; ++sb) {
+          for (int sb = c; sb < C;) {
+            const int gsz = (C - sb) < GMAX ? (C - sb) : GMAX;
+            const uint32_t idesc = make_idesc_f16(kTileM, gsz * kChunk);
             mbar_wait_relaxed(&s.b_full[st], phb);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(s.ring_b + (size_t)st * kStageBBytes);
+            const uint32_t b_addr = smem_u32(s.ring_b + (size_t)st * p.stage_b_bytes);
             const uint64_t b_hi = make_sw128_desc(b_addr);
-            const uint64_t b_lo = make_sw128_desc(b_addr + 8192);
+            const uint64_t b_lo = make_sw128_desc(b_addr + (uint32_t)gsz * 8192u);
             const uint32_t d_addr = d_base + (uint32_t)(sb * kChunk);
+            sb += gsz;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t ko = (uint64_t)(kk * 2);  // 16 fp16 = 32 bytes = 2 x 16-byte units
@@ -430,11 +486,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
   if (warp == kWarpProducer) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-template <int FAMILY, int LAG>
+template <int FAMILY, int LAG, bool PRE = false, int GMAX = 1>
 static int launch_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
-  BB_CUDA(cudaFuncSetAttribute(k_fused<FAMILY, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BB_CUDA(cudaFuncSetAttribute(k_fused<FAMILY, LAG, PRE, GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-  k_fused<FAMILY, LAG><<<grid, kFusedThreads, smem, stream>>>(p);
+  k_fused<FAMILY, LAG, PRE, GMAX><<<grid, kFusedThreads, smem, stream>>>(p);
   BB_LAUNCH_CHECK();
   return BB_OK;
 }
@@ -442,6 +498,57 @@ static int launch_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream
 template <int FAMILY>
 static int launch_family(FusedParams& p, int lag, int grid, size_t smem, cudaStream_t stream) {
   return lag ? launch_one<FAMILY, 1>(p, grid, smem, stream) : launch_one<FAMILY, 0>(p, grid, smem, stream);
+}
+
+// Wide-feature models: per block of <= wide_ws_rows candidates, k_kmat_tc writes the K* block into the
+// (L2-sized) workspace inside the model blob and k_fused<PRE> consumes it; both on the caller's stream.
+static int launch_wide_blocks(const bb_model* m, const FusedParams& full, int lag, int sms, int max_smem,
+                              cudaStream_t stream) {
+  BB_CHECK_SUPPORTED(m->d_wide_ws != nullptr && m->wide_ws_rows >= 256, "wide model without workspace");
+  const int64_t es = (full.layout == BB_ROW_MAJOR_F64 || full.layout == BB_COL_MAJOR_F64) ? 8 : 4;
+  const bool col_major = (full.layout == BB_COL_MAJOR_F32 || full.layout == BB_COL_MAJOR_F64);
+  for (int64_t b0 = 0; b0 < full.N; b0 += m->wide_ws_rows) {
+    const int64_t nb = full.N - b0 < m->wide_ws_rows ? full.N - b0 : m->wide_ws_rows;
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(full.x);
+    if (full.layout == BB_BITS_U8) xb += b0 * full.ldx;
+    else xb += col_major ? b0 * es : b0 * full.ldx * es;
+    const int64_t rows_pad = (nb + 255) / 256 * 256;
+    int rc = launch_kmat_wide(m, xb, full.layout, nb, full.ldx, m->d_wide_ws, m->n_pad, rows_pad, m->n_pad,
+                              stream);
+    if (rc != BB_OK) return rc;
+    FusedParams p = full;
+    p.x = xb;
+    p.N = nb;
+    p.num_tiles = (int)((nb + kTileM - 1) / kTileM);
+    p.kpre = m->d_wide_ws;
+    p.ldk = m->n_pad;
+    p.d = 0;
+    p.d_pad = 0;  // nothing of the feature dimension is staged by the K*-reading kernel
+    if (p.mu) p.mu += b0;
+    if (p.var) p.var += b0;
+    if (p.score) p.score += b0;
+    if (p.keep) p.keep += b0;
+    p.index_offset = full.index_offset + b0;
+    p.rimg = reinterpret_cast<const uint8_t*>(m->d_rimg4);
+    p.stage_b_bytes = 4 * kStageBBytes;  // groups of up to four sub-blocks: N = 256 MMAs
+    p.slots_a = 2;
+    p.stages_b = 2;
+    while (true) {
+      FusedParams t = p;
+      if (t.slots_a < 3) t.slots_a++;
+      else if (t.stages_b < 3) t.stages_b++;
+      else break;
+      if (fused_smem_bytes(t) > (size_t)max_smem) break;
+      p = t;
+    }
+    const size_t smem = fused_smem_bytes(p);
+    BB_CHECK_SUPPORTED(smem <= (size_t)max_smem, "shared-memory budget exceeded: need %zu bytes", smem);
+    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    rc = lag ? launch_one<BB_KERNEL_RBF, 1, true, 4>(p, grid, smem, stream)
+             : launch_one<BB_KERNEL_RBF, 0, true, 4>(p, grid, smem, stream);
+    if (rc != BB_OK) return rc;
+  }
+  return BB_OK;
 }
 
 static long long* g_trace_buf = nullptr;
@@ -453,11 +560,13 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
                  int64_t index_offset, cudaStream_t stream) {
   BB_CHECK_ARG(m && m->abi_version == BB_ABI_VERSION, "model struct missing or ABI mismatch");
   BB_CHECK_ARG(d_x != nullptr || N == 0, "candidate pointer is null");
-  BB_CHECK_ARG(layout >= 0 && layout <= 3, "unknown candidate layout %d", layout);
+  BB_CHECK_ARG(layout >= 0 && layout <= BB_BITS_U8, "unknown candidate layout %d", layout);
   BB_CHECK_ARG(N >= 0, "negative candidate count");
+  BB_CHECK_SUPPORTED(layout != BB_BITS_U8 || m->wide,
+                     "bit-packed candidates need a wide-feature model (n_pad*d_pad*4 > 56 KB)");
   const bool col_major = (layout == BB_COL_MAJOR_F32 || layout == BB_COL_MAJOR_F64);
-  BB_CHECK_ARG(col_major ? ldx >= N : ldx >= m->d, "leading dimension %lld too small",
-               (long long)ldx);
+  BB_CHECK_ARG(layout == BB_BITS_U8 ? ldx >= (m->d + 7) / 8 : (col_major ? ldx >= N : ldx >= m->d),
+               "leading dimension %lld too small", (long long)ldx);
   BB_CHECK_ARG(N + index_offset < 0xffffffffLL, "candidate index exceeds the 32-bit key range");
   BB_CHECK_SUPPORTED(m->n_tasks <= kMaxTasks, "at most %d tasks supported", kMaxTasks);
   if (acq) {
@@ -513,6 +622,7 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   p.keep = d_keep;
   p.best_key = reinterpret_cast<long long*>(d_best_key);
   p.index_offset = index_offset;
+  p.stage_b_bytes = kStageBBytes;
   p.trace = g_trace_buf;
   p.trace_cap = g_trace_cap;
   BB_CHECK_SUPPORTED(p.n_pad <= 512, "n_pad=%d exceeds the 512 TMEM columns", p.n_pad);
@@ -525,6 +635,7 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   BB_CUDA(cudaGetDevice(&dev));
   BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (m->wide) return launch_wide_blocks(m, p, lag, sms, max_smem, stream);
   if (fused_tc_supported(p, max_smem)) {
     const int grid_tc = p.num_tiles < sms ? p.num_tiles : sms;
     return launch_fused_tc(p, grid_tc, stream);

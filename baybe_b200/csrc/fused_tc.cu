@@ -95,32 +95,6 @@ __host__ __device__ inline size_t tc_carve(uint8_t* base, const FusedParams& p, 
   return off;
 }
 
-// 16 consecutive fp32 columns of this thread's TMEM lane.
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-
-// fp16 hi/mid/lo split of four fp32 values -> three 8-byte packets.
-__device__ __forceinline__ void split3_quad(const float (&x)[4], uint2& hi, uint2& mid, uint2& lo) {
-  __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
-  float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-  const float r0 = x[0] - f01.x, r1 = x[1] - f01.y, r2 = x[2] - f23.x, r3 = x[3] - f23.y;
-  __half2 m01 = __floats2half2_rn(r0, r1), m23 = __floats2half2_rn(r2, r3);
-  float2 g01 = __half22float2(m01), g23 = __half22float2(m23);
-  __half2 l01 = __floats2half2_rn(r0 - g01.x, r1 - g01.y), l23 = __floats2half2_rn(r2 - g23.x, r3 - g23.y);
-  hi = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
-  mid = make_uint2(*reinterpret_cast<uint32_t*>(&m01), *reinterpret_cast<uint32_t*>(&m23));
-  lo = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
-}
-
 constexpr int kTcStageQuads = 4;  // d_pad <= 64 -> at most 16 quads over 4 thread groups
 
 struct TcStageRegs {

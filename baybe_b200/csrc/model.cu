@@ -29,9 +29,16 @@ const char* last_error() { return g_err; }
 struct BlobLayout {
   size_t cand_scale, cand_shift, train_m2, train_sq, alpha, train_task, task_covar, mean_const,
       rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, bimg, rimg2, flags,
-      total;
+      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, total;
   int n_pad, d_pad, n_chunks, n_tiles;
+  int wide, d_wide;
+  int64_t wide_ws_rows;
 };
+
+// The CUDA-core assembly keeps the scaled training rows in shared memory (n_pad*d_pad*4 <= 56 KB);
+// anything larger takes the K-chunked tensor-core path of wide.cu.
+constexpr size_t kResidentTrainBytes = 56 * 1024;
+constexpr int64_t kWideWsRows = 148 * 256;  // one wave of 256-row work items per SM
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -70,6 +77,20 @@ static BlobLayout make_layout(int n, int d, int T) {
   L.bimg = take((size_t)L.n_chunks * 24576);
   L.rimg2 = take((size_t)L.n_tiles * 16384);
   L.flags = take(64);
+  L.wide = ((size_t)L.n_pad * L.d_pad * 4 > kResidentTrainBytes) ? 1 : 0;
+  L.d_wide = round_up(d, 32);
+  L.wimg = L.wimg_bits = L.wnorm_bits = L.wsrc = L.wide_ws = L.rimg4 = 0;
+  L.wide_ws_rows = 0;
+  if (L.wide) {
+    const size_t img = (size_t)L.n_pad * L.d_wide * 2 * 3;
+    L.wimg = take(img);
+    L.wimg_bits = take(img);
+    L.wnorm_bits = take(sizeof(float) * L.n_pad);
+    L.wsrc = take(sizeof(float) * (size_t)L.n_pad * L.d_wide);
+    L.rimg4 = take((size_t)L.n_tiles * 16384);
+    L.wide_ws_rows = kWideWsRows;
+    L.wide_ws = take(sizeof(float) * (size_t)L.wide_ws_rows * L.n_pad);
+  }
   L.total = off;
   return L;
 }
@@ -257,8 +278,15 @@ __global__ void k_build_rimg(const double* __restrict__ Linv, int n, int n_chunk
 // leading single tile if c is odd, then pairs (s, s+1) with s even, then a trailing single.
 // A pair block is [hi: 128 rows x 64 k | lo: same] = 32 KB, a single block [hi 8 KB | lo 8 KB];
 // blocks follow each other in consumption order.  One CTA per block (blockIdx.x = group index).
+// gmax = 2: aligned pairs as described above (fused_tc); gmax = 4: greedy groups of up to four
+// sub-blocks starting at s = c (N = 256 MMAs; the K*-reading kernel of the wide path).
+__host__ __device__ inline int rimg_group(int gmax, int s, int n_chunks) {
+  if (gmax == 2) return ((s & 1) == 0 && s + 1 < n_chunks) ? 2 : 1;
+  return (n_chunks - s) < gmax ? (n_chunks - s) : gmax;
+}
+
 __global__ void k_build_rimg2(const double* __restrict__ Linv, int n, int n_chunks, double scale,
-                              uint8_t* __restrict__ rimg2) {
+                              int gmax, uint8_t* __restrict__ rimg2) {
   // decode group -> (c, first sub-block s, size g) and byte offset
   int grp = blockIdx.x, c = 0, s0 = 0, g = 1;
   size_t off = 0;
@@ -267,7 +295,7 @@ __global__ void k_build_rimg2(const double* __restrict__ Linv, int n, int n_chun
   for (c = 0; c < n_chunks && !found; ++c) {
     int s = c;
     while (s < n_chunks) {
-      const int gg = ((s & 1) == 0 && s + 1 < n_chunks) ? 2 : 1;
+      const int gg = rimg_group(gmax, s, n_chunks);
       if (idx == grp) {
         s0 = s;
         g = gg;
@@ -316,6 +344,32 @@ __global__ void k_build_bimg(const float* __restrict__ train_m2, int n_pad, int 
     *reinterpret_cast<__half*>(bimg + off) = h;
     *reinterpret_cast<__half*>(bimg + split + off) = m;
     *reinterpret_cast<__half*>(bimg + 2 * split + off) = l;
+  }
+}
+
+// K-chunked fp16 hi/mid/lo image of scale * src[n_pad][d_wide] for wide.cu: per (256-row half,
+// 32-column K stage) `panels` panels [hi | mid (| lo)], each [ncols rows][32 fp16], 64-byte rows,
+// SWIZZLE_64B, 8-row groups contiguous -- one contiguous bulk copy per stage.
+__global__ void k_build_wimg(const float* __restrict__ src, int n_pad, int d_wide, float scale,
+                             int panels, uint8_t* __restrict__ img) {
+  const int n_kc = d_wide / 32;
+  const size_t total = (size_t)n_pad * d_wide;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / d_wide), k = (int)(e - (size_t)i * d_wide);
+    const int half = i >> 8, il = i & 255;
+    const int ncols = min(256, n_pad - half * 256);
+    const int kc = k >> 5, kl = k & 31;
+    const size_t panel = (size_t)ncols * 64;
+    const size_t base = (size_t)half * n_kc * ((size_t)panels * 256 * 64) + (size_t)kc * panels * panel;
+    const uint32_t off = swk_offset<32>((uint32_t)il, (uint32_t)(kl >> 3)) + (uint32_t)(kl & 7) * 2u;
+    const float v = src[e] * scale;
+    const __half h = __float2half_rn(v);
+    const float r1 = v - __half2float(h);
+    const __half m = __float2half_rn(r1);
+    const __half l = __float2half_rn(r1 - __half2float(m));
+    *reinterpret_cast<__half*>(img + base + off) = h;
+    *reinterpret_cast<__half*>(img + base + panel + off) = m;
+    if (panels > 2) *reinterpret_cast<__half*>(img + base + 2 * panel + off) = l;
   }
 }
 
@@ -430,12 +484,6 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
               bb_model_blob_bytes(n, d, T));
     return BB_ERR_WORKSPACE;
   }
-  // the scoring kernel keeps the scaled training rows resident in shared memory
-  BB_CHECK_SUPPORTED((size_t)L.n_pad * L.d_pad * 4 <= 56 * 1024,
-                     "bb_model_build: n_pad*d_pad = %d*%d floats exceeds the 56 KB shared-memory "
-                     "budget of the scoring kernel",
-                     L.n_pad, L.d_pad);
-
   // ---- host-side parameter packing (float64): Normalize / Standardize / ARD folding ----
   const double kfam = desc->family == BB_KERNEL_MATERN52   ? 5.0
                       : desc->family == BB_KERNEL_MATERN32 ? 3.0
@@ -600,8 +648,15 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
         sb += g;
         ++n_groups;
       }
-    k_build_rimg2<<<n_groups, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, B + L.rimg2);
+    k_build_rimg2<<<n_groups, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, 2, B + L.rimg2);
     BB_LAUNCH_CHECK();
+    if (L.wide) {
+      int n_groups4 = 0;
+      for (int c = 0; c < L.n_chunks; ++c)
+        for (int sb = c; sb < L.n_chunks; sb += rimg_group(4, sb, L.n_chunks)) ++n_groups4;
+      k_build_rimg2<<<n_groups4, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, 4, B + L.rimg4);
+      BB_LAUNCH_CHECK();
+    }
   }
   int dist_k = 0;
   if (L.d_pad <= 32) {
@@ -614,6 +669,41 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
     k_build_bimg<64><<<L.n_chunks, 256, 0, stream>>>((const float*)(B + L.train_m2), L.n_pad,
                                                      L.d_pad, dist_scale_b, B + L.bimg);
     BB_LAUNCH_CHECK();
+  }
+
+  float dist_scale_w = 1.0f;
+  if (L.wide) {
+    // float layouts: B = -2 b (same numbers as d_train_m2, K-chunked)
+    std::vector<float> src((size_t)L.n_pad * L.d_wide, 0.f);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < d; ++j) src[(size_t)i * L.d_wide + j] = tm2[(size_t)i * L.d_pad + j];
+    BB_CUDA(up(L.wsrc, src.data(), src.size() * 4));
+    k_build_wimg<<<296, 256, 0, stream>>>((const float*)(B + L.wsrc), L.n_pad, L.d_wide, dist_scale_b,
+                                          3, B + L.wimg);
+    BB_LAUNCH_CHECK();
+    BB_CUDA(cudaStreamSynchronize(stream));
+    // bit-packed layout: t = sum_j x_j W_ij + c_i with a_j = s_j x_j + h_j, x_j in {0,1}
+    std::vector<float> cvec(L.n_pad, 0.f);
+    float w_abs_max = 1e-30f;
+    for (int i = 0; i < n; ++i) {
+      double c = (double)tsq[i];
+      for (int j = 0; j < d; ++j) {
+        const double sj = cscale[j], hj = cshift[j], m2 = tm2[(size_t)i * L.d_pad + j];
+        const float w = (float)(sj * (m2 + sj + 2.0 * hj));
+        src[(size_t)i * L.d_wide + j] = w;
+        w_abs_max = fmaxf(w_abs_max, fabsf(w));
+        c += hj * (m2 + hj);
+      }
+      cvec[i] = (float)c;
+    }
+    if (!(w_abs_max > 1e-6f)) w_abs_max = 1.0f;
+    dist_scale_w = ldexpf(1.0f, (int)floorf(log2f(30000.0f / w_abs_max)));
+    BB_CUDA(up(L.wsrc, src.data(), src.size() * 4));
+    BB_CUDA(up(L.wnorm_bits, cvec.data(), cvec.size() * 4));
+    k_build_wimg<<<296, 256, 0, stream>>>((const float*)(B + L.wsrc), L.n_pad, L.d_wide, dist_scale_w,
+                                          2, B + L.wimg_bits);
+    BB_LAUNCH_CHECK();
+    BB_CUDA(cudaStreamSynchronize(stream));
   }
 
   memset(out, 0, sizeof(*out));
@@ -652,6 +742,17 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
   out->dist_scale_b = dist_scale_b;
   out->dist_k = dist_k;
   out->d_rimg2 = B + L.rimg2;
+  out->wide = L.wide;
+  out->d_wide = L.d_wide;
+  if (L.wide) {
+    out->d_wimg = B + L.wimg;
+    out->d_wimg_bits = B + L.wimg_bits;
+    out->d_wnorm_bits = (const float*)(B + L.wnorm_bits);
+    out->d_wide_ws = (float*)(B + L.wide_ws);
+    out->d_rimg4 = B + L.rimg4;
+    out->wide_ws_rows = L.wide_ws_rows;
+    out->dist_scale_w = dist_scale_w;
+  }
   BB_CUDA(cudaStreamSynchronize(stream));
   return BB_OK;
 }

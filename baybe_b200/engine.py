@@ -101,8 +101,12 @@ def _layout_of(x: torch.Tensor) -> tuple[int, int]:
     column-major (the reference hands BoTorch a float64 column-major matrix,
     baybe/utils/dataframe.py:68-81)."""
     n, d = x.shape
+    if x.dtype == torch.uint8:  # bit-packed binary features: rows of bytes
+        if n > 1 and x.stride(1) != 1:
+            raise ValueError("bit-packed candidate rows must be contiguous")
+        return (_lib.LAYOUT["bits_u8"], int(x.stride(0)) if n > 1 else d)
     if x.dtype not in (torch.float32, torch.float64):
-        raise ValueError(f"candidate dtype must be float32 or float64, got {x.dtype}")
+        raise ValueError(f"candidate dtype must be float32, float64 or uint8 (bit-packed), got {x.dtype}")
     f64 = x.dtype == torch.float64
     s0, s1 = x.stride()
     if n <= 1 or d <= 1 or (s1 == 1 and s0 >= d):
@@ -118,6 +122,10 @@ def _layout_of(x: torch.Tensor) -> tuple[int, int]:
 def _as_device_matrix(x, device: torch.device, d: int) -> torch.Tensor:
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(x)
+    if x.dim() == 2 and x.dtype == torch.uint8:  # bit-packed rows (BB_BITS_U8)
+        if x.shape[1] != (d + 7) // 8:
+            raise ValueError(f"expected a bit-packed (N, {(d + 7) // 8}) uint8 matrix, got {tuple(x.shape)}")
+        return x.to(device, non_blocking=True).contiguous()
     if x.dim() != 2 or x.shape[1] != d:
         raise ValueError(f"expected a (N, {d}) candidate matrix, got {tuple(x.shape)}")
     if x.dtype not in (torch.float32, torch.float64):

@@ -119,6 +119,37 @@ def task_workload(N_per_task: int, n_tasks: int = 4, d_num: int = 20, n_per_task
     )
 
 
+def fingerprint_workload(N: int, d: int = 2048, n: int = 512, density: float = 0.05, seed: int = 0,
+                         family: str = "rbf", ls_factor: float = 0.4, outputscale: float | None = 1.0,
+                         noise: float | None = None) -> Workload:
+    """BASELINE config 4 generator: binary substance fingerprints X ~ Bernoulli(density)
+    of width d, n training rows subsampled from them, ScaleKernel(RBF) with ARD lengthscale
+    sqrt(d) * ls_factor on every bit.  The target is a smooth function of 16 random bit-group counts.
+    ``candidates`` holds the unpacked 0/1 matrix (float64); ``pack_bits`` gives the device layout."""
+    rng = np.random.default_rng(seed)
+    cand = (rng.random((N, d)) < density).astype(np.float64)
+    n = min(n, N)
+    idx = rng.choice(N, size=n, replace=False)
+    tx = cand[idx]
+    groups = rng.integers(0, 16, size=d)
+    feats = np.stack([tx[:, groups == g].sum(axis=1) for g in range(16)], axis=1)
+    feats = feats / max(1.0, density * d / 16.0) / 2.0  # ~0.5 on average
+    ty = smooth_target(np.clip(feats, 0.0, 1.0)) + 0.01 * rng.standard_normal(n)
+    return Workload(
+        name=f"fingerprint{d}_N{N}_n{n}_{family}",
+        candidates=cand, train_idx=idx, train_x=tx, train_y=ty,
+        bounds=np.stack([np.zeros(d), np.ones(d)]), family=family,
+        lengthscale=np.full(d, math.sqrt(d) * ls_factor),
+        noise=np.array([PRIOR_MODE_NOISE if noise is None else noise]),
+        mean_const=np.array([0.0]), outputscale=outputscale,
+    )
+
+
+def pack_bits(x01: np.ndarray) -> np.ndarray:
+    """(N, d) 0/1 matrix -> (N, ceil(d/8)) uint8, feature j in bit (j & 7) of byte j >> 3 (BB_BITS_U8)."""
+    return np.packbits(np.asarray(x01) != 0, axis=1, bitorder="little")
+
+
 def mixed_small_workload(seed: int = 0) -> Workload:
     """BASELINE config 1 shape: 3 parameters (one-hot categorical with 3 levels, two numerical
     with 8 levels) -> ~192 candidates in 5 comp-rep columns, 15 training points."""

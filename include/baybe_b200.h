@@ -53,7 +53,9 @@ typedef enum bb_layout {
   BB_ROW_MAJOR_F32 = 0,
   BB_COL_MAJOR_F32 = 1,
   BB_ROW_MAJOR_F64 = 2,
-  BB_COL_MAJOR_F64 = 3
+  BB_COL_MAJOR_F64 = 3,
+  BB_BITS_U8 = 4 /* bit-packed binary features (substance fingerprints, BASELINE config 4): row r is
+                    ldx BYTES at d_x + r*ldx, feature j = (byte[j>>3] >> (j&7)) & 1; wide models only */
 } bb_layout;
 
 /* Acquisition kinds, named by the reference's abbreviations (baybe/acquisition/acqfs.py). */
@@ -135,6 +137,18 @@ typedef struct bb_model {
   int32_t dist_k;            /* K extent of the d_bimg tiles: 32 (d_pad<=32), 64, or 0 = none */
   int32_t pad_;
   const void* d_rimg2;       /* L^-1 image grouped in 128-column pair tiles (fused_tc kernel)   */
+  /* wide-feature path (n_pad*d_pad*4 > 56 KB, e.g. fingerprint spaces): K-chunked operand images of
+   * the tensor-core distance GEMM and an L2-sized K* workspace, all inside the blob */
+  int32_t wide;              /* 1: scoring runs k_kmat_tc + the K*-reading posterior kernel     */
+  int32_t d_wide;            /* d rounded up to 32 (K extent of the images)                     */
+  const void* d_wimg;        /* fp16 hi/mid/lo image of (-2 x) scaled training rows             */
+  const void* d_wimg_bits;   /* same for the bit-linear form t = sum_j x_j W_ij + c_i           */
+  const float* d_wnorm_bits; /* [n_pad] c_i                                                     */
+  float* d_wide_ws;          /* [wide_ws_rows * n_pad] fp32 K* block                            */
+  int64_t wide_ws_rows;
+  float dist_scale_w;        /* power-of-two scale folded into d_wimg_bits                      */
+  int32_t pad2_;
+  const void* d_rimg4;       /* L^-1 image grouped in <=256-column tiles (K*-reading kernel)    */
 } bb_model;
 
 /* Acquisition context built by BotorchAcquisitionFunctionBuilder.build
