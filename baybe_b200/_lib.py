@@ -55,7 +55,7 @@ class Model(C.Structure):
         ("wide", C.c_int32), ("d_wide", C.c_int32), ("d_wimg", C.c_void_p),
         ("d_wimg_bits", C.c_void_p), ("d_wnorm_bits", C.c_void_p), ("d_wide_ws", C.c_void_p),
         ("wide_ws_rows", C.c_int64), ("dist_scale_w", C.c_float), ("pad2_", C.c_int32),
-        ("d_rimg4", C.c_void_p),
+        ("d_rimg4", C.c_void_p), ("d_rimg2g", C.c_void_p),
     ]
 
 

@@ -497,7 +497,9 @@ static int launch_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream
 
 template <int FAMILY>
 static int launch_family(FusedParams& p, int lag, int grid, size_t smem, cudaStream_t stream) {
-  return lag ? launch_one<FAMILY, 1>(p, grid, smem, stream) : launch_one<FAMILY, 0>(p, grid, smem, stream);
+  if (lag) return launch_one<FAMILY, 1>(p, grid, smem, stream);
+  return p.stage_b_bytes == 2 * kStageBBytes ? launch_one<FAMILY, 0, false, 2>(p, grid, smem, stream)
+                                             : launch_one<FAMILY, 0>(p, grid, smem, stream);
 }
 
 // Wide-feature models: per block of <= wide_ws_rows candidates, k_kmat_tc writes the K* block into the
@@ -639,6 +641,17 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   if (fused_tc_supported(p, max_smem)) {
     const int grid_tc = p.num_tiles < sms ? p.num_tiles : sms;
     return launch_fused_tc(p, grid_tc, stream);
+  }
+  // n_pad > 256 (single accumulator): pair the L^-1 sub-blocks (N = 128 MMAs) when two 32 KB stages fit
+  if (!lag && m->d_rimg2g != nullptr) {
+    FusedParams t = p;
+    t.slots_a = 2;
+    t.stages_b = 2;
+    t.stage_b_bytes = 2 * kStageBBytes;
+    if (fused_smem_bytes(t) <= (size_t)max_smem) {
+      p.stage_b_bytes = 2 * kStageBBytes;
+      p.rimg = reinterpret_cast<const uint8_t*>(m->d_rimg2g);
+    }
   }
   // ring sizes: as many as fit, B stages first (they hide L2 latency), then A slots
   p.slots_a = 2;

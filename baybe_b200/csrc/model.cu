@@ -10,6 +10,8 @@
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bb {
@@ -29,7 +31,7 @@ const char* last_error() { return g_err; }
 struct BlobLayout {
   size_t cand_scale, cand_shift, train_m2, train_sq, alpha, train_task, task_covar, mean_const,
       rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, bimg, rimg2, flags,
-      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, total;
+      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, rimg2g, total;
   int n_pad, d_pad, n_chunks, n_tiles;
   int wide, d_wide;
   int64_t wide_ws_rows;
@@ -77,7 +79,9 @@ static BlobLayout make_layout(int n, int d, int T) {
   L.bimg = take((size_t)L.n_chunks * 24576);
   L.rimg2 = take((size_t)L.n_tiles * 16384);
   L.flags = take(64);
+  L.rimg2g = L.n_chunks > 4 ? take((size_t)L.n_tiles * 16384) : 0;
   L.wide = ((size_t)L.n_pad * L.d_pad * 4 > kResidentTrainBytes) ? 1 : 0;
+  if (const char* f = getenv("BAYBE_B200_FORCE_WIDE")) L.wide = (f[0] == '1') ? 1 : L.wide;  // experiments
   L.d_wide = round_up(d, 32);
   L.wimg = L.wimg_bits = L.wnorm_bits = L.wsrc = L.wide_ws = L.rimg4 = 0;
   L.wide_ws_rows = 0;
@@ -280,9 +284,11 @@ __global__ void k_build_rimg(const double* __restrict__ Linv, int n, int n_chunk
 // blocks follow each other in consumption order.  One CTA per block (blockIdx.x = group index).
 // gmax = 2: aligned pairs as described above (fused_tc); gmax = 4: greedy groups of up to four
 // sub-blocks starting at s = c (N = 256 MMAs; the K*-reading kernel of the wide path).
+// gmax = -2: greedy groups of two (k_fused with N = 128 MMAs when n_pad > 256).
 __host__ __device__ inline int rimg_group(int gmax, int s, int n_chunks) {
   if (gmax == 2) return ((s & 1) == 0 && s + 1 < n_chunks) ? 2 : 1;
-  return (n_chunks - s) < gmax ? (n_chunks - s) : gmax;
+  const int g = gmax < 0 ? -gmax : gmax;
+  return (n_chunks - s) < g ? (n_chunks - s) : g;
 }
 
 __global__ void k_build_rimg2(const double* __restrict__ Linv, int n, int n_chunks, double scale,
@@ -650,6 +656,13 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
       }
     k_build_rimg2<<<n_groups, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, 2, B + L.rimg2);
     BB_LAUNCH_CHECK();
+    if (L.n_chunks > 4) {  // n_pad > 256: k_fused pairs the V sub-blocks greedily
+      int n_groups2 = 0;
+      for (int c = 0; c < L.n_chunks; ++c)
+        for (int sb = c; sb < L.n_chunks; sb += rimg_group(-2, sb, L.n_chunks)) ++n_groups2;
+      k_build_rimg2<<<n_groups2, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, -2, B + L.rimg2g);
+      BB_LAUNCH_CHECK();
+    }
     if (L.wide) {
       int n_groups4 = 0;
       for (int c = 0; c < L.n_chunks; ++c)
@@ -742,6 +755,7 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
   out->dist_scale_b = dist_scale_b;
   out->dist_k = dist_k;
   out->d_rimg2 = B + L.rimg2;
+  out->d_rimg2g = L.n_chunks > 4 ? B + L.rimg2g : nullptr;
   out->wide = L.wide;
   out->d_wide = L.d_wide;
   if (L.wide) {

@@ -149,6 +149,7 @@ typedef struct bb_model {
   float dist_scale_w;        /* power-of-two scale folded into d_wimg_bits                      */
   int32_t pad2_;
   const void* d_rimg4;       /* L^-1 image grouped in <=256-column tiles (K*-reading kernel)    */
+  const void* d_rimg2g;      /* L^-1 image in greedy 128-column pairs (k_fused, n_pad > 256), or NULL */
 } bb_model;
 
 /* Acquisition context built by BotorchAcquisitionFunctionBuilder.build

@@ -64,6 +64,17 @@ def main():
     t_k2 = timed(lambda: gp2.kernel_matrix(x[:262144]))
     out.append(dict(case="float_d128_n256", N=N2, ms_score=t_s2, cand_per_s=N2 / t_s2 * 1e3, ms_kmat_262k=t_k2,
                     kmat_mma_tflops=6 * 262144 * 2.0 * 256 * 128 / t_k2 / 1e9))
+    del x, gp2
+    # ---- config 5: 4 tasks x 250k, d = 20 + task column, n = 512 ----
+    from baybe_b200.synthetic import task_workload
+    w5 = task_workload(N_per_task=250_000, n_tasks=4, d_num=20, n_per_task=128, seed=0)
+    gp5 = DeviceGP(device=dev, **w5.gp_kwargs())
+    x5 = torch.from_numpy(w5.candidates).to(dev, torch.float32)
+    acq5 = AcqConfig(kind="qLogEI", best_f=gp5.best_f(AcqConfig(kind="qLogEI")))
+    t_s5 = timed(lambda: gp5.score(acq5, x5, z, want_scores=False))
+    t_p5 = timed(lambda: gp5.posterior(x5))
+    out.append(dict(case="cfg5_tasks", wide=int(gp5.model.wide), N=x5.shape[0], ms_score=t_s5, ms_posterior=t_p5,
+                    cand_per_s=x5.shape[0] / t_s5 * 1e3))
     for o in out:
         print(json.dumps(o))
 
