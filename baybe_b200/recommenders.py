@@ -29,6 +29,7 @@ from attrs.converters import optional
 
 from baybe_b200.acquisition import (AcquisitionFunction, IncompatibleAcquisitionFunctionError,
                                     convert_acqf, qLogExpectedImprovement)
+from baybe_b200.bits import pack_bits
 from baybe_b200.engine import DEFAULT_MC_SAMPLES, AcqConfig, DeviceGP, sobol_normal_samples, unpack_best
 from baybe_b200.surrogates import GaussianProcessSurrogate
 
@@ -112,6 +113,11 @@ def greedy_select(gp: DeviceGP, cfg: AcqConfig, x_shard: torch.Tensor, x_all_hos
     return chosen, values
 
 
+# comp-reps that are all 0/1 and at least this wide (always a wide-feature model: n_pad*d*4 > 56 KB) are kept
+# bit-packed on the device
+BITS_MIN_COLUMNS = 256
+
+
 class _DeviceCache:
     """comp-rep matrices resident on the GPU, keyed by the identity of the subspace's cached
     ``comp_rep`` dataframe (attrs classes with ``eq=True`` are unhashable, dataframes are
@@ -126,7 +132,12 @@ class _DeviceCache:
         entry = self._store.get(key)
         if entry is None or entry[0]() is not comp_df or entry[1] != (str(device), lo, hi):
             host = np.ascontiguousarray(comp_df.to_numpy(dtype=np.float64))
-            dev = torch.from_numpy(host[lo:hi]).to(device=device, dtype=torch.float32)
+            shard = host[lo:hi]
+            if host.shape[1] >= BITS_MIN_COLUMNS and bool(((shard == 0.0) | (shard == 1.0)).all()):
+                # binary fingerprint space: 1 bit per feature on the device (BB_BITS_U8), 32x less HBM
+                dev = torch.from_numpy(pack_bits(shard)).to(device=device)
+            else:
+                dev = torch.from_numpy(shard).to(device=device, dtype=torch.float32)
             ref = weakref.ref(comp_df, lambda _r, k=key: self._store.pop(k, None))
             entry = (ref, (str(device), lo, hi), dev, host)
             self._store[key] = entry

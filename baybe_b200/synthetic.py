@@ -9,6 +9,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
+from baybe_b200.bits import pack_bits  # noqa: F401  (re-exported for tests and bench)
+
 
 @dataclass
 class Workload:
@@ -143,11 +145,6 @@ def fingerprint_workload(N: int, d: int = 2048, n: int = 512, density: float = 0
         noise=np.array([PRIOR_MODE_NOISE if noise is None else noise]),
         mean_const=np.array([0.0]), outputscale=outputscale,
     )
-
-
-def pack_bits(x01: np.ndarray) -> np.ndarray:
-    """(N, d) 0/1 matrix -> (N, ceil(d/8)) uint8, feature j in bit (j & 7) of byte j >> 3 (BB_BITS_U8)."""
-    return np.packbits(np.asarray(x01) != 0, axis=1, bitorder="little")
 
 
 def mixed_small_workload(seed: int = 0) -> Workload:

@@ -13,7 +13,8 @@ from pathlib import Path
 import numpy as np
 
 import oracle
-from baybe_b200.synthetic import mixed_small_workload, numeric_grid_workload, task_workload
+from baybe_b200.synthetic import (fingerprint_workload, mixed_small_workload, numeric_grid_workload,
+                                  task_workload)
 from tests.helpers import oracle_model
 
 HERE = Path(__file__).parent
@@ -21,6 +22,8 @@ WORKLOADS = {
     "cfg1": mixed_small_workload,
     "cfg2_slice": lambda: numeric_grid_workload(N=512, d=20, n=256),
     "task": lambda: task_workload(N_per_task=96, n_tasks=4, d_num=6, n_per_task=24, seed=2),
+    # BASELINE config 4 shape (2048-bit fingerprints, n = 512, ScaleKernel(RBF)) at 600 candidates
+    "cfg4_slice": lambda: fingerprint_workload(N=600, d=2048, n=512, seed=1),
 }
 ROWS = 48
 

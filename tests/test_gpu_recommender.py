@@ -146,3 +146,37 @@ def test_full_fit_and_transfer_learning_space(cuda_device):
     assert list(out.index) == list(ss.discrete.comp_rep.index[idx])
     with pytest.raises(NotEnoughPointsLeftError):
         rec.recommend(10_000, ss, obj, meas)
+
+
+def test_recommend_on_binary_fingerprint_space_uses_bit_layout(cuda_device):
+    """A comp-rep that is all 0/1 and >= 256 columns wide is kept bit-packed on the device and scored by
+    the wide-feature path; the recommendation equals the oracle's arg-max over the float matrix."""
+    from baybe_b200 import recommenders as R
+
+    rng = np.random.default_rng(5)
+    d, N, n = 320, 1500, 40
+    bits = (rng.random((N, d)) < 0.1).astype(np.float64)
+    cols = [f"b{j}" for j in range(d)]
+    df = pd.DataFrame(bits, columns=cols)
+    ss = SearchSpace.from_dataframe(df, [NumericalDiscreteParameter(c, [0.0, 1.0]) for c in cols])
+    rows = ss.discrete.exp_rep.sample(n=n, random_state=1)
+    comp = ss.transform(rows).to_numpy()
+    y = comp[:, :40].sum(axis=1) - 0.5 * comp[:, 40:80].sum(axis=1) + 0.05 * rng.standard_normal(n)
+    meas = rows.assign(Yield=y)
+    hp = {"family": "rbf", "lengthscale": np.full(d, 6.0), "noise": 0.01, "mean_const": 0.0, "outputscale": 1.3}
+    obj = SingleTargetObjective(NumericalTarget("Yield"))
+    rec = B200Recommender(surrogate_model=GaussianProcessSurrogate(hyperparameters=hp))
+    torch.manual_seed(11)
+    out = rec.recommend(1, ss, obj, meas)
+    x_dev, _ = R._cache.get(ss.discrete, cuda_device, 0, N)
+    assert x_dev.dtype == torch.uint8 and x_dev.shape == (N, d // 8)
+    torch.manual_seed(11)
+    seed = int(torch.randint(0, 1_000_000, (1,)))
+    spec = oracle.KernelSpec("rbf", hp["lengthscale"], list(range(d)), outputscale=1.3)
+    om = oracle.build_model(spec, comp, meas["Yield"].to_numpy(), ss.scaling_bounds.to_numpy(), noise=0.01,
+                            mean_const=0.0)
+    acq = oracle.AcqSpec("qLogEI")
+    acq.best_f = oracle.best_f_from_training(om, comp, acq)
+    idx, vals = oracle.optimize_acqf_discrete(om, acq, ss.discrete.comp_rep.to_numpy(), q=1, sampler_seed=seed)
+    assert list(out.index) == list(ss.discrete.comp_rep.index[idx])
+    assert np.allclose(rec._last_acq_values, vals, rtol=2e-3, atol=5e-3)

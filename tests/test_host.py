@@ -118,3 +118,26 @@ def test_surrogate_and_recommender_fail_loudly_without_fit_or_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             r.recommend(1, ss, obj, meas)
+
+
+def test_bit_packing_round_trip_and_layout():
+    """BB_BITS_U8: feature j lives in bit (j & 7) of byte j >> 3; padding bits of the last byte are 0."""
+    from baybe_b200.bits import pack_bits, unpack_bits
+
+    rng = np.random.default_rng(0)
+    x = (rng.random((37, 77)) < 0.3).astype(np.float64)
+    p = pack_bits(x)
+    assert p.dtype == np.uint8 and p.shape == (37, 10)
+    assert np.array_equal(unpack_bits(p, 77), x)
+    j = 13
+    assert np.array_equal((p[:, j >> 3] >> (j & 7)) & 1, x[:, j].astype(np.uint8))
+    assert (p[:, -1] >> 5 == 0).all()  # 77 = 9*8 + 5 valid bits in the last byte
+
+
+def test_fingerprint_workload_shape():
+    from baybe_b200.synthetic import fingerprint_workload
+
+    w = fingerprint_workload(N=300, d=256, n=64, seed=3)
+    assert w.candidates.shape == (300, 256) and set(np.unique(w.candidates)) <= {0.0, 1.0}
+    assert w.family == "rbf" and w.outputscale == 1.0 and w.train_x.shape == (64, 256)
+    assert np.allclose(w.lengthscale, np.sqrt(256) * 0.4)

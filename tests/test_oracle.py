@@ -198,7 +198,7 @@ def test_sobol_base_samples_are_reproducible_standard_normal():
     assert torch.isfinite(z).all()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2_slice", "task"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_slice", "task", "cfg4_slice"])
 def test_golden_fixtures(name):
     """Committed fixtures (generated by tests/golden/make_golden.py from this oracle) pin the
     oracle against silent drift; they are not reference outputs (parity unpinned)."""
