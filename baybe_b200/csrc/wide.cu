@@ -44,7 +44,7 @@ struct WideParams {
   int task_col, n_tasks, scaled;
   float* out;
   int64_t ldk, out_rows;
-  int out_cols, vec_ok;
+  int out_cols, vec_ok, bits_vec;
   int num_items, stages;
 };
 
@@ -191,19 +191,42 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_kmat_tc(const WideParams p
       double an = 0.0;
       float cur[16];
       uint32_t curb = 0;
-      if constexpr (BITS) curb = wide_load_bits16(p, row, kh * 16);
+      // bit rows 16-byte aligned: one 128-bit load covers four K stages and is issued four stages ahead
+      // (a one-stage-ahead load would put a full L2/HBM latency on every stage of the staging warps)
+      uint4 cur4 = make_uint4(0u, 0u, 0u, 0u), nxt4 = cur4;
+      const uint4* brow = nullptr;
+      if constexpr (BITS) {
+        if (p.bits_vec) {
+          if (row < p.N) brow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + row * p.ldx);
+          if (brow != nullptr) {
+            cur4 = __ldg(brow);
+            if (p.n_kc > 4) nxt4 = __ldg(brow + 1);
+          }
+        } else {
+          curb = wide_load_bits16(p, row, kh * 16);
+        }
+      }
       else wide_load16(p, row, kh * 16, cur);
       for (int kc = 0; kc < p.n_kc; ++kc) {
         const int k0 = kc * kWK + kh * 16;
         uint4 pk[PA][2];
         if constexpr (BITS) {
+          if (p.bits_vec) {
+            const int sub = kc & 3;
+            const uint32_t word = sub == 0 ? cur4.x : sub == 1 ? cur4.y : sub == 2 ? cur4.z : cur4.w;
+            curb = (word >> (kh * 16)) & 0xffffu;
+            if (sub == 3) {
+              cur4 = nxt4;
+              if (brow != nullptr && kc + 5 < p.n_kc) nxt4 = __ldg(brow + ((kc + 5) >> 2));
+            }
+          }
           uint32_t w[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e)
             w[e] = (((curb >> (2 * e)) & 1u) * 0x3C00u) | (((curb >> (2 * e + 1)) & 1u) * 0x3C000000u);
           pk[0][0] = make_uint4(w[0], w[1], w[2], w[3]);
           pk[0][1] = make_uint4(w[4], w[5], w[6], w[7]);
-          if (kc + 1 < p.n_kc) curb = wide_load_bits16(p, row, k0 + kWK);
+          if (!p.bits_vec && kc + 1 < p.n_kc) curb = wide_load_bits16(p, row, k0 + kWK);
         } else {
           float a[16];
 #pragma unroll
@@ -436,6 +459,7 @@ int launch_kmat_wide(const bb_model* m, const void* d_x, int32_t layout, int64_t
   p.out_cols = out_cols;
   p.vec_ok = ((ldk & 3) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) ? 1 : 0;
   p.num_items = (int)((N + kWTileM - 1) / kWTileM) * p.n_halves;
+  p.bits_vec = (bits && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (m->d & 127) == 0) ? 1 : 0;
   int dev = 0, max_smem = 0, sms = 0;
   BB_CUDA(cudaGetDevice(&dev));
   BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

@@ -98,3 +98,49 @@ def test_streamed_host_matrix_equals_resident_scoring(cuda_device):
 def test_config5_four_tasks_one_million_candidates(cuda_device):
     w = task_workload(N_per_task=250_000, n_tasks=4, d_num=20, n_per_task=64, seed=0)
     _check_fullsize(w, cuda_device, n_shards=4)
+
+
+def test_config4_shard_bit_packed_fingerprints(cuda_device):
+    """One GPU's shard of BASELINE config 4 (10M x 2048-bit fingerprints over 8 GPUs = 1.25M rows here,
+    n = 512, ScaleKernel(RBF), qLogEI) through the wide-feature path: oracle spot-check on 1024 random
+    rows, arg-max consistency, shard/offset invariance, determinism, duplicated rows score identically."""
+    from baybe_b200.bits import unpack_bits
+    from baybe_b200.synthetic import fingerprint_workload
+
+    dev = cuda_device
+    N = 1_250_000
+    w = fingerprint_workload(N=4096, d=2048, n=512, seed=1)
+    om = oracle_model(w)
+    gp = DeviceGP(device=dev, **w.gp_kwargs())
+    assert gp.model.wide == 1
+    g = torch.Generator(device="cuda").manual_seed(0)
+    bits = torch.rand((N, 256, 8), device=dev, generator=g) < 0.05
+    packed = (bits.to(torch.uint8) << torch.arange(8, device=dev, dtype=torch.uint8)).sum(dim=2).to(torch.uint8)
+    del bits
+    packed[N - 1] = packed[17]  # duplicates far apart (different blocks of the K* workspace)
+    packed[N // 2] = packed[17]
+    z = sobol_normal_samples(512, 1, seed=1234)
+    oacq = oracle.AcqSpec("qLogEI")
+    oacq.best_f = oracle.best_f_from_training(om, w.train_x, oacq)
+    acq = AcqConfig(kind="qLogEI", best_f=gp.best_f(AcqConfig(kind="qLogEI")))
+    scores, key = gp.score(acq, packed, z[:, 0])
+    val, idx = decode_best(key)
+    assert idx == int(torch.argmax(scores).item()) and val == float(scores[idx].item())
+    assert torch.isfinite(scores).all()
+    assert scores[17] == scores[N - 1] == scores[N // 2]
+    rows = np.random.default_rng(0).choice(N, size=1024, replace=False)
+    sub = unpack_bits(packed[torch.from_numpy(rows).to(dev)].cpu().numpy(), 2048)
+    ref = oracle.acq_values(om, oacq, sub, z[:, 0])
+    got = scores[torch.from_numpy(rows).to(dev)].double().cpu()
+    err = (got - ref).abs()
+    assert float((err > 5e-3 + 2e-3 * ref.abs()).double().mean()) <= 0.002, float(err.max())
+    mu, var = gp.posterior(packed[torch.from_numpy(rows).to(dev)])
+    mu_ref, var_ref = oracle.posterior(om, sub)
+    assert float((mu.double().cpu() - mu_ref).abs().max()) <= 5e-5 * max(1.0, float(mu_ref.abs().max()))
+    assert float((var.double().cpu() - var_ref).abs().max()) <= 2e-5 * om.y_std**2
+    # shards with global offsets reduce to the same key; second pass is bit-identical
+    bounds = [0, 400_000, 900_001, N]
+    keys = [gp.score(acq, packed[a:b], z[:, 0], index_offset=a, want_scores=False)[1] for a, b in zip(bounds, bounds[1:])]
+    assert int(torch.stack(keys).max()) == int(key)
+    scores2, key2 = gp.score(acq, packed, z[:, 0])
+    assert torch.equal(scores, scores2) and int(key2) == int(key)
