@@ -83,6 +83,9 @@ _SIGNATURES = {
     "bb_last_error": (C.c_char_p, []),
     "bb_model_blob_bytes": (_sz, [_i32, _i32, _i32]),
     "bb_model_build": (C.c_int, [C.POINTER(ModelDesc), _vp, _sz, C.POINTER(Model), _vp]),
+    "bb_fit_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "bb_fit_setup": (C.c_int, [_vp, _sz, _i32, _i32, _i32, _dp, _dp, C.POINTER(C.c_int32), _vp]),
+    "bb_fit_eval": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _dp, _dp, _dp, C.POINTER(C.c_int32), _vp]),
     "bb_kernel_matrix": (C.c_int, [C.POINTER(Model), _vp, _i32, _i64, _i64, _vp, _i64, _vp]),
     "bb_posterior": (C.c_int, [C.POINTER(Model), _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "bb_pending_stats": (C.c_int, [C.POINTER(Model), _vp, _i32, _vp, _vp, _vp, _vp]),

@@ -796,3 +796,272 @@ extern "C" int bb_pending_stats(const bb_model* m, const float* d_pend_x, int32_
   BB_LAUNCH_CHECK();
   return BB_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// MAP-fit objective on device: exact marginal log likelihood of the GP that
+// GaussianProcessSurrogate._fit hands to botorch.fit.fit_gpytorch_mll
+// (/root/reference/baybe/surrogates/gaussian_process/core.py:331-341, criterion
+// components/fit_criterion.py:22-41) and its gradient, float64.  The priors are closed-form in theta
+// and stay on the host, as does the L-BFGS-B driver (scipy, like botorch's scipy_minimize).
+//   theta = [ lengthscale[d] | noise | mean constant | B[T*T] task covariance (outputscale folded in) ]
+//   mll   = -1/2 r^T K^-1 r - 1/2 log|K| - n/2 log 2 pi ,  r = y - c
+//   d mll / d theta_p = 1/2 tr((alpha alpha^T - K^-1) dK/dtheta_p) ,  d mll / dc = sum(alpha)
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct FitLayout {
+  size_t xn, y, task, theta, K, Linv, Kinv, alpha, resid, partial, out, alpha32, flag, total;
+  int nblk, np;
+};
+
+FitLayout fit_layout(int n, int d, int T) {
+  FitLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  L.np = d + 2 + T * T;
+  L.nblk = (int)(((size_t)n * n + 1023) / 1024);
+  L.xn = take(sizeof(double) * (size_t)n * d);
+  L.y = take(sizeof(double) * n);
+  L.task = take(sizeof(int32_t) * n);
+  L.theta = take(sizeof(double) * L.np);
+  L.K = take(sizeof(double) * (size_t)n * n);
+  L.Linv = take(sizeof(double) * (size_t)n * n);
+  L.Kinv = take(sizeof(double) * (size_t)n * n);
+  L.alpha = take(sizeof(double) * n);
+  L.resid = take(sizeof(double) * n * 2);
+  L.partial = take(sizeof(double) * (size_t)L.nblk * L.np);
+  L.out = take(sizeof(double) * (L.np + 1));
+  L.alpha32 = take(sizeof(float) * n);
+  L.flag = take(64);
+  L.total = off;
+  return L;
+}
+
+// d k / d(r^2) of the stationary kernels (r2 > 0)
+__device__ __forceinline__ double dkernel_f64(int family, double r2) {
+  if (family == BB_KERNEL_RBF) return -0.5 * exp(-0.5 * r2);
+  const double r = sqrt(fmax(r2, 1e-300));
+  if (family == BB_KERNEL_MATERN12) return r2 > 1e-24 ? -exp(-r) / (2.0 * r) : 0.0;
+  if (family == BB_KERNEL_MATERN32) return -1.5 * exp(-1.7320508075688772 * r);
+  const double s = 2.23606797749979 * r;
+  return -(5.0 / 6.0) * (1.0 + s) * exp(-s);
+}
+
+__global__ void k_fit_gram(const double* __restrict__ xn, const int32_t* __restrict__ task,
+                           const double* __restrict__ theta, const double* __restrict__ y, int n, int d,
+                           int T, int family, double* __restrict__ K, double* __restrict__ resid) {
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || j >= n) return;
+  const double* B = theta + d + 2;
+  double k = 1.0;
+  if (i != j) {
+    double r2 = 0.0;
+    for (int c = 0; c < d; ++c) {
+      const double u = (xn[(size_t)i * d + c] - xn[(size_t)j * d + c]) / theta[c];
+      r2 += u * u;
+    }
+    k = kernel_f64(family, r2);
+  }
+  k *= B[task[i] * T + task[j]];
+  if (i == j) {
+    k += theta[d];
+    resid[i] = y[i] - theta[d + 1];
+  }
+  K[(size_t)i * n + j] = k;
+}
+
+// K^-1 = L^-T L^-1
+__global__ void k_fit_kinv(const double* __restrict__ Linv, int n, double* __restrict__ Kinv) {
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || k >= n) return;
+  double s = 0.0;
+  for (int m = max(i, k); m < n; ++m) s += Linv[(size_t)m * n + i] * Linv[(size_t)m * n + k];
+  Kinv[(size_t)i * n + k] = s;
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+  const int t = threadIdx.x;
+  red[t] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (t < s) red[t] += red[t + s];
+    __syncthreads();
+  }
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// per-block partial gradients over 1024 (i,k) pairs; fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) k_fit_grad(const double* __restrict__ xn, const int32_t* __restrict__ task,
+                                                  const double* __restrict__ theta, const double* __restrict__ alpha,
+                                                  const double* __restrict__ Kinv, int n, int d, int T, int family,
+                                                  double* __restrict__ partial) {
+  __shared__ double red[256];
+  const double* B = theta + d + 2;
+  const int np = d + 2 + T * T;
+  double g[4], hb[4];  // 1/2 W B dk/dr2 ; 1/2 W kbase
+  int pi[4], pk[4];
+  double gn = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const size_t e = (size_t)blockIdx.x * 1024 + q * 256 + threadIdx.x;
+    g[q] = hb[q] = 0.0;
+    pi[q] = pk[q] = 0;
+    if (e < (size_t)n * n) {
+      const int i = (int)(e / n), k = (int)(e - (size_t)i * n);
+      pi[q] = i;
+      pk[q] = k;
+      const double W = alpha[i] * alpha[k] - Kinv[e];
+      if (i == k) {
+        gn += 0.5 * W;
+        hb[q] = 0.5 * W;
+      } else {
+        double r2 = 0.0;
+        for (int c = 0; c < d; ++c) {
+          const double u = (xn[(size_t)i * d + c] - xn[(size_t)k * d + c]) / theta[c];
+          r2 += u * u;
+        }
+        hb[q] = 0.5 * W * kernel_f64(family, r2);
+        g[q] = 0.5 * W * B[task[i] * T + task[k]] * dkernel_f64(family, r2);
+      }
+    }
+  }
+  double* out = partial + (size_t)blockIdx.x * np;
+  for (int c = 0; c < d; ++c) {
+    const double il = 1.0 / theta[c];
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double dl = xn[(size_t)pi[q] * d + c] - xn[(size_t)pk[q] * d + c];
+      s += g[q] * dl * dl;
+    }
+    const double tot = block_sum_256(-2.0 * s * il * il * il, red);  // d r2 / d l_c = -2 delta^2 / l_c^3
+    if (threadIdx.x == 0) out[c] = tot;
+  }
+  {
+    const double tot = block_sum_256(gn, red);
+    if (threadIdx.x == 0) {
+      out[d] = tot;
+      out[d + 1] = 0.0;
+    }
+  }
+  for (int ab = 0; ab < T * T; ++ab) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (hb[q] != 0.0 && task[pi[q]] * T + task[pk[q]] == ab) s += hb[q];
+    const double tot = block_sum_256(s, red);
+    if (threadIdx.x == 0) out[d + 2 + ab] = tot;
+  }
+}
+
+__global__ void k_fit_final(const double* __restrict__ partial, int nblk, int np, const double* __restrict__ resid,
+                            const double* __restrict__ alpha, const double* __restrict__ Linv, int n, int d,
+                            double* __restrict__ out) {
+  __shared__ double red[256];
+  for (int p = threadIdx.x; p < np; p += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * np + p];
+    out[1 + p] = s;
+  }
+  double quad = 0.0, logd = 0.0, sa = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    quad += resid[i] * alpha[i];
+    logd += log(Linv[(size_t)i * n + i]);  // = -log L_ii
+    sa += alpha[i];
+  }
+  quad = block_sum_256(quad, red);
+  logd = block_sum_256(logd, red);
+  sa = block_sum_256(sa, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[0] = -0.5 * quad + logd - 0.5 * n * 1.8378770664093453;
+    out[1 + d + 1] = sa;
+  }
+}
+
+}  // namespace
+
+extern "C" size_t bb_fit_workspace_bytes(int32_t n, int32_t d, int32_t n_tasks) {
+  if (n <= 0 || d <= 0 || n_tasks <= 0) return 0;
+  return fit_layout(n, d, n_tasks).total;
+}
+
+extern "C" int bb_fit_setup(void* d_ws, size_t ws_bytes, int32_t n, int32_t d, int32_t n_tasks,
+                            const double* xn, const double* y, const int32_t* task, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  BB_CHECK_ARG(d_ws && xn && y, "bb_fit_setup: null argument");
+  BB_CHECK_ARG(n >= 1 && d >= 1 && n_tasks >= 1, "bb_fit_setup: n, d, n_tasks must be positive");
+  BB_CHECK_SUPPORTED(n <= BB_MAX_TRAIN, "bb_fit_setup: n=%d exceeds this build's limit of %d", n, BB_MAX_TRAIN);
+  BB_CHECK_SUPPORTED(n_tasks <= 16, "bb_fit_setup: at most 16 tasks supported");
+  BB_CHECK_ARG(n_tasks == 1 || task != nullptr, "bb_fit_setup: task ids missing");
+  const FitLayout L = fit_layout(n, d, n_tasks);
+  if (ws_bytes < L.total) {
+    set_error("bb_fit_setup: workspace of %zu bytes is smaller than the required %zu", ws_bytes, L.total);
+    return BB_ERR_WORKSPACE;
+  }
+  uint8_t* W = (uint8_t*)d_ws;
+  BB_CUDA(cudaMemsetAsync(W, 0, L.total, stream));
+  BB_CUDA(cudaMemcpyAsync(W + L.xn, xn, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, stream));
+  BB_CUDA(cudaMemcpyAsync(W + L.y, y, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+  if (task) {
+    for (int i = 0; i < n; ++i)
+      BB_CHECK_ARG(task[i] >= 0 && task[i] < n_tasks, "bb_fit_setup: task id %d outside [0,%d)", task[i], n_tasks);
+    BB_CUDA(cudaMemcpyAsync(W + L.task, task, sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
+  }
+  BB_CUDA(cudaStreamSynchronize(stream));
+  return BB_OK;
+}
+
+// value[0] = mll, grad[np] = d mll / d theta (np = d + 2 + T*T); *not_pd != 0 when K is not positive
+// definite at this theta (value/grad are then unspecified).  Synchronises the stream.
+extern "C" int bb_fit_eval(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, int32_t family,
+                           const double* theta, double* value, double* grad, int32_t* not_pd, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  BB_CHECK_ARG(d_ws && theta && value && grad && not_pd, "bb_fit_eval: null argument");
+  BB_CHECK_ARG(family >= 0 && family <= 3, "bb_fit_eval: unknown kernel family %d", family);
+  const FitLayout L = fit_layout(n, d, n_tasks);
+  uint8_t* W = (uint8_t*)d_ws;
+  for (int c = 0; c < d; ++c) BB_CHECK_ARG(theta[c] > 0.0, "bb_fit_eval: lengthscale %d is not positive", c);
+  BB_CUDA(cudaMemcpyAsync(W + L.theta, theta, sizeof(double) * L.np, cudaMemcpyHostToDevice, stream));
+  const double* dtheta = (const double*)(W + L.theta);
+  double* dK = (double*)(W + L.K);
+  double* dLinv = (double*)(W + L.Linv);
+  double* dresid = (double*)(W + L.resid);
+  dim3 blk(16, 16), grd((n + 15) / 16, (n + 15) / 16);
+  k_fit_gram<<<grd, blk, 0, stream>>>((const double*)(W + L.xn), (const int32_t*)(W + L.task), dtheta,
+                                      (const double*)(W + L.y), n, d, n_tasks, family, dK, dresid);
+  BB_LAUNCH_CHECK();
+  BB_CUDA(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * n)));
+  k_cholesky<<<1, 1024, sizeof(double) * n, stream>>>(dK, n, (int*)(W + L.flag));
+  BB_LAUNCH_CHECK();
+  k_tri_inverse<<<(n + 31) / 32, 32, 0, stream>>>(dK, n, dLinv);
+  BB_LAUNCH_CHECK();
+  k_alpha<<<1, 1024, 0, stream>>>(dLinv, dresid, n, dresid + n, (double*)(W + L.alpha), (float*)(W + L.alpha32));
+  BB_LAUNCH_CHECK();
+  k_fit_kinv<<<grd, blk, 0, stream>>>(dLinv, n, (double*)(W + L.Kinv));
+  BB_LAUNCH_CHECK();
+  k_fit_grad<<<L.nblk, 256, 0, stream>>>((const double*)(W + L.xn), (const int32_t*)(W + L.task), dtheta,
+                                         (const double*)(W + L.alpha), (const double*)(W + L.Kinv), n, d, n_tasks,
+                                         family, (double*)(W + L.partial));
+  BB_LAUNCH_CHECK();
+  k_fit_final<<<1, 256, 0, stream>>>((const double*)(W + L.partial), L.nblk, L.np, dresid,
+                                     (const double*)(W + L.alpha), dLinv, n, d, (double*)(W + L.out));
+  BB_LAUNCH_CHECK();
+  std::vector<double> out(L.np + 1);
+  int flag = 0;
+  BB_CUDA(cudaMemcpyAsync(out.data(), W + L.out, sizeof(double) * (L.np + 1), cudaMemcpyDeviceToHost, stream));
+  BB_CUDA(cudaMemcpyAsync(&flag, W + L.flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  BB_CUDA(cudaStreamSynchronize(stream));
+  *not_pd = flag;
+  *value = out[0];
+  for (int p = 0; p < L.np; ++p) grad[p] = out[1 + p];
+  return BB_OK;
+}

@@ -6,7 +6,8 @@ and the model owns input Normalize / output Standardize (core.py:130-141 "Scalin
 
 The fitted model lives on the GPU as a ``DeviceGP`` (caches built by ``bb_model_build``); every
 posterior evaluation runs the tcgen05 kernel.  Hyper-parameter fitting (*before*
-the hot path) is host-side float64 torch + scipy L-BFGS-B on the BayBE preset's MAP objective
+the hot path) evaluates the exact marginal likelihood and its gradient on the GPU (``bb_fit_eval``, float64)
+under scipy's L-BFGS-B on the BayBE preset's MAP objective
 (``presets/baybe.py:57-144``: Matern-5/2 ARD, Gamma(3, rate(d)) lengthscale prior with lower bound
 2.5e-2, Gamma(2, e^5) noise prior with floor 1e-4, constant mean, no output scale).
 """
@@ -24,7 +25,8 @@ from attrs import define, field
 from baybe_b200.engine import DeviceGP
 from baybe_b200.searchspace import objective_affine
 
-__all__ = ["GaussianProcessSurrogate", "ModelNotTrainedError", "fit_map_hyperparameters"]
+__all__ = ["GaussianProcessSurrogate", "ModelNotTrainedError", "fit_map_hyperparameters",
+           "fit_map_hyperparameters_device", "DeviceMLL"]
 
 MIN_INFERRED_NOISE_LEVEL = 1e-4
 MIN_LENGTHSCALE = 2.5e-2
@@ -102,6 +104,107 @@ def fit_map_hyperparameters(Xn: np.ndarray, y_std: np.ndarray, active: Sequence[
             "n_iter": int(res.nit)}
 
 
+class DeviceMLL:
+    """Exact marginal log likelihood and its gradient on the GPU (``bb_fit_setup`` / ``bb_fit_eval``,
+    float64): theta = [lengthscale[d] | noise | mean constant | B[T*T]]."""
+
+    def __init__(self, Xa: np.ndarray, y_std: np.ndarray, task_ids=None, n_tasks: int = 1,
+                 family: str = "matern52", device=None):
+        import ctypes as C
+
+        from baybe_b200 import _lib
+        from baybe_b200.engine import _require_cuda, _stream_ptr
+
+        self._C, self._lib_mod, self._stream_ptr = C, _lib, _stream_ptr
+        self.device = _require_cuda(device)
+        self.lib = _lib.load()
+        self.n, self.d = Xa.shape
+        self.T = int(n_tasks)
+        self.family = _lib.KERNEL_FAMILY[family]
+        self.np = self.d + 2 + self.T * self.T
+        xa = np.ascontiguousarray(Xa, dtype=np.float64)
+        yy = np.ascontiguousarray(y_std, dtype=np.float64)
+        tt = None if task_ids is None else np.ascontiguousarray(task_ids, dtype=np.int32)
+        nbytes = self.lib.bb_fit_workspace_bytes(self.n, self.d, self.T)
+        with torch.cuda.device(self.device):
+            self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            self._base = (self._ws.data_ptr() + 255) // 256 * 256
+            dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+            _lib.check(self.lib.bb_fit_setup(
+                C.c_void_p(self._base), nbytes, self.n, self.d, self.T, dp(xa), dp(yy),
+                None if tt is None else tt.ctypes.data_as(C.POINTER(C.c_int32)), _stream_ptr()), "bb_fit_setup")
+
+    def __call__(self, theta: np.ndarray) -> tuple[float, np.ndarray, bool]:
+        """(mll, d mll / d theta, positive_definite)."""
+        C = self._C
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        if th.shape != (self.np,):
+            raise ValueError(f"theta must have {self.np} entries")
+        val = C.c_double(0.0)
+        grad = np.zeros(self.np)
+        bad = C.c_int32(0)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+        with torch.cuda.device(self.device):
+            self._lib_mod.check(self.lib.bb_fit_eval(
+                C.c_void_p(self._base), self.n, self.d, self.T, self.family, dp(th), C.byref(val), dp(grad),
+                C.byref(bad), self._stream_ptr()), "bb_fit_eval")
+        return float(val.value), grad, bad.value == 0
+
+
+def fit_map_hyperparameters_device(Xn: np.ndarray, y_std: np.ndarray, active: Sequence[int], task_ids=None,
+                                   n_tasks: int = 1, max_iter: int = 200, device=None) -> dict:
+    """Same MAP objective, start point, bounds and optimiser as ``fit_map_hyperparameters``; the marginal
+    likelihood and its gradient are evaluated on the GPU (Cholesky, K^-1 and the n^2 d gradient contraction
+    in float64 kernels), the Gamma priors and scipy's L-BFGS-B step on the host."""
+    from scipy.optimize import minimize
+
+    Xa = np.ascontiguousarray(np.asarray(Xn, dtype=np.float64)[:, list(active)])
+    n, da = Xa.shape
+    T = n_tasks if task_ids is not None else 1
+    mll = DeviceMLL(Xa, y_std, task_ids, T, "matern52", device)
+    conc_l, rate_l = 3.0, 2.0 / math.exp(math.sqrt(2.0) - 3.0) / math.sqrt(da)
+    conc_n, rate_n = 2.0, 1.0 / math.exp(-5.0)
+    ls0 = (conc_l - 1.0) / rate_l
+    nz0 = (conc_n - 1.0) / rate_n
+    n_task_par = 0 if task_ids is None else T * T + T
+    x0 = np.concatenate([np.full(da, ls0), [max(nz0, MIN_INFERRED_NOISE_LEVEL)], [0.0],
+                         np.concatenate([np.eye(T).reshape(-1) * 0.8 + 0.2, np.full(T, 0.1)]) if n_task_par else []])
+    bounds = [(MIN_LENGTHSCALE, None)] * da + [(MIN_INFERRED_NOISE_LEVEL, None), (None, None)] + \
+             [(1e-6, None)] * n_task_par
+
+    def task_cov(x):
+        if not n_task_par:
+            return np.ones((1, 1)), None, None
+        W = x[da + 2: da + 2 + T * T].reshape(T, T)
+        v = x[da + 2 + T * T:]
+        return W @ W.T + np.diag(v), W, v
+
+    def objective(x):
+        B, W, _ = task_cov(x)
+        theta = np.concatenate([x[: da + 2], B.reshape(-1)])
+        val, g, ok = mll(theta)
+        if not ok or not np.isfinite(val):
+            return 1e10, np.zeros_like(x)
+        ls, nz = x[:da], x[da]
+        lp = ((conc_l - 1.0) * np.log(ls) - rate_l * ls).sum() + (conc_n - 1.0) * math.log(nz) - rate_n * nz
+        grad = np.zeros_like(x)
+        grad[:da] = g[:da] + (conc_l - 1.0) / ls - rate_l
+        grad[da] = g[da] + (conc_n - 1.0) / nz - rate_n
+        grad[da + 1] = g[da + 1]
+        if n_task_par:
+            gB = g[da + 2:].reshape(T, T)
+            grad[da + 2: da + 2 + T * T] = ((gB + gB.T) @ W).reshape(-1)
+            grad[da + 2 + T * T:] = np.diag(gB)
+        return -(val + lp) / n, -grad / n
+
+    res = minimize(objective, x0, jac=True, method="L-BFGS-B", bounds=bounds,
+                   options={"maxiter": max_iter, "ftol": 1e-10, "gtol": 1e-7})
+    B, _, _ = task_cov(res.x)
+    return {"lengthscale": res.x[:da].copy(), "noise": float(res.x[da]), "mean_const": float(res.x[da + 1]),
+            "task_covar": B if n_task_par else None, "objective": float(res.fun), "n_iter": int(res.nit),
+            "n_eval": int(res.nfev), "backend": "device"}
+
+
 class _Posterior:
     """Marginal (t-batch) posterior with the attribute names BayBE reads from BoTorch posteriors
     (``mean``, ``variance``, ``quantile``; surrogates/base.py:352-375)."""
@@ -129,6 +232,9 @@ class GaussianProcessSurrogate:
 
     device: str | None = field(default=None)
     max_fit_iter: int = field(default=200)
+    fit_backend: str = field(default="device")
+    """"device": marginal likelihood + gradient on the GPU (bb_fit_eval); "host": float64 torch autograd
+    (kept as the independent cross-check of the device objective)."""
 
     device_gp: DeviceGP | None = field(init=False, default=None, eq=False, repr=False)
     fitted_hyperparameters: dict | None = field(init=False, default=None, eq=False, repr=False)
@@ -165,8 +271,9 @@ class GaussianProcessSurrogate:
             ys = train_y.std(ddof=1) if len(train_y) > 1 else 1.0
             ys = ys if ys >= 1e-8 else 1.0
             tids = None if task_col is None else np.rint(train_x[:, task_col]).astype(int)
-            hp = fit_map_hyperparameters(Xn, (train_y - train_y.mean()) / ys, active, tids, n_tasks,
-                                         self.max_fit_iter)
+            fit = fit_map_hyperparameters if self.fit_backend == "host" else fit_map_hyperparameters_device
+            kw = {} if self.fit_backend == "host" else {"device": self.device}
+            hp = fit(Xn, (train_y - train_y.mean()) / ys, active, tids, n_tasks, self.max_fit_iter, **kw)
         ls_full = np.full(d, -1.0)
         ls_full[active] = np.broadcast_to(np.asarray(hp["lengthscale"], dtype=np.float64), (len(active),))
         task_covar = hp.get("task_covar")

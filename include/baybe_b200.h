@@ -182,6 +182,18 @@ size_t bb_model_blob_bytes(int32_t n, int32_t d, int32_t n_tasks);
 int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t blob_bytes, bb_model* out,
                    void* stream);
 
+/* ---- hyper-parameter fit: value and gradient of the exact marginal log likelihood that
+ * GaussianProcessSurrogate._fit maximises through botorch.fit.fit_gpytorch_mll (core.py:331-341,
+ * components/fit_criterion.py:22-41), float64 on device.  theta (HOST) = [lengthscale[d] | noise | mean
+ * constant | task covariance B[T*T] (outputscale folded in; [1.0] without tasks)]; xn [n*d] are the
+ * normalised ACTIVE columns, y [n] the standardised targets, task [n] task ids or NULL.  The priors and the
+ * L-BFGS-B driver stay on the host (baybe_b200/surrogates.py).  bb_fit_eval synchronises the stream. ---- */
+size_t bb_fit_workspace_bytes(int32_t n, int32_t d, int32_t n_tasks);
+int bb_fit_setup(void* d_ws, size_t ws_bytes, int32_t n, int32_t d, int32_t n_tasks, const double* xn,
+                 const double* y, const int32_t* task, void* stream);
+int bb_fit_eval(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, int32_t family, const double* theta,
+                double* value, double* grad, int32_t* not_pd, void* stream);
+
 /* ---- K2: K(X*, X_train), fp32 row-major [N, ldk>=n].  Replaces gpytorch
  * MaternKernel/RBFKernel/ScaleKernel/ProductKernel.forward built at
  * baybe/kernels/base.py:173-178 and components/kernel.py:337. ---------------------------- */

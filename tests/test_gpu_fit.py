@@ -1,0 +1,126 @@
+"""GPU tests of the device-side hyper-parameter fit: bb_fit_eval's marginal log
+likelihood and gradient against float64 torch autograd on the CPU, and the fitted hyper-parameters of
+the device-driven MAP fit against the host fit (same objective, same optimiser)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from baybe_b200.surrogates import DeviceMLL, fit_map_hyperparameters, fit_map_hyperparameters_device
+from baybe_b200.synthetic import numeric_grid_workload, task_workload
+
+pytestmark = pytest.mark.gpu
+
+
+def _kernel(family, d2):
+    if family == "rbf":
+        return torch.exp(-0.5 * d2)
+    r = d2.clamp_min(1e-30).sqrt()
+    if family == "matern12":
+        return torch.exp(-r)
+    if family == "matern32":
+        s = math.sqrt(3.0) * r
+        return (1.0 + s) * torch.exp(-s)
+    s = math.sqrt(5.0) * r
+    return (1.0 + s + (5.0 / 3.0) * d2) * torch.exp(-s)
+
+
+def _host_mll(X, y, tid, T, family, theta):
+    """Independent float64 restatement: returns (mll, gradient) by autograd."""
+    n, d = X.shape
+    t = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+    ls, nz, c, B = t[:d], t[d], t[d + 1], t[d + 2:].reshape(T, T)
+    Xt = torch.as_tensor(X)
+    diff = (Xt[:, None, :] - Xt[None, :, :]) / ls
+    d2 = (diff * diff).sum(-1)
+    K = _kernel(family, d2)
+    K = K * (1.0 - torch.eye(n, dtype=torch.float64)) + torch.eye(n, dtype=torch.float64)  # exact unit diagonal
+    tt = torch.zeros(n, dtype=torch.long) if tid is None else torch.as_tensor(tid, dtype=torch.long)
+    K = K * B[tt][:, tt] + nz * torch.eye(n, dtype=torch.float64)
+    L = torch.linalg.cholesky(K)
+    r = (torch.as_tensor(y) - c).unsqueeze(-1)
+    a = torch.cholesky_solve(r, L)
+    mll = -0.5 * (r * a).sum() - torch.log(torch.diagonal(L)).sum() - 0.5 * n * math.log(2 * math.pi)
+    mll.backward()
+    return float(mll), t.grad.numpy().copy()
+
+
+@pytest.mark.parametrize("family", ["matern52", "matern32", "rbf", "matern12"])
+@pytest.mark.parametrize("tasks", [False, True])
+def test_device_mll_and_gradient_match_autograd(family, tasks, cuda_device):
+    rng = np.random.default_rng(3)
+    if tasks:
+        w = task_workload(N_per_task=60, n_tasks=3, d_num=5, n_per_task=25, seed=4)
+        X = np.delete(w.train_x, w.task_col, axis=1)
+        tid = np.rint(w.train_x[:, w.task_col]).astype(np.int32)
+        T = 3
+        A = rng.uniform(0.2, 1.0, size=(T, T))
+        B = A @ A.T + np.diag(rng.uniform(0.1, 0.5, T))
+    else:
+        w = numeric_grid_workload(N=400, d=7, n=90, seed=5)
+        X, tid, T, B = w.train_x, None, 1, np.array([[1.3]])
+    y = (w.train_y - w.train_y.mean()) / w.train_y.std(ddof=1)
+    d = X.shape[1]
+    mll = DeviceMLL(X, y, tid, T, family, cuda_device)
+    for trial in range(3):
+        theta = np.concatenate([rng.uniform(0.3, 2.0, d), [rng.uniform(1e-3, 0.1)], [rng.normal(0, 0.3)], B.reshape(-1)])
+        val, grad, ok = mll(theta)
+        ref_val, ref_grad = _host_mll(X, y, tid, T, family, theta)
+        assert ok
+        assert abs(val - ref_val) <= 1e-9 * max(1.0, abs(ref_val))
+        assert np.abs(grad - ref_grad).max() <= 1e-8 * max(1.0, np.abs(ref_grad).max()), (grad, ref_grad)
+
+
+def test_not_positive_definite_is_reported(cuda_device):
+    X = np.zeros((6, 2))  # six identical points, no noise to speak of: singular Gram matrix
+    mll = DeviceMLL(X, np.zeros(6), None, 1, "rbf", cuda_device)
+    _, _, ok = mll(np.array([1.0, 1.0, -1e-3, 0.0, 1.0]))
+    assert not ok
+
+
+@pytest.mark.parametrize("tasks", [False, True])
+def test_device_fit_equals_host_fit(tasks, cuda_device):
+    if tasks:
+        w = task_workload(N_per_task=50, n_tasks=2, d_num=4, n_per_task=30, seed=7)
+        active = [j for j in range(w.train_x.shape[1]) if j != w.task_col]
+        tid, T = np.rint(w.train_x[:, w.task_col]).astype(int), 2
+    else:
+        w = numeric_grid_workload(N=500, d=6, n=80, seed=8)
+        active, tid, T = list(range(6)), None, 1
+    y = (w.train_y - w.train_y.mean()) / w.train_y.std(ddof=1)
+    host = fit_map_hyperparameters(w.train_x, y, active, tid, T, 200)
+    dev = fit_map_hyperparameters_device(w.train_x, y, active, tid, T, 200, device=cuda_device)
+    assert dev["backend"] == "device"
+    # same objective, same optimiser, float64 on both sides: the optima coincide
+    assert abs(dev["objective"] - host["objective"]) <= 1e-6 * max(1.0, abs(host["objective"]))
+    assert np.allclose(dev["lengthscale"], host["lengthscale"], rtol=2e-3, atol=1e-4)
+    assert np.isclose(dev["noise"], host["noise"], rtol=2e-3, atol=1e-6)
+    assert np.isclose(dev["mean_const"], host["mean_const"], rtol=2e-3, atol=1e-4)
+    if tasks:
+        assert np.allclose(dev["task_covar"], host["task_covar"], rtol=5e-3, atol=1e-4)
+
+
+def test_surrogate_fit_backends_recommend_the_same_point(cuda_device):
+    import pandas as pd
+
+    from baybe_b200.recommenders import B200Recommender
+    from baybe_b200.searchspace import NumericalDiscreteParameter, NumericalTarget, SearchSpace, SingleTargetObjective
+    from baybe_b200.surrogates import GaussianProcessSurrogate
+
+    ss = SearchSpace.from_product([NumericalDiscreteParameter(f"x{j}", np.linspace(0, 1, 7)) for j in range(4)])
+    rows = ss.discrete.exp_rep.sample(n=25, random_state=2)
+    comp = ss.transform(rows).to_numpy()
+    meas = rows.assign(Yield=np.sin(3 * comp[:, 0]) + comp[:, 1] ** 2 - 0.5 * comp[:, 2] + 0.01 * np.arange(25) % 3)
+    obj = SingleTargetObjective(NumericalTarget("Yield"))
+    out = {}
+    for backend in ("device", "host"):
+        rec = B200Recommender(surrogate_model=GaussianProcessSurrogate(fit_backend=backend))
+        torch.manual_seed(5)
+        out[backend] = rec.recommend(2, ss, obj, meas)
+        hp = rec.surrogate_model.fitted_hyperparameters
+        assert hp["noise"] >= 1e-4 and (hp["lengthscale"] >= 2.5e-2).all()
+    assert list(out["device"].index) == list(out["host"].index)
+    assert isinstance(out["device"], pd.DataFrame)
