@@ -147,67 +147,165 @@ __global__ void k_train_gram(const double* __restrict__ xn, const int32_t* __res
   K[(size_t)i * n + j] = k;
 }
 
-// In-place lower Cholesky of the n x n row-major matrix A (single CTA).  fail[0] != 0 on a
-// non-positive pivot.
-__global__ void __launch_bounds__(1024) k_cholesky(double* __restrict__ A, int n,
-                                                   int* __restrict__ fail) {
-  extern __shared__ double col[];
+// ---- blocked float64 Cholesky / triangular inverse (32 x 32 blocks, many CTAs) -------------------
+// n <= 512 makes these launch-latency sized problems: a single-CTA unblocked factorisation took 12 ms at
+// n = 512 (and the thread-per-column inverse 14 ms), which dominated every bb_model_build and every
+// objective evaluation of the hyper-parameter fit; the blocked forms take a few hundred microseconds.
+constexpr int kNB = 32;
+
+// Panel step at column j0, part 1: factor the (already updated) 32 x 32 diagonal block in place (one CTA).
+__global__ void __launch_bounds__(1024) k_chol_diag(double* __restrict__ A, int n, int j0, int* __restrict__ fail) {
+  __shared__ double D[kNB][kNB + 1];
   __shared__ int bad;
-  int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) bad = 0;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (column, row) inside the block
+  const int gi = j0 + ty, gj = j0 + tx;
+  D[ty][tx] = (gi < n && gj < n && tx <= ty) ? A[(size_t)gi * n + gj] : (tx == ty ? 1.0 : 0.0);
+  if (tx == 0 && ty == 0) bad = 0;
   __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    if (tid == 0) {
-      double dj = A[(size_t)j * n + j];
+  for (int j = 0; j < kNB; ++j) {
+    if (tx == j && ty == j) {
+      double dj = D[j][j];
       if (!(dj > 0.0)) {
         bad = 1;
         dj = 1.0;
       }
-      A[(size_t)j * n + j] = sqrt(dj);
+      D[j][j] = sqrt(dj);
     }
     __syncthreads();
-    double inv = 1.0 / A[(size_t)j * n + j];
-    for (int i = j + 1 + tid; i < n; i += nt) {
-      double v = A[(size_t)i * n + j] * inv;
-      A[(size_t)i * n + j] = v;
-      col[i] = v;
-    }
+    if (tx == j && ty > j) D[ty][j] /= D[j][j];
     __syncthreads();
-    int m = n - j - 1;  // trailing size
-    for (int e = tid; e < m * m; e += nt) {
-      int ii = e / m, kk = e - ii * m;
-      if (kk <= ii) {
-        int i = j + 1 + ii, k = j + 1 + kk;
-        A[(size_t)i * n + k] -= col[i] * col[k];
-      }
+    if (tx > j && tx <= ty) D[ty][tx] -= D[ty][j] * D[tx][j];
+    __syncthreads();
+  }
+  if (gi < n && gj < n) A[(size_t)gi * n + gj] = (tx <= ty) ? D[ty][tx] : 0.0;
+  if (tx == 0 && ty == 0 && bad) fail[0] = 1;
+}
+
+// Part 2: CTA b solves its 32-row slab below the diagonal block:  X L11^T = A21.
+__global__ void __launch_bounds__(1024) k_chol_trsm(double* __restrict__ A, int n, int j0) {
+  __shared__ double D[kNB][kNB + 1], S[kNB][kNB + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int gi = j0 + ty, gj = j0 + tx;
+  D[ty][tx] = (gi < n && gj < n && tx <= ty) ? A[(size_t)gi * n + gj] : (tx == ty ? 1.0 : 0.0);
+  const int ri = j0 + kNB * (1 + blockIdx.x) + ty;
+  S[ty][tx] = (ri < n && gj < n) ? A[(size_t)ri * n + gj] : 0.0;
+  __syncthreads();
+  for (int c = 0; c < kNB; ++c) {
+    if (tx == c) {
+      double sv = S[ty][c];
+      for (int k = 0; k < c; ++k) sv -= S[ty][k] * D[c][k];
+      S[ty][c] = sv / D[c][c];
     }
     __syncthreads();
   }
-  if (tid == 0) fail[0] = bad;
-  // zero the strict upper triangle so that A is exactly L
-  for (int e = tid; e < n * n; e += nt) {
-    int i = e / n, k = e - i * n;
-    if (k > i) A[e] = 0.0;
+  if (ri < n && gj < n) A[(size_t)ri * n + gj] = S[ty][tx];
+}
+
+// Trailing update after the panel at j0: A22 -= L21 L21^T (lower blocks only).
+__global__ void __launch_bounds__(1024) k_chol_update(double* __restrict__ A, int n, int j0) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  __shared__ double P[kNB][kNB + 1], Q[kNB][kNB + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i0 = j0 + kNB * (1 + bi), k0 = j0 + kNB * (1 + bj);
+  P[ty][tx] = (i0 + ty < n && j0 + tx < n) ? A[(size_t)(i0 + ty) * n + j0 + tx] : 0.0;
+  Q[ty][tx] = (k0 + ty < n && j0 + tx < n) ? A[(size_t)(k0 + ty) * n + j0 + tx] : 0.0;
+  __syncthreads();
+  const int gi = i0 + ty, gj = k0 + tx;
+  if (gi < n && gj < n && gj <= gi) {
+    double sv = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < kNB; ++k) sv += P[ty][k] * Q[tx][k];
+    A[(size_t)gi * n + gj] -= sv;
   }
 }
 
-// X = L^-1 (lower triangular), one thread per column, forward substitution.
-__global__ void k_tri_inverse(const double* __restrict__ L, int n, double* __restrict__ X) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  for (int i = 0; i < c; ++i) X[(size_t)i * n + c] = 0.0;
-  X[(size_t)c * n + c] = 1.0 / L[(size_t)c * n + c];
-  for (int i = c + 1; i < n; ++i) {
-    const double* Li = L + (size_t)i * n;
-    double s0 = 0.0, s1 = 0.0;
-    int k = c;
-    for (; k + 1 < i; k += 2) {
-      s0 += Li[k] * X[(size_t)k * n + c];
-      s1 += Li[k + 1] * X[(size_t)(k + 1) * n + c];
+__global__ void k_zero_upper(double* __restrict__ A, int n) {
+  const int i = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && k < n && k > i) A[(size_t)i * n + k] = 0.0;
+}
+
+// In-place lower Cholesky of the n x n row-major matrix A; fail[0] != 0 on a non-positive pivot; the strict
+// upper triangle is zeroed so that A is exactly L.
+static int launch_cholesky(double* A, int n, int* fail, cudaStream_t stream) {
+  BB_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), stream));
+  const int nb = (n + kNB - 1) / kNB;
+  for (int p = 0; p < nb; ++p) {
+    k_chol_diag<<<1, dim3(kNB, kNB), 0, stream>>>(A, n, p * kNB, fail);
+    BB_LAUNCH_CHECK();
+    if (p + 1 < nb) {
+      k_chol_trsm<<<nb - p - 1, dim3(kNB, kNB), 0, stream>>>(A, n, p * kNB);
+      BB_LAUNCH_CHECK();
+      k_chol_update<<<dim3(nb - p - 1, nb - p - 1), dim3(kNB, kNB), 0, stream>>>(A, n, p * kNB);
+      BB_LAUNCH_CHECK();
     }
-    if (k < i) s0 += Li[k] * X[(size_t)k * n + c];
-    X[(size_t)i * n + c] = -(s0 + s1) / Li[i];
   }
+  k_zero_upper<<<dim3((n + 15) / 16, (n + 15) / 16), dim3(16, 16), 0, stream>>>(A, n);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+// X = L^-1 (lower triangular).  Step 1: inverses of the diagonal blocks (one CTA each).
+__global__ void __launch_bounds__(1024) k_trinv_diag(const double* __restrict__ L, int n, double* __restrict__ X) {
+  __shared__ double D[kNB][kNB + 1], V[kNB][kNB + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y, j0 = blockIdx.x * kNB;
+  const int gi = j0 + ty, gj = j0 + tx;
+  D[ty][tx] = (gi < n && gj < n && tx <= ty) ? L[(size_t)gi * n + gj] : (tx == ty ? 1.0 : 0.0);
+  V[ty][tx] = 0.0;
+  __syncthreads();
+  if (ty == 0) {  // thread tx owns column c = tx of the inverse
+    const int c = tx;
+    V[c][c] = 1.0 / D[c][c];
+    for (int i = c + 1; i < kNB; ++i) {
+      double sv = 0.0;
+      for (int k = c; k < i; ++k) sv += D[i][k] * V[k][c];
+      V[i][c] = -sv / D[i][i];
+    }
+  }
+  __syncthreads();
+  if (gi < n && gj < n) X[(size_t)gi * n + gj] = V[ty][tx];
+}
+
+// Step 2: block column J per CTA:  X_IJ = -X_II * sum_{K=J}^{I-1} L_IK X_KJ  for I = J+1.. (X_II from step 1).
+__global__ void __launch_bounds__(1024) k_trinv_offdiag(const double* __restrict__ L, int n, double* X) {
+  __shared__ double Ls[kNB][kNB + 1], Xs[kNB][kNB + 1], Ts[kNB][kNB + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y, J = blockIdx.x;
+  const int nb = (n + kNB - 1) / kNB;
+  const int gj = J * kNB + tx;
+  for (int I = 0; I < J; ++I) {  // blocks above the diagonal are zero
+    const int gi = I * kNB + ty;
+    if (gi < n && gj < n) X[(size_t)gi * n + gj] = 0.0;
+  }
+  for (int I = J + 1; I < nb; ++I) {
+    const int gi = I * kNB + ty;
+    double acc = 0.0;
+    for (int K = J; K < I; ++K) {
+      const int lk = K * kNB + tx, xk = K * kNB + ty;
+      Ls[ty][tx] = (gi < n && lk < n) ? L[(size_t)gi * n + lk] : 0.0;
+      Xs[ty][tx] = (xk < n && gj < n) ? X[(size_t)xk * n + gj] : 0.0;
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < kNB; ++k) acc += Ls[ty][k] * Xs[k][tx];
+      __syncthreads();
+    }
+    Ts[ty][tx] = acc;
+    const int dk = I * kNB + tx;  // X_II (lower triangular)
+    Ls[ty][tx] = (gi < n && dk < n && tx <= ty) ? X[(size_t)gi * n + dk] : 0.0;
+    __syncthreads();
+    double v = 0.0;
+    for (int k = 0; k <= ty; ++k) v += Ls[ty][k] * Ts[k][tx];
+    if (gi < n && gj < n) X[(size_t)gi * n + gj] = -v;
+    __syncthreads();  // X_IJ is read (as X_KJ) by the next block rows
+  }
+}
+
+static int launch_tri_inverse(const double* L, int n, double* X, cudaStream_t stream) {
+  const int nb = (n + kNB - 1) / kNB;
+  k_trinv_diag<<<nb, dim3(kNB, kNB), 0, stream>>>(L, n, X);
+  BB_LAUNCH_CHECK();
+  k_trinv_offdiag<<<nb, dim3(kNB, kNB), 0, stream>>>(L, n, X);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
 }
 
 // u = Linv r ; alpha = Linv^T u   (single CTA, n <= 1024 threads)
@@ -599,8 +697,6 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
   double* dLinv = (double*)(B + L.linv);
   int* dflag = (int*)(B + L.flags);
   double* dmax = (double*)(B + L.flags + 16);
-  BB_CUDA(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(sizeof(double) * n)));
   int tries = 0;
   double jitter = 0.0;
   for (;; ++tries) {
@@ -613,8 +709,10 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
                                           (const double*)(B + L.noise_row), n, d, T, desc->family,
                                           jitter, dK);
     BB_LAUNCH_CHECK();
-    k_cholesky<<<1, 1024, sizeof(double) * n, stream>>>(dK, n, dflag);
-    BB_LAUNCH_CHECK();
+    {
+      const int rc_chol = launch_cholesky(dK, n, dflag, stream);
+      if (rc_chol != BB_OK) return rc_chol;
+    }
     int flag = 0;
     BB_CUDA(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, stream));
     BB_CUDA(cudaStreamSynchronize(stream));
@@ -624,8 +722,10 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
       return BB_ERR_NOT_PD;
     }
   }
-  k_tri_inverse<<<(n + 31) / 32, 32, 0, stream>>>(dK, n, dLinv);
-  BB_LAUNCH_CHECK();
+  {
+    const int rc_inv = launch_tri_inverse(dK, n, dLinv, stream);
+    if (rc_inv != BB_OK) return rc_inv;
+  }
   k_alpha<<<1, 1024, 0, stream>>>(dLinv, (const double*)(B + L.resid), n,
                                   (double*)(B + L.resid) + n, (double*)(B + L.alpha64),
                                   (float*)(B + L.alpha));
@@ -1039,11 +1139,10 @@ extern "C" int bb_fit_eval(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, in
   k_fit_gram<<<grd, blk, 0, stream>>>((const double*)(W + L.xn), (const int32_t*)(W + L.task), dtheta,
                                       (const double*)(W + L.y), n, d, n_tasks, family, dK, dresid);
   BB_LAUNCH_CHECK();
-  BB_CUDA(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * n)));
-  k_cholesky<<<1, 1024, sizeof(double) * n, stream>>>(dK, n, (int*)(W + L.flag));
-  BB_LAUNCH_CHECK();
-  k_tri_inverse<<<(n + 31) / 32, 32, 0, stream>>>(dK, n, dLinv);
-  BB_LAUNCH_CHECK();
+  int rc_f = launch_cholesky(dK, n, (int*)(W + L.flag), stream);
+  if (rc_f != BB_OK) return rc_f;
+  rc_f = launch_tri_inverse(dK, n, dLinv, stream);
+  if (rc_f != BB_OK) return rc_f;
   k_alpha<<<1, 1024, 0, stream>>>(dLinv, dresid, n, dresid + n, (double*)(W + L.alpha), (float*)(W + L.alpha32));
   BB_LAUNCH_CHECK();
   k_fit_kinv<<<grd, blk, 0, stream>>>(dLinv, n, (double*)(W + L.Kinv));
