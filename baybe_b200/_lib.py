@@ -56,6 +56,8 @@ class Model(C.Structure):
         ("d_wimg_bits", C.c_void_p), ("d_wnorm_bits", C.c_void_p), ("d_wide_ws", C.c_void_p),
         ("wide_ws_rows", C.c_int64), ("dist_scale_w", C.c_float), ("pad2_", C.c_int32),
         ("d_rimg4", C.c_void_p), ("d_rimg2g", C.c_void_p),
+        ("d_pend_img", C.c_void_p), ("d_pend_norm", C.c_void_p), ("d_pend_task", C.c_void_p),
+        ("d_kpend_ws", C.c_void_p), ("dist_scale_p", C.c_float), ("dist_scale_wp", C.c_float),
     ]
 
 

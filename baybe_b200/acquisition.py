@@ -78,8 +78,6 @@ class AcquisitionFunction:
         from baybe_b200.engine import DEFAULT_MC_SAMPLES
         from baybe_b200.recommenders import _draw_sampler_seed, _scores_for
 
-        if jointly:
-            raise NotImplementedError("joint (q=N) evaluation is outside the B200 fast path")
         surrogate.fit(searchspace, objective, measurements)
         cfg = self.to_engine(surrogate, searchspace, objective, measurements, pending_experiments)
         comp = searchspace.transform(candidates, allow_extra=True)
@@ -88,6 +86,25 @@ class AcquisitionFunction:
         if pending_experiments is not None:
             pend = searchspace.transform(pending_experiments, allow_extra=True).to_numpy(dtype="float64")
         seed = _draw_sampler_seed()
+        if jointly:
+            # one q-batch [x_1..x_q ; X_pending] (botorch concatenates pending points behind the batch):
+            # the joint kernel's "candidate first" order is exactly this order with x_1 as the candidate
+            import numpy as np
+
+            from baybe_b200.engine import sobol_normal_samples
+            from baybe_b200._lib import MAX_PENDING
+
+            rows = comp.to_numpy(dtype="float64")
+            rest = rows[1:] if pend is None else np.concatenate([rows[1:], pend.reshape(-1, rows.shape[1])], axis=0)
+            if len(rest) == 0:
+                return float(_scores_for(surrogate.device_gp, cfg, x[:1], None, seed, DEFAULT_MC_SAMPLES)[0])
+            if not cfg.is_mc:
+                raise IncompatibleAcquisitionFunctionError(
+                    f"'{type(self).__name__}' is analytic and cannot value a batch of {len(rows)} points jointly.")
+            if len(rest) > MAX_PENDING:
+                raise NotImplementedError(f"joint evaluation supports at most {MAX_PENDING + 1} points")
+            z = sobol_normal_samples(DEFAULT_MC_SAMPLES, 1 + len(rest), seed)
+            return float(surrogate.device_gp.score_joint(cfg, x[:1], rest, z)[0])
         scores = _scores_for(surrogate.device_gp, cfg, x, pend, seed, DEFAULT_MC_SAMPLES)
         return pd.Series(scores.double().cpu().numpy(), index=candidates.index)
 

@@ -505,8 +505,12 @@ static int launch_family(FusedParams& p, int lag, int grid, size_t smem, cudaStr
 // Wide-feature models: per block of <= wide_ws_rows candidates, k_kmat_tc writes the K* block into the
 // (L2-sized) workspace inside the model blob and k_fused<PRE> consumes it; both on the caller's stream.
 static int launch_wide_blocks(const bb_model* m, const FusedParams& full, int lag, int sms, int max_smem,
-                              cudaStream_t stream) {
+                              const WideCross* wc, cudaStream_t stream) {
   BB_CHECK_SUPPORTED(m->d_wide_ws != nullptr && m->wide_ws_rows >= 256, "wide model without workspace");
+  if (wc != nullptr) {
+    const int rcp = launch_pend_images(m, full.layout, wc->pend_x, wc->P, stream);
+    if (rcp != BB_OK) return rcp;
+  }
   const int64_t es = (full.layout == BB_ROW_MAJOR_F64 || full.layout == BB_COL_MAJOR_F64) ? 8 : 4;
   const bool col_major = (full.layout == BB_COL_MAJOR_F32 || full.layout == BB_COL_MAJOR_F64);
   for (int64_t b0 = 0; b0 < full.N; b0 += m->wide_ws_rows) {
@@ -518,6 +522,10 @@ static int launch_wide_blocks(const bb_model* m, const FusedParams& full, int la
     int rc = launch_kmat_wide(m, xb, full.layout, nb, full.ldx, m->d_wide_ws, m->n_pad, rows_pad, m->n_pad,
                               stream);
     if (rc != BB_OK) return rc;
+    if (wc != nullptr) {
+      rc = launch_cross_wide(m, xb, full.layout, nb, full.ldx, wc->pend_beta, wc->P, wc->cross + b0 * wc->P, stream);
+      if (rc != BB_OK) return rc;
+    }
     FusedParams p = full;
     p.x = xb;
     p.N = nb;
@@ -559,7 +567,7 @@ static int g_trace_cap = 0;
 int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
                  const bb_acq_spec* acq, const float* d_z, int32_t S, const uint8_t* d_keep,
                  float* d_mu, float* d_var, float* d_score, int64_t* d_best_key,
-                 int64_t index_offset, cudaStream_t stream) {
+                 int64_t index_offset, cudaStream_t stream, const WideCross* wc = nullptr) {
   BB_CHECK_ARG(m && m->abi_version == BB_ABI_VERSION, "model struct missing or ABI mismatch");
   BB_CHECK_ARG(d_x != nullptr || N == 0, "candidate pointer is null");
   BB_CHECK_ARG(layout >= 0 && layout <= BB_BITS_U8, "unknown candidate layout %d", layout);
@@ -637,7 +645,7 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   BB_CUDA(cudaGetDevice(&dev));
   BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  if (m->wide) return launch_wide_blocks(m, p, lag, sms, max_smem, stream);
+  if (m->wide) return launch_wide_blocks(m, p, lag, sms, max_smem, wc, stream);
   if (fused_tc_supported(p, max_smem)) {
     const int grid_tc = p.num_tiles < sms ? p.num_tiles : sms;
     return launch_fused_tc(p, grid_tc, stream);
@@ -710,6 +718,14 @@ extern "C" int bb_posterior(const bb_model* m, const void* d_x, int32_t layout, 
                             const float* d_pend_x, const float* d_pend_beta, int32_t n_pending,
                             void* stream) {
   BB_CHECK_ARG(N == 0 || (d_mu != nullptr && d_var != nullptr), "bb_posterior: output pointers are null");
+  if (m && m->abi_version == BB_ABI_VERSION && m->wide && d_cross != nullptr && n_pending > 0) {
+    // wide-feature models: the cross-covariances reuse each K* block while it sits in the workspace
+    BB_CHECK_ARG(d_pend_x && d_pend_beta, "pending buffers are null");
+    BB_CHECK_ARG(n_pending <= BB_MAX_PENDING, "n_pending=%d outside [1,%d]", n_pending, BB_MAX_PENDING);
+    WideCross wc{d_pend_x, d_pend_beta, n_pending, d_cross};
+    return launch_fused(m, d_x, layout, N, ldx, nullptr, nullptr, 0, nullptr, d_mu, d_var, nullptr, nullptr, 0,
+                        (cudaStream_t)stream, &wc);
+  }
   int rc = launch_fused(m, d_x, layout, N, ldx, nullptr, nullptr, 0, nullptr, d_mu, d_var, nullptr,
                         nullptr, 0, (cudaStream_t)stream);
   if (rc != BB_OK) return rc;

@@ -118,6 +118,16 @@ __device__ __forceinline__ void split3_quad(const float (&x)[4], uint2& hi, uint
 
 int launch_fused_tc(FusedParams& p, int grid, cudaStream_t stream);
 bool fused_tc_supported(FusedParams& p, int max_smem);
+int launch_pend_images(const bb_model* m, int32_t layout, const float* d_pend_x, int32_t P, cudaStream_t stream);
+int launch_cross_wide(const bb_model* m, const void* d_x, int32_t layout, int64_t nb, int64_t ldx,
+                      const float* d_pend_beta, int32_t P, float* d_cross_blk, cudaStream_t stream);
+// pending-point request threaded through launch_fused on the wide path (null members: none)
+struct WideCross {
+  const float* pend_x;
+  const float* pend_beta;
+  int32_t P;
+  float* cross;
+};
 int launch_kmat_wide(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
                      float* d_out, int64_t ldk, int64_t out_rows, int out_cols, cudaStream_t stream);
 

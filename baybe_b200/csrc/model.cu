@@ -31,7 +31,7 @@ const char* last_error() { return g_err; }
 struct BlobLayout {
   size_t cand_scale, cand_shift, train_m2, train_sq, alpha, train_task, task_covar, mean_const,
       rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, bimg, rimg2, flags,
-      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, rimg2g, total;
+      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, rimg2g, pend_img, pend_norm2, pend_task, kpend_ws, total;
   int n_pad, d_pad, n_chunks, n_tiles;
   int wide, d_wide;
   int64_t wide_ws_rows;
@@ -84,6 +84,7 @@ static BlobLayout make_layout(int n, int d, int T) {
   if (const char* f = getenv("BAYBE_B200_FORCE_WIDE")) L.wide = (f[0] == '1') ? 1 : L.wide;  // experiments
   L.d_wide = round_up(d, 32);
   L.wimg = L.wimg_bits = L.wnorm_bits = L.wsrc = L.wide_ws = L.rimg4 = 0;
+  L.pend_img = L.pend_norm2 = L.pend_task = L.kpend_ws = 0;
   L.wide_ws_rows = 0;
   if (L.wide) {
     const size_t img = (size_t)L.n_pad * L.d_wide * 2 * 3;
@@ -94,6 +95,10 @@ static BlobLayout make_layout(int n, int d, int T) {
     L.rimg4 = take((size_t)L.n_tiles * 16384);
     L.wide_ws_rows = kWideWsRows;
     L.wide_ws = take(sizeof(float) * (size_t)L.wide_ws_rows * L.n_pad);
+    L.pend_img = take((size_t)64 * L.d_wide * 2 * 3);
+    L.pend_norm2 = take(sizeof(float) * 64);
+    L.pend_task = take(sizeof(int32_t) * 64);
+    L.kpend_ws = take(sizeof(float) * (size_t)L.wide_ws_rows * 64);
   }
   L.total = off;
   return L;
@@ -784,8 +789,17 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
     BB_LAUNCH_CHECK();
   }
 
-  float dist_scale_w = 1.0f;
+  float dist_scale_w = 1.0f, dist_scale_p = 1.0f, dist_scale_wp = 1.0f;
   if (L.wide) {
+    // pending points lie inside the scaling bounds like candidates: bound their operand magnitudes there
+    float wp_max = 1e-30f;
+    for (int j = 0; j < d; ++j) {
+      const float aj = fmaxf(fabsf((float)desc->lower[j] * cscale[j] + cshift[j]),
+                             fabsf((float)desc->upper[j] * cscale[j] + cshift[j]));
+      wp_max = fmaxf(wp_max, fabsf(cscale[j]) * (2.0f * aj + fabsf(cscale[j]) + 2.0f * fabsf(cshift[j])));
+    }
+    dist_scale_p = ldexpf(1.0f, (int)floorf(log2f(30000.0f / (2.0f * a_abs_max))));
+    dist_scale_wp = ldexpf(1.0f, (int)floorf(log2f(30000.0f / wp_max)));
     // float layouts: B = -2 b (same numbers as d_train_m2, K-chunked)
     std::vector<float> src((size_t)L.n_pad * L.d_wide, 0.f);
     for (int i = 0; i < n; ++i)
@@ -864,6 +878,12 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
     out->d_wnorm_bits = (const float*)(B + L.wnorm_bits);
     out->d_wide_ws = (float*)(B + L.wide_ws);
     out->d_rimg4 = B + L.rimg4;
+    out->d_pend_img = B + L.pend_img;
+    out->d_pend_norm = (float*)(B + L.pend_norm2);
+    out->d_pend_task = (int32_t*)(B + L.pend_task);
+    out->d_kpend_ws = (float*)(B + L.kpend_ws);
+    out->dist_scale_p = dist_scale_p;
+    out->dist_scale_wp = dist_scale_wp;
     out->wide_ws_rows = L.wide_ws_rows;
     out->dist_scale_w = dist_scale_w;
   }

@@ -422,15 +422,19 @@ static int launch_kmat_family(WideParams& p, bool bits, int sms, int max_smem, c
               : launch_kmat_one<FAMILY, false>(p, sms, max_smem, stream);
 }
 
-// K(X*[0..N), X) -> d_out[row * ldk + i]; rows < out_rows and columns < out_cols are written.
-int launch_kmat_wide(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
-                     float* d_out, int64_t ldk, int64_t out_rows, int out_cols, cudaStream_t stream) {
-  BB_CHECK_SUPPORTED(m->wide != 0, "model has no wide-feature images");
-  BB_CHECK_SUPPORTED(m->family != BB_KERNEL_MATERN12,
-                     "Matern-1/2 is not supported on the wide-feature path (GEMM-form distances are "
-                     "singular at r = 0)");
+// Column set of a K(X*, .) launch: the training rows (model images) or the pending points (scratch images).
+struct WideColumns {
+  const uint8_t* wimg;
+  const float* wnorm;
+  const int32_t* task;
+  int n, n_pad;
+  float inv_scale;
+};
+
+static int launch_kmat_cols(const bb_model* m, const WideColumns& c, const void* d_x, int32_t layout, int64_t N,
+                            int64_t ldx, float* d_out, int64_t ldk, int64_t out_rows, int out_cols,
+                            cudaStream_t stream) {
   const bool bits = layout == BB_BITS_U8;
-  BB_CHECK_SUPPORTED(!(bits && m->task_col >= 0), "bit-packed candidates cannot carry a task column");
   WideParams p;
   memset(&p, 0, sizeof(p));
   p.x = d_x;
@@ -438,17 +442,17 @@ int launch_kmat_wide(const bb_model* m, const void* d_x, int32_t layout, int64_t
   p.N = N;
   p.ldx = ldx;
   p.d = m->d;
-  p.n = m->n;
-  p.n_pad = m->n_pad;
-  p.n_halves = (m->n_pad + kWHalfN - 1) / kWHalfN;
+  p.n = c.n;
+  p.n_pad = c.n_pad;
+  p.n_halves = (c.n_pad + kWHalfN - 1) / kWHalfN;
   p.n_kc = m->d_wide / kWK;
   p.cand_scale = m->d_cand_scale;
   p.cand_shift = m->d_cand_shift;
-  p.wimg = reinterpret_cast<const uint8_t*>(bits ? m->d_wimg_bits : m->d_wimg);
-  p.wnorm = bits ? m->d_wnorm_bits : m->d_train_sq;
+  p.wimg = c.wimg;
+  p.wnorm = c.wnorm;
   p.a_scale = bits ? 1.0f : m->dist_scale_a;
-  p.inv_scale = bits ? 1.0f / m->dist_scale_w : 1.0f / (m->dist_scale_a * m->dist_scale_b);
-  p.train_task = m->d_train_task;
+  p.inv_scale = c.inv_scale;
+  p.train_task = c.task;
   p.task_covar = m->d_task_covar;
   p.task_col = m->task_col;
   p.n_tasks = m->n_tasks;
@@ -469,6 +473,152 @@ int launch_kmat_wide(const bb_model* m, const void* d_x, int32_t layout, int64_t
     case BB_KERNEL_MATERN52: return launch_kmat_family<BB_KERNEL_MATERN52>(p, bits, sms, max_smem, stream);
     default: return launch_kmat_family<BB_KERNEL_RBF>(p, bits, sms, max_smem, stream);
   }
+}
+
+static int wide_checks(const bb_model* m, int32_t layout) {
+  BB_CHECK_SUPPORTED(m->wide != 0, "model has no wide-feature images");
+  BB_CHECK_SUPPORTED(m->family != BB_KERNEL_MATERN12,
+                     "Matern-1/2 is not supported on the wide-feature path (GEMM-form distances are "
+                     "singular at r = 0)");
+  BB_CHECK_SUPPORTED(!(layout == BB_BITS_U8 && m->task_col >= 0), "bit-packed candidates cannot carry a task column");
+  return BB_OK;
+}
+
+// K(X*[0..N), X) -> d_out[row * ldk + i]; rows < out_rows and columns < out_cols are written.
+int launch_kmat_wide(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
+                     float* d_out, int64_t ldk, int64_t out_rows, int out_cols, cudaStream_t stream) {
+  const int rc = wide_checks(m, layout);
+  if (rc != BB_OK) return rc;
+  const bool bits = layout == BB_BITS_U8;
+  WideColumns c;
+  c.wimg = reinterpret_cast<const uint8_t*>(bits ? m->d_wimg_bits : m->d_wimg);
+  c.wnorm = bits ? m->d_wnorm_bits : m->d_train_sq;
+  c.task = m->d_train_task;
+  c.n = m->n;
+  c.n_pad = m->n_pad;
+  c.inv_scale = bits ? 1.0f / m->dist_scale_w : 1.0f / (m->dist_scale_a * m->dist_scale_b);
+  return launch_kmat_cols(m, c, d_x, layout, N, ldx, d_out, ldk, out_rows, out_cols, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// pending points (sequential greedy, K9 prologue) on the wide path: the <= 31 pending rows become a
+// 64-column "training set" of their own -- k(x*, pending) comes out of the same tensor-core kernel --
+// and the posterior cross-covariance  cov(x*, p_j) = k(x*, p_j) - K*(x*) . beta_j  is a small CUDA-core
+// contraction over the K* block that is already in the workspace.
+// ------------------------------------------------------------------------------------------
+// One CTA per pending row pp < 64 (rows >= P are zero): operand image (float form: -2 b; bit-linear form:
+// W = s (-2 b + s + 2 h)), additive norm term, task id.
+__global__ void __launch_bounds__(256) k_build_pend_img(const float* __restrict__ pend_x, int P, int d, int d_wide,
+                                                        const float* __restrict__ cscale, const float* __restrict__ cshift,
+                                                        int bits, float scale, int task_col, int n_tasks,
+                                                        uint8_t* __restrict__ img, float* __restrict__ norm,
+                                                        int32_t* __restrict__ task) {
+  __shared__ double red[256];
+  const int pp = blockIdx.x, panels = bits ? 2 : 3;
+  const size_t panel = 64 * 64;  // bytes: 64 rows x 32 fp16
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < d_wide; k += blockDim.x) {
+    float b = 0.f, sk = 0.f, hk = 0.f;
+    if (pp < P && k < d) {
+      sk = __ldg(cscale + k);
+      hk = __ldg(cshift + k);
+      b = fmaf(__ldg(pend_x + (size_t)pp * d + k), sk, hk);
+    }
+    float v;
+    if (bits) {
+      v = sk * (-2.0f * b + sk + 2.0f * hk);
+      acc += (double)b * b + (double)hk * (-2.0 * (double)b + (double)hk);
+    } else {
+      v = -2.0f * b;
+      acc += (double)b * b;
+    }
+    v *= scale;
+    const int kc = k >> 5, kl = k & 31;
+    const size_t base = (size_t)kc * panels * panel;
+    const uint32_t off = swk_offset<32>((uint32_t)pp, (uint32_t)(kl >> 3)) + (uint32_t)(kl & 7) * 2u;
+    const __half h = __float2half_rn(v);
+    const float r1 = v - __half2float(h);
+    const __half mid = __float2half_rn(r1);
+    *reinterpret_cast<__half*>(img + base + off) = h;
+    *reinterpret_cast<__half*>(img + base + panel + off) = mid;
+    if (panels > 2) *reinterpret_cast<__half*>(img + base + 2 * panel + off) = __float2half_rn(r1 - __half2float(mid));
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    norm[pp] = pp < P ? (float)red[0] : 0.f;
+    int t = 0;
+    if (task_col >= 0 && pp < P)
+      t = min(max(__float2int_rn(__ldg(pend_x + (size_t)pp * d + task_col)), 0), n_tasks - 1);
+    task[pp] = t;
+  }
+}
+
+// cross[row][j] = y_std^2 * ( kpend[row][j] - sum_i kstar[row][i] beta[j][i] ): one warp per candidate row.
+__global__ void __launch_bounds__(256) k_cross_pre(const float* __restrict__ kstar, const float* __restrict__ kpend,
+                                                   const float* __restrict__ beta, int P, int n_pad, int64_t nrows,
+                                                   float s2, float* __restrict__ cross) {
+  extern __shared__ float beta_s[];  // [P][n_pad]
+  for (int e = threadIdx.x; e < P * n_pad; e += blockDim.x) beta_s[e] = __ldg(beta + e);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + wib; row < nrows; row += (int64_t)gridDim.x * wpb) {
+    float acc[BB_MAX_PENDING];
+#pragma unroll
+    for (int j = 0; j < BB_MAX_PENDING; ++j) acc[j] = 0.f;
+    const float* kr = kstar + row * n_pad;
+    for (int i = lane; i < n_pad; i += 32) {
+      const float kv = kr[i];
+#pragma unroll
+      for (int j = 0; j < BB_MAX_PENDING; ++j)
+        if (j < P) acc[j] = fmaf(kv, beta_s[j * n_pad + i], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < BB_MAX_PENDING; ++j) {
+      if (j < P) {
+        float v = acc[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) cross[row * P + j] = s2 * (kpend[row * 64 + j] - v);
+      }
+    }
+  }
+}
+
+// Scratch images of the pending rows (once per bb_posterior call).
+int launch_pend_images(const bb_model* m, int32_t layout, const float* d_pend_x, int32_t P, cudaStream_t stream) {
+  const bool bits = layout == BB_BITS_U8;
+  k_build_pend_img<<<64, 256, 0, stream>>>(d_pend_x, P, m->d, m->d_wide, m->d_cand_scale, m->d_cand_shift, bits ? 1 : 0,
+                                           bits ? m->dist_scale_wp : m->dist_scale_p, m->task_col, m->n_tasks,
+                                           reinterpret_cast<uint8_t*>(m->d_pend_img), m->d_pend_norm, m->d_pend_task);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+// One block of candidates: k(x*, pending) through k_kmat_tc, then the cross-covariances from the K* block
+// that launch_kmat_wide left in the workspace.
+int launch_cross_wide(const bb_model* m, const void* d_x, int32_t layout, int64_t nb, int64_t ldx,
+                      const float* d_pend_beta, int32_t P, float* d_cross_blk, cudaStream_t stream) {
+  const bool bits = layout == BB_BITS_U8;
+  WideColumns c;
+  c.wimg = reinterpret_cast<const uint8_t*>(m->d_pend_img);
+  c.wnorm = m->d_pend_norm;
+  c.task = m->d_pend_task;
+  c.n = P;
+  c.n_pad = 64;
+  c.inv_scale = bits ? 1.0f / m->dist_scale_wp : 1.0f / (m->dist_scale_a * m->dist_scale_p);
+  const int64_t rows_pad = (nb + 255) / 256 * 256;
+  int rc = launch_kmat_cols(m, c, d_x, layout, nb, ldx, m->d_kpend_ws, 64, rows_pad, 64, stream);
+  if (rc != BB_OK) return rc;
+  const size_t smem = (size_t)P * m->n_pad * sizeof(float);
+  BB_CUDA(cudaFuncSetAttribute(k_cross_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_cross_pre<<<148 * 4, 256, smem, stream>>>(m->d_wide_ws, m->d_kpend_ws, d_pend_beta, P, m->n_pad, nb,
+                                              m->y_std * m->y_std, d_cross_blk);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
 }
 
 }  // namespace bb

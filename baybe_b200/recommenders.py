@@ -228,3 +228,12 @@ class B200Recommender:
         acqf = acquisition_function or self._get_acquisition_function(objective)
         return acqf.evaluate(candidates, surrogate, searchspace, objective, measurements,
                              pending_experiments, jointly=False)
+
+    def joint_acquisition_value(self, candidates: pd.DataFrame, searchspace, objective, measurements,
+                                pending_experiments: pd.DataFrame | None = None,
+                                acquisition_function: AcquisitionFunction | None = None) -> float:
+        """Joint acquisition value of the whole candidate batch (bayesian/base.py:239-277)."""
+        surrogate = self.get_surrogate(searchspace, objective, measurements)
+        acqf = acquisition_function or self._get_acquisition_function(objective)
+        return acqf.evaluate(candidates, surrogate, searchspace, objective, measurements,
+                             pending_experiments, jointly=True)

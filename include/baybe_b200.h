@@ -150,6 +150,13 @@ typedef struct bb_model {
   int32_t pad2_;
   const void* d_rimg4;       /* L^-1 image grouped in <=256-column tiles (K*-reading kernel)    */
   const void* d_rimg2g;      /* L^-1 image in greedy 128-column pairs (k_fused, n_pad > 256), or NULL */
+  /* wide path, pending points (sequential greedy): scratch images of <=31 pending rows as extra K columns */
+  void* d_pend_img;          /* [64 rows] K-chunked split image, rebuilt per bb_posterior call          */
+  float* d_pend_norm;        /* [64]                                                                    */
+  int32_t* d_pend_task;      /* [64]                                                                    */
+  float* d_kpend_ws;         /* [wide_ws_rows * 64] k(x*, pending) block                                */
+  float dist_scale_p;        /* power-of-two scales of the pending images (float form / bit-linear form) */
+  float dist_scale_wp;
 } bb_model;
 
 /* Acquisition context built by BotorchAcquisitionFunctionBuilder.build

@@ -148,7 +148,8 @@ def test_full_fit_and_transfer_learning_space(cuda_device):
         rec.recommend(10_000, ss, obj, meas)
 
 
-def test_recommend_on_binary_fingerprint_space_uses_bit_layout(cuda_device):
+@pytest.mark.parametrize("batch_size", [1, 3])
+def test_recommend_on_binary_fingerprint_space_uses_bit_layout(batch_size, cuda_device):
     """A comp-rep that is all 0/1 and >= 256 columns wide is kept bit-packed on the device and scored by
     the wide-feature path; the recommendation equals the oracle's arg-max over the float matrix."""
     from baybe_b200 import recommenders as R
@@ -167,7 +168,7 @@ def test_recommend_on_binary_fingerprint_space_uses_bit_layout(cuda_device):
     obj = SingleTargetObjective(NumericalTarget("Yield"))
     rec = B200Recommender(surrogate_model=GaussianProcessSurrogate(hyperparameters=hp))
     torch.manual_seed(11)
-    out = rec.recommend(1, ss, obj, meas)
+    out = rec.recommend(batch_size, ss, obj, meas)
     x_dev, _ = R._cache.get(ss.discrete, cuda_device, 0, N)
     assert x_dev.dtype == torch.uint8 and x_dev.shape == (N, d // 8)
     torch.manual_seed(11)
@@ -177,6 +178,38 @@ def test_recommend_on_binary_fingerprint_space_uses_bit_layout(cuda_device):
                             mean_const=0.0)
     acq = oracle.AcqSpec("qLogEI")
     acq.best_f = oracle.best_f_from_training(om, comp, acq)
-    idx, vals = oracle.optimize_acqf_discrete(om, acq, ss.discrete.comp_rep.to_numpy(), q=1, sampler_seed=seed)
+    idx, vals = oracle.optimize_acqf_discrete(om, acq, ss.discrete.comp_rep.to_numpy(), q=batch_size,
+                                              sampler_seed=seed)
     assert list(out.index) == list(ss.discrete.comp_rep.index[idx])
     assert np.allclose(rec._last_acq_values, vals, rtol=2e-3, atol=5e-3)
+
+
+def test_joint_acquisition_value_of_a_batch(cuda_device):
+    """AcquisitionFunction.evaluate(jointly=True) / BayesianRecommender.joint_acquisition_value
+    (acquisition/base.py:112-159, bayesian/base.py:239-277): one q-batch value for the whole candidate set."""
+    from baybe_b200.acquisition import IncompatibleAcquisitionFunctionError, UpperConfidenceBound
+
+    ss = _space()
+    meas = _measure(ss, 15, seed=6)
+    obj = SingleTargetObjective(NumericalTarget("Yield"))
+    rec = B200Recommender(surrogate_model=GaussianProcessSurrogate(hyperparameters=HP))
+    batch = ss.discrete.exp_rep.iloc[[5, 77, 130, 9]]
+    pend = ss.discrete.exp_rep.iloc[[40]]
+    torch.manual_seed(21)
+    got = rec.joint_acquisition_value(batch, ss, obj, meas, pending_experiments=pend)
+    torch.manual_seed(21)
+    seed = int(torch.randint(0, 1_000_000, (1,)))
+    om = _oracle_model(ss, meas, HP)
+    acq = oracle.AcqSpec("qLogEI")
+    acq.best_f = oracle.best_f_from_training(om, ss.transform(meas).to_numpy(), acq)
+    rows = np.concatenate([ss.transform(batch).to_numpy(), ss.transform(pend).to_numpy()], axis=0)
+    z = oracle.sobol_normal_samples(512, len(rows), seed)
+    ref = float(oracle.acq_values_joint(om, acq, rows[:1], rows[1:], z)[0])
+    assert isinstance(got, float) and abs(got - ref) <= 5e-3 + 2e-3 * abs(ref)
+    # a single point valued "jointly" is its ordinary q=1 value
+    torch.manual_seed(21)
+    one = rec.joint_acquisition_value(batch.iloc[:1], ss, obj, meas)
+    torch.manual_seed(21)
+    assert abs(one - float(rec.acquisition_values(batch.iloc[:1], ss, obj, meas).iloc[0])) < 1e-6
+    with pytest.raises(IncompatibleAcquisitionFunctionError):
+        rec.joint_acquisition_value(batch, ss, obj, meas, acquisition_function=UpperConfidenceBound())

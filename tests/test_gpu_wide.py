@@ -102,6 +102,32 @@ def test_wide_scores_and_argmax(kind, name, cuda_device):
     assert float(ref[idx]) >= ref_best - (atol + rtol * abs(ref_best))
 
 
+@pytest.mark.parametrize("P", [1, 5])
+@pytest.mark.parametrize("name", ["d100_n200_m52", "fp2048_n512", "fp1000_n300"])
+def test_wide_joint_scores_with_pending_points(name, P, cuda_device):
+    """Sequential-greedy round on the wide path: pending rows become 64 extra K columns of k_kmat_tc and the
+    cross-covariances are contracted from the K* block in the workspace."""
+    w = WIDE[name]()
+    om = oracle_model(w)
+    gp = _gp(w, cuda_device)
+    oacq = oracle.AcqSpec(kind="qLogEI")
+    oacq.best_f = oracle.best_f_from_training(om, w.train_x, oacq)
+    acq = AcqConfig(kind="qLogEI", best_f=oacq.best_f)
+    rng = np.random.default_rng(P)
+    pend_rows = rng.choice(len(w.candidates), size=P, replace=False)
+    pending = w.candidates[pend_rows]
+    keep = np.setdiff1d(np.arange(len(w.candidates)), pend_rows)[:900]
+    cand = w.candidates[keep]
+    z = sobol_normal_samples(512, 1 + P, seed=99)
+    x = torch.from_numpy(pack_bits(cand)).to(cuda_device) if name.startswith("fp") else \
+        torch.from_numpy(cand).to(cuda_device, torch.float32)
+    got = gp.score_joint(acq, x, pending, z).double().cpu()
+    ref = oracle.acq_values_joint(om, oacq, cand, pending, z)
+    err = (got - ref).abs()
+    assert float((err > 4 * 5e-3 + 4 * 2e-3 * ref.abs()).double().mean()) <= 0.005, float(err.max())
+    assert float(ref[int(torch.argmax(got))]) >= float(ref.max()) - 4 * (5e-3 + 2e-3 * abs(float(ref.max())))
+
+
 def test_bits_and_float_layouts_agree(cuda_device):
     """The bit-linear form and the generic float form are two roundings of the same distances."""
     w = WIDE["fp2048_n512"]()
