@@ -20,7 +20,7 @@ ACQ_KIND = {
 }
 MC_KINDS = ("qLogEI", "qEI", "qUCB", "qSR", "qPI")
 MAX_PENDING = 31
-MAX_TRAIN = 512
+MAX_TRAIN = 1024
 
 BB_ERR_INVALID, BB_ERR_UNSUPPORTED, BB_ERR_CUDA, BB_ERR_NOT_PD, BB_ERR_WORKSPACE = -1, -2, -3, -4, -5
 
@@ -58,6 +58,7 @@ class Model(C.Structure):
         ("d_rimg4", C.c_void_p), ("d_rimg2g", C.c_void_p),
         ("d_pend_img", C.c_void_p), ("d_pend_norm", C.c_void_p), ("d_pend_task", C.c_void_p),
         ("d_kpend_ws", C.c_void_p), ("dist_scale_p", C.c_float), ("dist_scale_wp", C.c_float),
+        ("d_wide_vacc", C.c_void_p),
     ]
 
 

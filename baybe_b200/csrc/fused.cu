@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const FusedSmem s = carve_fused(smem_raw, p);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int C = p.n_chunks;
+  const int C = p.c_count;  // K* chunks feeding this launch's column panel
+  const int ncol = (p.sb_hi - p.sb_lo) * kChunk;  // V columns of the panel
   const int dq = p.d_pad >> 2;
   if (tid == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();  // swizzled tiles need 1024-B alignment
 
@@ -208,8 +209,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
       tc_fence_after();
       {
         float ss = 0.f;
-        const uint32_t col0 = tmem_base + lane_base + (uint32_t)(buf * p.n_pad);
-        for (int cb = sg; cb * 32 < p.n_pad; cb += 4) {
+        const uint32_t col0 = tmem_base + lane_base + (uint32_t)(buf * ncol);
+        for (int cb = sg; cb * 32 < ncol; cb += 4) {
           float v[32];
           tmem_ld32(col0 + (uint32_t)(cb * 32), v);
           tmem_ld_wait();
@@ -228,8 +229,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
       float msum = s.meanc[ct];
 #pragma unroll
       for (int gg = 0; gg < 8; ++gg) msum += mpart[gg * kTileM + row_e];
-      const float vsum = (s.var_part[row_e] + s.var_part[kTileM + row_e]) +
-                         (s.var_part[2 * kTileM + row_e] + s.var_part[3 * kTileM + row_e]);
+      float vsum = (s.var_part[row_e] + s.var_part[kTileM + row_e]) +
+                   (s.var_part[2 * kTileM + row_e] + s.var_part[3 * kTileM + row_e]);
+      if (p.vacc_in != nullptr && e_row0 + row_e < p.N) vsum += p.vacc_in[e_row0 + row_e];
+      if (p.vacc_out != nullptr) {  // earlier column panel of a model with n_pad > 512: partial only
+        if (sg == 0 && e_row0 + row_e < p.N) p.vacc_out[e_row0 + row_e] = vsum;
+        bar_compute();  // partial buffers are rewritten by the next epilogue
+        return;
+      }
       const float kss = p.scaled ? s.tcov[ct * p.n_tasks + ct] : 1.0f;
       const float var_t = fmaxf(kss - vsum * p.inv_r_scale2, 1e-10f);
       const float mu = fmaf(p.y_std, msum, p.y_mean);
@@ -410,8 +417,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         size_t off = 0;
         for (int c = 0; c < C; ++c) {
-          for (int sb = c; sb < C;) {
-            const int gsz = (C - sb) < GMAX ? (C - sb) : GMAX;
+          for (int sb = c > p.sb_lo ? c : p.sb_lo; sb < p.sb_hi;) {
+            const int gsz = (p.sb_hi - sb) < GMAX ? (p.sb_hi - sb) : GMAX;
             const uint32_t bytes = (uint32_t)gsz * kStageBBytes;
             mbar_wait_relaxed(&s.b_empty[st], ph ^ 1u);
             mbar_expect_tx(&s.b_full[st], bytes);
@@ -439,22 +446,22 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
         // the epilogue that last read this accumulator has drained it
         mbar_wait_relaxed(&s.d_empty[buf], (uint32_t)((use & 1) ^ 1));
         tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)(buf * p.n_pad);
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * ncol);
         for (int c = 0; c < C; ++c) {
           mbar_wait_relaxed(&s.a_full[slot], pha);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(s.ring_a + (size_t)slot * kSlotABytes);
           const uint64_t a_hi = make_sw128_desc(a_addr);
           const uint64_t a_lo = make_sw128_desc(a_addr + 16384);
-          for (int sb = c; sb < C;) {
-            const int gsz = (C - sb) < GMAX ? (C - sb) : GMAX;
+          for (int sb = c > p.sb_lo ? c : p.sb_lo; sb < p.sb_hi;) {
+            const int gsz = (p.sb_hi - sb) < GMAX ? (p.sb_hi - sb) : GMAX;
             const uint32_t idesc = make_idesc_f16(kTileM, gsz * kChunk);
             mbar_wait_relaxed(&s.b_full[st], phb);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(s.ring_b + (size_t)st * p.stage_b_bytes);
             const uint64_t b_hi = make_sw128_desc(b_addr);
             const uint64_t b_lo = make_sw128_desc(b_addr + (uint32_t)gsz * 8192u);
-            const uint32_t d_addr = d_base + (uint32_t)(sb * kChunk);
+            const uint32_t d_addr = d_base + (uint32_t)((sb - p.sb_lo) * kChunk);
             sb += gsz;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -526,37 +533,64 @@ static int launch_wide_blocks(const bb_model* m, const FusedParams& full, int la
       rc = launch_cross_wide(m, xb, full.layout, nb, full.ldx, wc->pend_beta, wc->P, wc->cross + b0 * wc->P, stream);
       if (rc != BB_OK) return rc;
     }
-    FusedParams p = full;
-    p.x = xb;
-    p.N = nb;
-    p.num_tiles = (int)((nb + kTileM - 1) / kTileM);
-    p.kpre = m->d_wide_ws;
-    p.ldk = m->n_pad;
-    p.d = 0;
-    p.d_pad = 0;  // nothing of the feature dimension is staged by the K*-reading kernel
-    if (p.mu) p.mu += b0;
-    if (p.var) p.var += b0;
-    if (p.score) p.score += b0;
-    if (p.keep) p.keep += b0;
-    p.index_offset = full.index_offset + b0;
-    p.rimg = reinterpret_cast<const uint8_t*>(m->d_rimg4);
-    p.stage_b_bytes = 4 * kStageBBytes;  // groups of up to four sub-blocks: N = 256 MMAs
-    p.slots_a = 2;
-    p.stages_b = 2;
-    while (true) {
-      FusedParams t = p;
-      if (t.slots_a < 3) t.slots_a++;
-      else if (t.stages_b < 3) t.stages_b++;
-      else break;
-      if (fused_smem_bytes(t) > (size_t)max_smem) break;
-      p = t;
+    // V column panels: TMEM holds 512 columns, so a model with n_pad > 512 takes two passes over the K* block
+    // (the first only leaves its |V|^2 partial in the workspace)
+    const int C = m->n_chunks;
+    const int n_pass = C > 8 ? 2 : 1;
+    size_t rimg_off = 0;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      FusedParams p = full;
+      p.x = xb;
+      p.N = nb;
+      p.num_tiles = (int)((nb + kTileM - 1) / kTileM);
+      p.kpre = m->d_wide_ws;
+      p.ldk = m->n_pad;
+      p.d = 0;
+      p.d_pad = 0;  // nothing of the feature dimension is staged by the K*-reading kernel
+      p.sb_lo = pass == 0 ? 0 : 8;
+      p.sb_hi = (n_pass == 2 && pass == 0) ? 8 : C;
+      p.c_count = p.sb_hi;
+      const bool last = pass == n_pass - 1;
+      if (last) {
+        if (p.mu) p.mu += b0;
+        if (p.var) p.var += b0;
+        if (p.score) p.score += b0;
+        if (p.keep) p.keep += b0;
+        p.index_offset = full.index_offset + b0;
+        p.vacc_in = pass > 0 ? m->d_wide_vacc : nullptr;
+      } else {
+        p.mu = p.var = p.score = nullptr;
+        p.keep = nullptr;
+        p.best_key = nullptr;
+        p.has_acq = 0;
+        p.vacc_out = m->d_wide_vacc;
+      }
+      const int ncol = (p.sb_hi - p.sb_lo) * kChunk;
+      const int plag = (2 * ncol <= 512) ? 1 : 0;
+      uint32_t cols = 32;
+      while ((int)cols < (plag ? 2 : 1) * ncol) cols <<= 1;
+      p.tmem_cols = cols;
+      p.rimg = reinterpret_cast<const uint8_t*>(m->d_rimg4) + rimg_off;
+      for (int c = 0; c < p.c_count; ++c)  // bytes of this panel's image = its (chunk, sub-block) tile count
+        rimg_off += (size_t)(p.sb_hi - (c > p.sb_lo ? c : p.sb_lo)) * kStageBBytes;
+      p.stage_b_bytes = 4 * kStageBBytes;  // groups of up to four sub-blocks: N = 256 MMAs
+      p.slots_a = 2;
+      p.stages_b = 2;
+      while (true) {
+        FusedParams t = p;
+        if (t.slots_a < 3) t.slots_a++;
+        else if (t.stages_b < 3) t.stages_b++;
+        else break;
+        if (fused_smem_bytes(t) > (size_t)max_smem) break;
+        p = t;
+      }
+      const size_t smem = fused_smem_bytes(p);
+      BB_CHECK_SUPPORTED(smem <= (size_t)max_smem, "shared-memory budget exceeded: need %zu bytes", smem);
+      const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+      rc = plag ? launch_one<BB_KERNEL_RBF, 1, true, 4>(p, grid, smem, stream)
+                : launch_one<BB_KERNEL_RBF, 0, true, 4>(p, grid, smem, stream);
+      if (rc != BB_OK) return rc;
     }
-    const size_t smem = fused_smem_bytes(p);
-    BB_CHECK_SUPPORTED(smem <= (size_t)max_smem, "shared-memory budget exceeded: need %zu bytes", smem);
-    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-    rc = lag ? launch_one<BB_KERNEL_RBF, 1, true, 4>(p, grid, smem, stream)
-             : launch_one<BB_KERNEL_RBF, 0, true, 4>(p, grid, smem, stream);
-    if (rc != BB_OK) return rc;
   }
   return BB_OK;
 }
@@ -615,6 +649,9 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   p.d = m->d;
   p.d_pad = m->d_pad;
   p.n_chunks = m->n_chunks;
+  p.sb_lo = 0;
+  p.sb_hi = m->n_chunks;
+  p.c_count = m->n_chunks;
   p.task_col = m->task_col;
   p.n_tasks = m->n_tasks;
   p.y_mean = m->y_mean;
@@ -635,7 +672,7 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   p.stage_b_bytes = kStageBBytes;
   p.trace = g_trace_buf;
   p.trace_cap = g_trace_cap;
-  BB_CHECK_SUPPORTED(p.n_pad <= 512, "n_pad=%d exceeds the 512 TMEM columns", p.n_pad);
+  BB_CHECK_SUPPORTED(p.n_pad <= 512 || m->wide, "n_pad=%d exceeds the 512 TMEM columns", p.n_pad);
   const int lag = (2 * p.n_pad <= 512) ? 1 : 0;  // two accumulators fit: defer the epilogue
   uint32_t cols = 32;
   while ((int)cols < (lag ? 2 : 1) * p.n_pad) cols <<= 1;

@@ -52,6 +52,11 @@ struct FusedParams {
   const uint8_t* keep;
   long long* best_key;
   int64_t index_offset;
+  // column panel of V handled by this launch (TMEM holds 512 columns): sub-blocks [sb_lo, sb_hi) of 64 columns,
+  // fed by the first c_count K* chunks; a model with n_pad <= 512 is one panel (0, n_chunks, n_chunks)
+  int sb_lo, sb_hi, c_count;
+  const float* vacc_in;   // |V|^2 partial of the earlier panels (null: none)
+  float* vacc_out;        // non-null: this is not the last panel -- store the partial and stop
   const float* kpre;  // wide-feature path: K* block already materialised by k_kmat_tc (else null)
   int64_t ldk;
   long long* trace;  // test-only event trace (bb_debug_set_trace); null in normal operation

@@ -31,7 +31,7 @@ const char* last_error() { return g_err; }
 struct BlobLayout {
   size_t cand_scale, cand_shift, train_m2, train_sq, alpha, train_task, task_covar, mean_const,
       rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, bimg, rimg2, flags,
-      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, rimg2g, pend_img, pend_norm2, pend_task, kpend_ws, total;
+      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, rimg2g, pend_img, pend_norm2, pend_task, kpend_ws, vacc, total;
   int n_pad, d_pad, n_chunks, n_tiles;
   int wide, d_wide;
   int64_t wide_ws_rows;
@@ -80,11 +80,11 @@ static BlobLayout make_layout(int n, int d, int T) {
   L.rimg2 = take((size_t)L.n_tiles * 16384);
   L.flags = take(64);
   L.rimg2g = L.n_chunks > 4 ? take((size_t)L.n_tiles * 16384) : 0;
-  L.wide = ((size_t)L.n_pad * L.d_pad * 4 > kResidentTrainBytes) ? 1 : 0;
+  L.wide = ((size_t)L.n_pad * L.d_pad * 4 > kResidentTrainBytes || L.n_pad > 512) ? 1 : 0;
   if (const char* f = getenv("BAYBE_B200_FORCE_WIDE")) L.wide = (f[0] == '1') ? 1 : L.wide;  // experiments
   L.d_wide = round_up(d, 32);
   L.wimg = L.wimg_bits = L.wnorm_bits = L.wsrc = L.wide_ws = L.rimg4 = 0;
-  L.pend_img = L.pend_norm2 = L.pend_task = L.kpend_ws = 0;
+  L.pend_img = L.pend_norm2 = L.pend_task = L.kpend_ws = L.vacc = 0;
   L.wide_ws_rows = 0;
   if (L.wide) {
     const size_t img = (size_t)L.n_pad * L.d_wide * 2 * 3;
@@ -99,6 +99,7 @@ static BlobLayout make_layout(int n, int d, int T) {
     L.pend_norm2 = take(sizeof(float) * 64);
     L.pend_task = take(sizeof(int32_t) * 64);
     L.kpend_ws = take(sizeof(float) * (size_t)L.wide_ws_rows * 64);
+    L.vacc = take(sizeof(float) * (size_t)L.wide_ws_rows);
   }
   L.total = off;
   return L;
@@ -389,22 +390,23 @@ __global__ void k_build_rimg(const double* __restrict__ Linv, int n, int n_chunk
 // sub-blocks starting at s = c (N = 256 MMAs; the K*-reading kernel of the wide path).
 // gmax = -2: greedy groups of two (k_fused with N = 128 MMAs when n_pad > 256).
 __host__ __device__ inline int rimg_group(int gmax, int s, int n_chunks) {
-  if (gmax == 2) return ((s & 1) == 0 && s + 1 < n_chunks) ? 2 : 1;
+  if (gmax == 2) return ((s & 1) == 0 && s + 1 < n_chunks) ? 2 : 1;  // n_chunks: end of the panel
   const int g = gmax < 0 ? -gmax : gmax;
   return (n_chunks - s) < g ? (n_chunks - s) : g;
 }
 
+// [sb_lo, sb_hi): the column panel the image serves (fed by chunks c < c_count); whole matrix = (0, C, C).
 __global__ void k_build_rimg2(const double* __restrict__ Linv, int n, int n_chunks, double scale,
-                              int gmax, uint8_t* __restrict__ rimg2) {
+                              int gmax, int sb_lo, int sb_hi, int c_count, uint8_t* __restrict__ rimg2) {
   // decode group -> (c, first sub-block s, size g) and byte offset
   int grp = blockIdx.x, c = 0, s0 = 0, g = 1;
   size_t off = 0;
   bool found = false;
   int idx = 0;
-  for (c = 0; c < n_chunks && !found; ++c) {
-    int s = c;
-    while (s < n_chunks) {
-      const int gg = rimg_group(gmax, s, n_chunks);
+  for (c = 0; c < c_count && !found; ++c) {
+    int s = c > sb_lo ? c : sb_lo;
+    while (s < sb_hi) {
+      const int gg = rimg_group(gmax, s, sb_hi);
       if (idx == grp) {
         s0 = s;
         g = gg;
@@ -759,21 +761,33 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
         sb += g;
         ++n_groups;
       }
-    k_build_rimg2<<<n_groups, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, 2, B + L.rimg2);
+    k_build_rimg2<<<n_groups, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, 2, 0, L.n_chunks, L.n_chunks,
+                                                B + L.rimg2);
     BB_LAUNCH_CHECK();
     if (L.n_chunks > 4) {  // n_pad > 256: k_fused pairs the V sub-blocks greedily
       int n_groups2 = 0;
       for (int c = 0; c < L.n_chunks; ++c)
         for (int sb = c; sb < L.n_chunks; sb += rimg_group(-2, sb, L.n_chunks)) ++n_groups2;
-      k_build_rimg2<<<n_groups2, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, -2, B + L.rimg2g);
+      k_build_rimg2<<<n_groups2, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, -2, 0, L.n_chunks, L.n_chunks,
+                                                   B + L.rimg2g);
       BB_LAUNCH_CHECK();
     }
     if (L.wide) {
-      int n_groups4 = 0;
-      for (int c = 0; c < L.n_chunks; ++c)
-        for (int sb = c; sb < L.n_chunks; sb += rimg_group(4, sb, L.n_chunks)) ++n_groups4;
-      k_build_rimg2<<<n_groups4, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, 4, B + L.rimg4);
-      BB_LAUNCH_CHECK();
+      // one image per V column panel (<= 8 sub-blocks = 512 TMEM columns), stored back to back
+      size_t off4 = 0;
+      for (int lo = 0; lo < L.n_chunks; lo += 8) {
+        const int hi = L.n_chunks < lo + 8 ? L.n_chunks : lo + 8;
+        int n_groups4 = 0;
+        size_t tiles = 0;
+        for (int c = 0; c < hi; ++c) {
+          const int s0 = c > lo ? c : lo;
+          tiles += (size_t)(hi - s0);
+          for (int sb = s0; sb < hi; sb += rimg_group(4, sb, hi)) ++n_groups4;
+        }
+        k_build_rimg2<<<n_groups4, 256, 0, stream>>>(dLinv, n, L.n_chunks, scale, 4, lo, hi, hi, B + L.rimg4 + off4);
+        BB_LAUNCH_CHECK();
+        off4 += tiles * 16384;
+      }
     }
   }
   int dist_k = 0;
@@ -882,6 +896,7 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
     out->d_pend_norm = (float*)(B + L.pend_norm2);
     out->d_pend_task = (int32_t*)(B + L.pend_task);
     out->d_kpend_ws = (float*)(B + L.kpend_ws);
+    out->d_wide_vacc = (float*)(B + L.vacc);
     out->dist_scale_p = dist_scale_p;
     out->dist_scale_wp = dist_scale_wp;
     out->wide_ws_rows = L.wide_ws_rows;

@@ -74,7 +74,8 @@ typedef enum bb_acq_kind {
 } bb_acq_kind;
 
 #define BB_MAX_PENDING 31 /* max pending points in a joint (q>1) evaluation */
-#define BB_MAX_TRAIN 512  /* max training points of this build (reference: exact Cholesky <= 800) */
+#define BB_MAX_TRAIN 1024 /* max training points of this build (gpytorch switches away from exact Cholesky
+                             above 800); n > 512 always takes the wide-feature path (two V column panels) */
 
 /*
  * Description of a fitted GP, i.e. what botorch.models.SingleTaskGP holds after
@@ -157,6 +158,7 @@ typedef struct bb_model {
   float* d_kpend_ws;         /* [wide_ws_rows * 64] k(x*, pending) block                                */
   float dist_scale_p;        /* power-of-two scales of the pending images (float form / bit-linear form) */
   float dist_scale_wp;
+  float* d_wide_vacc;        /* [wide_ws_rows] |V|^2 partial between the two column-panel passes (n_pad > 512) */
 } bb_model;
 
 /* Acquisition context built by BotorchAcquisitionFunctionBuilder.build

@@ -243,7 +243,7 @@ def test_errors_are_loud(cuda_device):
         gp.posterior(torch.zeros(10, 4))  # wrong column count
     with pytest.raises(ValueError):
         gp.score(AcqConfig(kind="qLogEI"), torch.from_numpy(w.candidates), None)  # no base samples
-    big = numeric_grid_workload(N=600, d=4, n=600)
+    big = numeric_grid_workload(N=1100, d=4, n=1100)
     with pytest.raises(NotImplementedError):
         DeviceGP(device=cuda_device, **big.gp_kwargs())  # n > BB_MAX_TRAIN
     with pytest.raises(ValueError):

@@ -39,6 +39,10 @@ WIDE = {
                                                           outputscale=1.7, lengthscale=6.0),
     "d40_n512_m32": lambda: numeric_grid_workload(N=2500, d=40, n=512, family="matern32", seed=13,
                                                   lengthscale=2.0),
+    # n > 512: always wide, two V column panels (TMEM holds 512 columns)
+    "d12_n700_m52": lambda: numeric_grid_workload(N=2000, d=12, n=700, seed=14, lengthscale=1.2),
+    "d40_n1024_rbf": lambda: numeric_grid_workload(N=1800, d=40, n=1024, family="rbf", seed=15, lengthscale=2.5,
+                                                   outputscale=0.8),
     "fp2048_n512": lambda: fingerprint_workload(N=2300, d=2048, n=512, seed=1),
     "fp1000_n300": lambda: fingerprint_workload(N=1500, d=1000, n=300, seed=2, density=0.1, family="matern52",
                                                 ls_factor=0.25, outputscale=None),
@@ -80,7 +84,7 @@ def test_wide_posterior(name, cuda_device):
 
 
 @pytest.mark.parametrize("kind", ["qLogEI", "qEI", "UCB", "LogEI"])
-@pytest.mark.parametrize("name", ["d100_n200_m52", "fp2048_n512"])
+@pytest.mark.parametrize("name", ["d100_n200_m52", "fp2048_n512", "d12_n700_m52"])
 def test_wide_scores_and_argmax(kind, name, cuda_device):
     w = WIDE[name]()
     om = oracle_model(w)
@@ -103,7 +107,7 @@ def test_wide_scores_and_argmax(kind, name, cuda_device):
 
 
 @pytest.mark.parametrize("P", [1, 5])
-@pytest.mark.parametrize("name", ["d100_n200_m52", "fp2048_n512", "fp1000_n300"])
+@pytest.mark.parametrize("name", ["d100_n200_m52", "fp2048_n512", "fp1000_n300", "d40_n1024_rbf"])
 def test_wide_joint_scores_with_pending_points(name, P, cuda_device):
     """Sequential-greedy round on the wide path: pending rows become 64 extra K columns of k_kmat_tc and the
     cross-covariances are contracted from the K* block in the workspace."""
