@@ -25,8 +25,8 @@ from attrs import define, field
 from baybe_b200.engine import DeviceGP
 from baybe_b200.searchspace import objective_affine
 
-__all__ = ["GaussianProcessSurrogate", "ModelNotTrainedError", "fit_map_hyperparameters",
-           "fit_map_hyperparameters_device", "DeviceMLL"]
+__all__ = ["GaussianProcessSurrogate", "ModelNotTrainedError", "fit_map", "fit_map_hyperparameters",
+           "fit_map_hyperparameters_device", "DeviceMLL", "HostMLL"]
 
 MIN_INFERRED_NOISE_LEVEL = 1e-4
 MIN_LENGTHSCALE = 2.5e-2
@@ -36,72 +36,51 @@ class ModelNotTrainedError(Exception):
     """Same name/meaning as baybe.exceptions.ModelNotTrainedError (surrogates/base.py:240-243)."""
 
 
-def _matern52(Xa: torch.Tensor, Xb: torch.Tensor, ls: torch.Tensor) -> torch.Tensor:
-    a, b = Xa / ls, Xb / ls
-    d2 = (a * a).sum(-1, keepdim=True) + (b * b).sum(-1, keepdim=True).T - 2.0 * a @ b.T
+def _torch_kernel(family: str, d2: torch.Tensor) -> torch.Tensor:
+    if family == "rbf":
+        return torch.exp(-0.5 * d2)
     r = d2.clamp_min(1e-30).sqrt()
+    if family == "matern12":
+        return torch.exp(-r)
+    if family == "matern32":
+        s = math.sqrt(3.0) * r
+        return (1.0 + s) * torch.exp(-s)
     s = math.sqrt(5.0) * r
     return (1.0 + s + (5.0 / 3.0) * d2.clamp_min(0.0)) * torch.exp(-s)
 
 
-def fit_map_hyperparameters(Xn: np.ndarray, y_std: np.ndarray, active: Sequence[int], task_ids=None,
-                            n_tasks: int = 1, max_iter: int = 200) -> dict:
-    """MAP fit of (lengthscales, noise, constant mean[, task covariance]) on normalised inputs and
-    standardised targets: maximises (log marginal likelihood + log priors) / n like
-    ``botorch.fit.fit_gpytorch_mll`` on an ``ExactMarginalLogLikelihood`` (core.py:340-341),
-    starting from the prior modes (``initial_value=prior.mode``, presets/baybe.py:100-107,134-144).
-    """
-    from scipy.optimize import minimize
+class HostMLL:
+    """Float64 torch-autograd twin of ``DeviceMLL`` (same call signature); the independent cross-check of
+    the device objective and the ``fit_backend="host"`` path."""
 
-    X = torch.as_tensor(Xn[:, list(active)], dtype=torch.float64)
-    y = torch.as_tensor(y_std, dtype=torch.float64)
-    n, da = X.shape
-    conc_l, rate_l = 3.0, 2.0 / math.exp(math.sqrt(2.0) - 3.0) / math.sqrt(da)
-    conc_n, rate_n = 2.0, 1.0 / math.exp(-5.0)
-    ls0 = (conc_l - 1.0) / rate_l
-    nz0 = (conc_n - 1.0) / rate_n
-    T = n_tasks
-    tid = None if task_ids is None else torch.as_tensor(task_ids, dtype=torch.long)
-    n_task_par = 0 if tid is None else T * T + T
-    x0 = np.concatenate([np.full(da, ls0), [max(nz0, MIN_INFERRED_NOISE_LEVEL)], [0.0],
-                         np.concatenate([np.eye(T).reshape(-1) * 0.8 + 0.2, np.full(T, 0.1)]) if n_task_par else []])
-    bounds = [(MIN_LENGTHSCALE, None)] * da + [(MIN_INFERRED_NOISE_LEVEL, None), (None, None)] + \
-             [(1e-6, None)] * n_task_par
+    def __init__(self, Xa: np.ndarray, y_std: np.ndarray, task_ids=None, n_tasks: int = 1,
+                 family: str = "matern52", device=None):
+        self.X = torch.as_tensor(np.ascontiguousarray(Xa), dtype=torch.float64)
+        self.y = torch.as_tensor(np.ascontiguousarray(y_std), dtype=torch.float64)
+        self.n, self.d = self.X.shape
+        self.T = int(n_tasks)
+        self.family = family
+        self.tid = (torch.zeros(self.n, dtype=torch.long) if task_ids is None
+                    else torch.as_tensor(np.asarray(task_ids), dtype=torch.long))
+        self.np = self.d + 2 + self.T * self.T
 
-    def unpack(t):
-        ls, nz, c = t[:da], t[da], t[da + 1]
-        B = None
-        if n_task_par:
-            W = t[da + 2: da + 2 + T * T].reshape(T, T)
-            v = t[da + 2 + T * T:]
-            B = W @ W.T + torch.diag(v)
-        return ls, nz, c, B
-
-    def objective(theta_np):
-        t = torch.tensor(theta_np, dtype=torch.float64, requires_grad=True)
-        ls, nz, c, B = unpack(t)
-        K = _matern52(X, X, ls)
-        if B is not None:
-            K = K * B[tid][:, tid]
-        K = K + nz * torch.eye(n, dtype=torch.float64)
+    def __call__(self, theta: np.ndarray) -> tuple[float, np.ndarray, bool]:
+        t = torch.tensor(np.asarray(theta, dtype=np.float64), requires_grad=True)
+        d, n, T = self.d, self.n, self.T
+        ls, nz, c, B = t[:d], t[d], t[d + 1], t[d + 2:].reshape(T, T)
+        diff = (self.X[:, None, :] - self.X[None, :, :]) / ls  # direct differences, like the device kernels
+        d2 = (diff * diff).sum(-1)
+        eye = torch.eye(n, dtype=torch.float64)
+        K = _torch_kernel(self.family, d2) * (1.0 - eye) + eye  # exact unit diagonal (x1 is x2)
+        K = K * B[self.tid][:, self.tid] + nz * eye
         L, info = torch.linalg.cholesky_ex(K)
         if int(info) != 0:
-            return 1e10, np.zeros_like(theta_np)
-        r = (y - c).unsqueeze(-1)
-        a = torch.cholesky_solve(r, L)
-        mll = -0.5 * (r * a).sum() - torch.log(torch.diagonal(L)).sum() - 0.5 * n * math.log(2 * math.pi)
-        lp = ((conc_l - 1.0) * torch.log(ls) - rate_l * ls).sum() + (conc_n - 1.0) * torch.log(nz) - rate_n * nz
-        loss = -(mll + lp) / n
-        loss.backward()
-        return float(loss.detach()), t.grad.numpy().copy()
-
-    res = minimize(objective, x0, jac=True, method="L-BFGS-B", bounds=bounds,
-                   options={"maxiter": max_iter, "ftol": 1e-10, "gtol": 1e-7})
-    t = torch.tensor(res.x, dtype=torch.float64)
-    ls, nz, c, B = unpack(t)
-    return {"lengthscale": ls.numpy(), "noise": float(nz), "mean_const": float(c),
-            "task_covar": None if B is None else B.numpy(), "objective": float(res.fun),
-            "n_iter": int(res.nit)}
+            return float("nan"), np.zeros(self.np), False
+        r = (self.y - c).unsqueeze(-1)
+        alpha = torch.cholesky_solve(r, L)
+        mll = -0.5 * (r * alpha).sum() - torch.log(torch.diagonal(L)).sum() - 0.5 * n * math.log(2 * math.pi)
+        mll.backward()
+        return float(mll.detach()), t.grad.numpy().copy(), True
 
 
 class DeviceMLL:
@@ -151,58 +130,92 @@ class DeviceMLL:
         return float(val.value), grad, bad.value == 0
 
 
-def fit_map_hyperparameters_device(Xn: np.ndarray, y_std: np.ndarray, active: Sequence[int], task_ids=None,
-                                   n_tasks: int = 1, max_iter: int = 200, device=None) -> dict:
-    """Same MAP objective, start point, bounds and optimiser as ``fit_map_hyperparameters``; the marginal
-    likelihood and its gradient are evaluated on the GPU (Cholesky, K^-1 and the n^2 d gradient contraction
-    in float64 kernels), the Gamma priors and scipy's L-BFGS-B step on the host."""
+def fit_map(Xn: np.ndarray, y_std: np.ndarray, active: Sequence[int], task_ids=None, n_tasks: int = 1,
+            max_iter: int = 200, config=None, backend: str = "device", device=None) -> dict:
+    """MAP fit of (lengthscales, noise, constant mean[, output scale][, task covariance]) on normalised inputs
+    and standardised targets: maximises (log marginal likelihood + log priors) / n like
+    ``botorch.fit.fit_gpytorch_mll`` on an ``ExactMarginalLogLikelihood`` (core.py:340-341), starting from the
+    preset's initial values (prior modes for the BayBE preset, presets/baybe.py:100-107,134-144).
+
+    The marginal likelihood and its gradient come from ``DeviceMLL`` (GPU, default) or ``HostMLL`` (torch
+    autograd); priors, bounds and scipy's L-BFGS-B step are shared host code."""
     from scipy.optimize import minimize
+
+    from baybe_b200.kernels import gp_preset
 
     Xa = np.ascontiguousarray(np.asarray(Xn, dtype=np.float64)[:, list(active)])
     n, da = Xa.shape
-    T = n_tasks if task_ids is not None else 1
-    mll = DeviceMLL(Xa, y_std, task_ids, T, "matern52", device)
-    conc_l, rate_l = 3.0, 2.0 / math.exp(math.sqrt(2.0) - 3.0) / math.sqrt(da)
-    conc_n, rate_n = 2.0, 1.0 / math.exp(-5.0)
-    ls0 = (conc_l - 1.0) / rate_l
-    nz0 = (conc_n - 1.0) / rate_n
-    n_task_par = 0 if task_ids is None else T * T + T
-    x0 = np.concatenate([np.full(da, ls0), [max(nz0, MIN_INFERRED_NOISE_LEVEL)], [0.0],
-                         np.concatenate([np.eye(T).reshape(-1) * 0.8 + 0.2, np.full(T, 0.1)]) if n_task_par else []])
-    bounds = [(MIN_LENGTHSCALE, None)] * da + [(MIN_INFERRED_NOISE_LEVEL, None), (None, None)] + \
-             [(1e-6, None)] * n_task_par
+    cfg = gp_preset("BAYBE", da) if config is None else config
+    has_tasks = task_ids is not None
+    T = n_tasks if has_tasks else 1
+    mll = (DeviceMLL if backend == "device" else HostMLL)(Xa, y_std, task_ids, T, cfg.family, device)
+    fit_os = cfg.outputscale and cfg.outputscale_trainable
+    i_os = da + 2 if fit_os else None
+    i_w = da + 2 + (1 if fit_os else 0)
+    n_task_par = T * T + T if has_tasks else 0
+    x0 = np.concatenate([
+        np.full(da, max(cfg.lengthscale_initial_value, cfg.lengthscale_lower)),
+        [max(cfg.noise_initial_value, cfg.noise_lower)], [0.0],
+        [cfg.outputscale_initial_value] if fit_os else [],
+        np.concatenate([np.eye(T).reshape(-1) * 0.8 + 0.2, np.full(T, 0.1)]) if n_task_par else []])
+    bounds = [(cfg.lengthscale_lower, None)] * da + [(cfg.noise_lower, None), (None, None)] + \
+             ([(1e-6, None)] if fit_os else []) + [(1e-6, None)] * n_task_par
+    os_fixed = cfg.outputscale_initial_value if (cfg.outputscale and not fit_os) else 1.0
 
-    def task_cov(x):
+    def parts(x):
+        osv = x[i_os] if fit_os else os_fixed
         if not n_task_par:
-            return np.ones((1, 1)), None, None
-        W = x[da + 2: da + 2 + T * T].reshape(T, T)
-        v = x[da + 2 + T * T:]
-        return W @ W.T + np.diag(v), W, v
+            return osv, np.ones((1, 1)), None
+        W = x[i_w: i_w + T * T].reshape(T, T)
+        v = x[i_w + T * T:]
+        return osv, W @ W.T + np.diag(v), W
 
     def objective(x):
-        B, W, _ = task_cov(x)
-        theta = np.concatenate([x[: da + 2], B.reshape(-1)])
+        osv, Bi, W = parts(x)
+        theta = np.concatenate([x[: da + 2], (osv * Bi).reshape(-1)])
         val, g, ok = mll(theta)
         if not ok or not np.isfinite(val):
             return 1e10, np.zeros_like(x)
         ls, nz = x[:da], x[da]
-        lp = ((conc_l - 1.0) * np.log(ls) - rate_l * ls).sum() + (conc_n - 1.0) * math.log(nz) - rate_n * nz
         grad = np.zeros_like(x)
-        grad[:da] = g[:da] + (conc_l - 1.0) / ls - rate_l
-        grad[da] = g[da] + (conc_n - 1.0) / nz - rate_n
-        grad[da + 1] = g[da + 1]
+        grad[: da + 2] = g[: da + 2]
+        lp = 0.0
+        if cfg.lengthscale_prior is not None:
+            lp += float(np.sum(cfg.lengthscale_prior.log_prob(ls)))
+            grad[:da] += cfg.lengthscale_prior.grad(ls)
+        if cfg.noise_prior is not None:
+            lp += float(cfg.noise_prior.log_prob(nz))
+            grad[da] += float(cfg.noise_prior.grad(nz))
+        gB = g[da + 2:].reshape(T, T)
+        if fit_os:
+            grad[i_os] = float(np.sum(gB * Bi))
+            if cfg.outputscale_prior is not None:
+                lp += float(cfg.outputscale_prior.log_prob(osv))
+                grad[i_os] += float(cfg.outputscale_prior.grad(osv))
         if n_task_par:
-            gB = g[da + 2:].reshape(T, T)
-            grad[da + 2: da + 2 + T * T] = ((gB + gB.T) @ W).reshape(-1)
-            grad[da + 2 + T * T:] = np.diag(gB)
+            grad[i_w: i_w + T * T] = (osv * (gB + gB.T) @ W).reshape(-1)
+            grad[i_w + T * T:] = osv * np.diag(gB)
         return -(val + lp) / n, -grad / n
 
     res = minimize(objective, x0, jac=True, method="L-BFGS-B", bounds=bounds,
                    options={"maxiter": max_iter, "ftol": 1e-10, "gtol": 1e-7})
-    B, _, _ = task_cov(res.x)
+    osv, Bi, _ = parts(res.x)
     return {"lengthscale": res.x[:da].copy(), "noise": float(res.x[da]), "mean_const": float(res.x[da + 1]),
-            "task_covar": B if n_task_par else None, "objective": float(res.fun), "n_iter": int(res.nit),
-            "n_eval": int(res.nfev), "backend": "device"}
+            "outputscale": float(osv) if cfg.outputscale else None,
+            "task_covar": Bi if n_task_par else None, "family": cfg.family, "objective": float(res.fun),
+            "n_iter": int(res.nit), "n_eval": int(res.nfev), "backend": backend}
+
+
+def fit_map_hyperparameters(Xn, y_std, active, task_ids=None, n_tasks: int = 1, max_iter: int = 200,
+                            config=None) -> dict:
+    """``fit_map`` with the objective evaluated by float64 torch autograd on the host."""
+    return fit_map(Xn, y_std, active, task_ids, n_tasks, max_iter, config, backend="host")
+
+
+def fit_map_hyperparameters_device(Xn, y_std, active, task_ids=None, n_tasks: int = 1, max_iter: int = 200,
+                                   device=None, config=None) -> dict:
+    """``fit_map`` with the objective evaluated on the GPU (``bb_fit_eval``)."""
+    return fit_map(Xn, y_std, active, task_ids, n_tasks, max_iter, config, backend="device", device=device)
 
 
 class _Posterior:
@@ -232,6 +245,10 @@ class GaussianProcessSurrogate:
 
     device: str | None = field(default=None)
     max_fit_iter: int = field(default=200)
+    kernel_or_factory: object = field(default=None)
+    """None (BayBE preset), a preset name ("BAYBE", "CHEN", "EDBO") or a ``baybe_b200.kernels`` kernel object
+    (``GaussianProcessSurrogate(kernel_or_factory=...)``, surrogates/gaussian_process/core.py:147-186)."""
+
     fit_backend: str = field(default="device")
     """"device": marginal likelihood + gradient on the GPU (bb_fit_eval); "host": float64 torch autograd
     (kept as the independent cross-check of the device objective)."""
@@ -271,9 +288,19 @@ class GaussianProcessSurrogate:
             ys = train_y.std(ddof=1) if len(train_y) > 1 else 1.0
             ys = ys if ys >= 1e-8 else 1.0
             tids = None if task_col is None else np.rint(train_x[:, task_col]).astype(int)
-            fit = fit_map_hyperparameters if self.fit_backend == "host" else fit_map_hyperparameters_device
-            kw = {} if self.fit_backend == "host" else {"device": self.device}
-            hp = fit(Xn, (train_y - train_y.mean()) / ys, active, tids, n_tasks, self.max_fit_iter, **kw)
+            from baybe_b200.kernels import Kernel, gp_preset, resolve_kernel
+
+            kf = self.kernel_or_factory
+            if kf is None:
+                config = gp_preset("BAYBE", len(active))
+            elif isinstance(kf, str):
+                config = gp_preset(kf, len(active))
+            elif isinstance(kf, Kernel):
+                config = resolve_kernel(kf)
+            else:
+                raise TypeError("kernel_or_factory must be None, a preset name or a baybe_b200.kernels.Kernel")
+            hp = fit_map(Xn, (train_y - train_y.mean()) / ys, active, tids, n_tasks, self.max_fit_iter, config,
+                         backend=self.fit_backend, device=self.device)
         ls_full = np.full(d, -1.0)
         ls_full[active] = np.broadcast_to(np.asarray(hp["lengthscale"], dtype=np.float64), (len(active),))
         task_covar = hp.get("task_covar")

@@ -141,3 +141,79 @@ def test_fingerprint_workload_shape():
     assert w.candidates.shape == (300, 256) and set(np.unique(w.candidates)) <= {0.0, 1.0}
     assert w.family == "rbf" and w.outputscale == 1.0 and w.train_x.shape == (64, 256)
     assert np.allclose(w.lengthscale, np.sqrt(256) * 0.4)
+
+
+def test_priors_match_scipy_and_their_gradients():
+    """Priors of baybe/priors/basic.py: log densities (up to a constant) against scipy.stats, gradients
+    against central differences."""
+    from scipy import stats
+
+    from baybe_b200.priors import (GammaPrior, HalfCauchyPrior, HalfNormalPrior, LogNormalPrior, NormalPrior,
+                                   SmoothedBoxPrior)
+
+    x = np.array([0.07, 0.6, 1.3, 4.0])
+    cases = [
+        (GammaPrior(3.0, 2.0), stats.gamma(a=3.0, scale=0.5)),
+        (LogNormalPrior(0.3, 0.7), stats.lognorm(s=0.7, scale=np.exp(0.3))),
+        (NormalPrior(0.5, 1.2), stats.norm(0.5, 1.2)),
+        (HalfNormalPrior(0.8), stats.halfnorm(scale=0.8)),
+        (HalfCauchyPrior(1.5), stats.halfcauchy(scale=1.5)),
+    ]
+    for prior, ref in cases:
+        diff = prior.log_prob(x) - ref.logpdf(x)
+        assert np.allclose(diff, diff[0], atol=1e-12), type(prior).__name__  # equal up to the constant
+        fd = (prior.log_prob(x + 1e-6) - prior.log_prob(x - 1e-6)) / 2e-6
+        assert np.allclose(prior.grad(x), fd, rtol=1e-6, atol=1e-8), type(prior).__name__
+    assert GammaPrior(3.0, 2.0).mode == 1.0 and np.isclose(LogNormalPrior(0.3, 0.7).mode, np.exp(0.3 - 0.49))
+    box = SmoothedBoxPrior(0.5, 2.0, 0.1)
+    assert box.log_prob(np.array([1.0]))[0] == 0.0 and box.log_prob(np.array([2.3]))[0] == pytest.approx(-4.5)
+    with pytest.raises(ValueError):
+        SmoothedBoxPrior(2.0, 1.0)
+
+
+def test_kernel_specs_and_presets():
+    """kernels/basic.py + composite.py mirrors and the presets built from them."""
+    import math
+
+    from baybe_b200.kernels import MaternKernel, RBFKernel, ScaleKernel, gp_preset, resolve_kernel
+    from baybe_b200.priors import GammaPrior
+
+    assert MaternKernel("3/2").family == "matern32" and MaternKernel().family == "matern52"
+    with pytest.raises(ValueError):
+        MaternKernel(2.0)
+    with pytest.raises(NotImplementedError):
+        ScaleKernel(ScaleKernel(RBFKernel()))
+    cfg = resolve_kernel(ScaleKernel(RBFKernel(GammaPrior(3.0, 6.0)), GammaPrior(2.0, 0.15), 5.0))
+    assert (cfg.family, cfg.outputscale, cfg.lengthscale_initial_value, cfg.outputscale_initial_value) == \
+           ("rbf", True, pytest.approx(1.0 / 3.0), 5.0)
+    b = gp_preset("BAYBE", 20)  # presets/baybe.py:95-99,134-144
+    assert b.family == "matern52" and not b.outputscale and b.lengthscale_lower == 2.5e-2
+    assert b.lengthscale_initial_value == pytest.approx(math.exp(math.sqrt(2.0) - 3.0) * math.sqrt(20))
+    assert b.noise_initial_value == pytest.approx(math.exp(-5.0))
+    c = gp_preset("chen", 9)  # presets/chen.py:35-61
+    assert c.outputscale and c.lengthscale_initial_value == pytest.approx(0.4 * 3 + 4.0) and c.noise_prior is None
+    assert gp_preset("EDBO", 3).lengthscale_initial_value == 0.2 and gp_preset("EDBO", 30).outputscale_initial_value == 20.0
+    with pytest.raises(ValueError):
+        gp_preset("nope", 3)
+
+
+def test_host_fit_with_presets_improves_on_the_start_point():
+    from baybe_b200.kernels import gp_preset
+    from baybe_b200.surrogates import HostMLL, fit_map_hyperparameters
+    from baybe_b200.synthetic import numeric_grid_workload
+
+    w = numeric_grid_workload(N=200, d=3, n=30, seed=2)
+    y = (w.train_y - w.train_y.mean()) / w.train_y.std(ddof=1)
+    for name in ("BAYBE", "CHEN", "EDBO"):
+        cfg = gp_preset(name, 3)
+        hp = fit_map_hyperparameters(w.train_x, y, [0, 1, 2], None, 1, 60, config=cfg)
+        assert hp["family"] == "matern52" and (hp["outputscale"] is not None) == cfg.outputscale
+        assert hp["noise"] >= 1e-4 and (hp["lengthscale"] >= cfg.lengthscale_lower).all()
+        # the optimum is at least as good as the start point
+        mll = HostMLL(w.train_x, y, None, 1, cfg.family)
+        os0 = cfg.outputscale_initial_value if cfg.outputscale else 1.0
+        v0, _, ok = mll(np.concatenate([np.full(3, cfg.lengthscale_initial_value), [cfg.noise_initial_value, 0.0, os0]]))
+        lp0 = sum(p.log_prob(np.asarray(x)).sum() for p, x in [
+            (cfg.lengthscale_prior, np.full(3, cfg.lengthscale_initial_value)), (cfg.noise_prior, cfg.noise_initial_value),
+            (cfg.outputscale_prior if cfg.outputscale else None, os0)] if p is not None)
+        assert ok and hp["objective"] <= -(v0 + lp0) / 30 + 1e-9
