@@ -511,7 +511,7 @@ static int launch_family(FusedParams& p, int lag, int grid, size_t smem, cudaStr
 
 // Wide-feature models: per block of <= wide_ws_rows candidates, k_kmat_tc writes the K* block into the
 // (L2-sized) workspace inside the model blob and k_fused<PRE> consumes it; both on the caller's stream.
-static int launch_wide_blocks(const bb_model* m, const FusedParams& full, int lag, int sms, int max_smem,
+static int launch_wide_blocks(const bb_model* m, const FusedParams& full, int sms, int max_smem,
                               const WideCross* wc, cudaStream_t stream) {
   BB_CHECK_SUPPORTED(m->d_wide_ws != nullptr && m->wide_ws_rows >= 256, "wide model without workspace");
   if (wc != nullptr) {
@@ -682,7 +682,7 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   BB_CUDA(cudaGetDevice(&dev));
   BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  if (m->wide) return launch_wide_blocks(m, p, lag, sms, max_smem, wc, stream);
+  if (m->wide) return launch_wide_blocks(m, p, sms, max_smem, wc, stream);
   if (fused_tc_supported(p, max_smem)) {
     const int grid_tc = p.num_tiles < sms ? p.num_tiles : sms;
     return launch_fused_tc(p, grid_tc, stream);

@@ -81,7 +81,6 @@ static BlobLayout make_layout(int n, int d, int T) {
   L.flags = take(64);
   L.rimg2g = L.n_chunks > 4 ? take((size_t)L.n_tiles * 16384) : 0;
   L.wide = ((size_t)L.n_pad * L.d_pad * 4 > kResidentTrainBytes || L.n_pad > 512) ? 1 : 0;
-  if (const char* f = getenv("BAYBE_B200_FORCE_WIDE")) L.wide = (f[0] == '1') ? 1 : L.wide;  // experiments
   L.d_wide = round_up(d, 32);
   L.wimg = L.wimg_bits = L.wnorm_bits = L.wsrc = L.wide_ws = L.rimg4 = 0;
   L.pend_img = L.pend_norm2 = L.pend_task = L.kpend_ws = L.vacc = 0;

@@ -15,6 +15,8 @@
  *   - every call takes the caller's CUDA stream (a cudaStream_t passed as void*), enqueues
  *     its kernels there and returns without synchronising, EXCEPT bb_model_build which
  *     synchronises the stream once (Cholesky success flag / jitter escalation).
+ *   - a wide-feature model (bb_model.wide) owns scratch inside its blob (K* block, pending-point images):
+ *     calls that use the same bb_model must be ordered on one stream (or serialised by the caller).
  *   - return value: BB_OK (0) or a negative bb_status; bb_last_error() gives the message.
  *     No partial results: on error the output buffers are unspecified.
  */
