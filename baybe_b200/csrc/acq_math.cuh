@@ -114,6 +114,146 @@ __device__ __forceinline__ void mc_accumulate(int kind, float c0, float c1, cons
   else if (kind == BB_ACQ_QPI) mc_partial_kind<BB_ACQ_QPI>(c0, c1, z4, n4, s0, s1);
 }
 
+// ------------------------------------------------------------------------------------------
+// qLogEI, tabulated fat-tail sum (q = 1, shared base samples).
+// With x_s = (o_s - best_f)/tau = c0 + c1 z_s, tau = 1e-6 and zeta = sign(c1) z sorted descending, a candidate
+// with at most 8 improving samples (x_(9) <= 0: nearly every row of a discrete space) splits its sum
+//   sum_s fatplus(x_s)/tau = [16 largest zeta: exact terms]  +  c1^-2 H(w),   w = -c0/|c1| >= zeta_(9),
+//   H(w) = sum_{s > 16} (zeta_(s) - w)^-2      (those samples sit at x <= -1024: softplus = 0, 1/(1+x^2) = x^-2).
+// H is ONE function of one variable for every candidate: it is tabulated once per CTA as
+// F(v) = H(w) (w - zeta_(9) + 1)^2 over v = 1/(w - zeta_(9) + 1) in [0,1] (linear interpolation, 512 intervals,
+// relative error < 1e-5; the nearest pole zeta_(17) stays >= 0.25 away).  Rows outside the envelope take the
+// exact sum over all S samples (mc_row_exact_warp).
+// Table region (1024 floats): [0..512] F | [520..535] top-16 zeta (descending) | [536] table valid |
+//                             [544..799] scratch for the callers (exact (s0, s1) per row).
+// ------------------------------------------------------------------------------------------
+constexpr int kMcNT = 512, kMcTop = 520, kMcOk = 536, kMcRows = 544, kMcK = 16, kMcJ = 8;
+
+__device__ __forceinline__ bool mc_table_applicable(int has_acq, const bb_acq_spec& a, int S) {
+  return has_acq && a.kind == BB_ACQ_QLOGEI && S >= 64 && (S & 63) == 0 && S <= 512;
+}
+
+// Called by EVERY thread of the CTA (contains __syncthreads); z_s: the S base samples in shared memory.
+__device__ __forceinline__ void mc_table_setup(float* __restrict__ tab, const float* __restrict__ z_s, int S,
+                                               float sgn) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {  // sixteen largest zeta: S/32 values per lane, sixteen rounds of warp arg-max
+    float vals[16];
+    const int per_lane = S >> 5;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) vals[j] = j < per_lane ? sgn * z_s[j * 32 + lane] : -INFINITY;
+    for (int k = 0; k < kMcK; ++k) {
+      float m = -INFINITY;
+      int mj = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (vals[j] > m) {
+          m = vals[j];
+          mj = j;
+        }
+      float wm = m;
+      for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+      const unsigned who = __ballot_sync(0xffffffffu, m == wm);
+      if (lane == (int)(__ffs(who) - 1)) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j == mj) vals[j] = -INFINITY;
+      }
+      if (lane == 0) tab[kMcTop + k] = wm;
+    }
+  }
+  __syncthreads();
+  const float thr = tab[kMcTop + kMcK - 1], w0 = tab[kMcTop + kMcJ];
+  if (warp == 1) {  // ties at the threshold would make "top 16" ambiguous: then every row takes the exact path
+    int cnt = 0;
+    for (int e = lane; e < S; e += 32) cnt += (sgn * z_s[e] >= thr) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) tab[kMcOk] = (cnt == kMcK) ? 1.f : 0.f;
+  }
+  for (int j = tid; j <= kMcNT; j += blockDim.x) {
+    float f = (float)(S - kMcK);
+    if (j > 0) {
+      const float a = (float)kMcNT / (float)j;  // a = w - zeta_(9) + 1 = 1/v
+      const float w = w0 - 1.0f + a;
+      const float cut = thr - w;  // zeta < thr  <=>  zeta - w < cut
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+      for (int e = 0; e < S; e += 2) {
+        const float d0 = fmaf(sgn, z_s[e], -w), d1 = fmaf(sgn, z_s[e + 1], -w);
+        const float r0 = fast_rcp(d0 * d0), r1 = fast_rcp(d1 * d1);
+        acc0 += d0 < cut ? r0 : 0.f;
+        acc1 += d1 < cut ? r1 : 0.f;
+      }
+      f = (acc0 + acc1) * a * a;
+    }
+    tab[j] = f;
+  }
+  __syncthreads();
+}
+
+// (s0, s1) of one row from the table; false (and s0 = s1 = 0) if the row lies outside the envelope.
+__device__ __forceinline__ bool mc_row_fast(const float* __restrict__ tab, float c0, float c1, float& s0,
+                                            float& s1) {
+  const float ac1 = fabsf(c1);
+  const float t9 = fmaf(ac1, tab[kMcTop + kMcJ], c0);        // 9th largest x_s of this row
+  const float t17 = fmaf(ac1, tab[kMcTop + kMcK - 1], c0);   // bounds every tabulated sample from above
+  const bool fast = tab[kMcOk] != 0.f && ac1 > 1e-30f && t9 <= 0.f && t17 <= -1024.f;
+  s0 = 0.f;
+  s1 = 0.f;
+  if (fast) {
+    float tmin = 1e30f;
+#pragma unroll
+    for (int k = 0; k < kMcK; ++k) {
+      const float t = fmaf(ac1, tab[kMcTop + k], c0);
+      s0 += fmaxf(t, 0.f);
+      s1 += fast_rcp(fmaf(t, t, 1.0f));
+      tmin = fminf(tmin, fabsf(t));
+    }
+    if (tmin < 30.f) {  // a sample within 30 tau of the incumbent: softplus differs from relu there (rare)
+      for (int k = 0; k < kMcK; ++k) {
+        const float t = fabsf(fmaf(ac1, tab[kMcTop + k], c0));
+        if (t < 30.f) s0 += softplus_tail(t);
+      }
+    }
+    const float inv = 1.0f / ac1;
+    const float a = fmaf(-t9, inv, 1.0f);  // w - zeta_(9) + 1 >= 1, no cancellation
+    const float v = 1.0f / a;
+    const float x = v * (float)kMcNT;
+    const int i = min((int)x, kMcNT - 1);
+    const float fr = x - (float)i;
+    const float f0 = tab[i], f1 = tab[i + 1];
+    const float q = v * inv;
+    s1 = fmaf(fmaf(fr, f1 - f0, f0), q * q, s1);
+  }
+  return fast;
+}
+
+// Exact (s0, s1) of one row by a whole warp: lane l takes samples l, l+32, ...; fixed reduction order, so a row's
+// value does not depend on where it is evaluated.  Result in every lane.
+__device__ __forceinline__ void mc_row_exact_warp(const float* __restrict__ z_s, int S, float c0, float c1, int lane,
+                                                  float& a0, float& a1) {
+  float b0 = 0.f, b1 = 0.f;
+  a0 = 0.f;
+  a1 = 0.f;
+  for (int e = lane; e < S; e += 64) {  // S is a multiple of 64 on this path; two independent chains
+    const float t = fmaf(c1, z_s[e], c0), u = fmaf(c1, z_s[e + 32], c0);
+    a0 += fmaxf(t, 0.f);
+    b0 += fmaxf(u, 0.f);
+    a1 += fast_rcp(fmaf(t, t, 1.0f));
+    b1 += fast_rcp(fmaf(u, u, 1.0f));
+    if (fminf(fabsf(t), fabsf(u)) < 30.f) {
+      if (fabsf(t) < 30.f) a0 += softplus_tail(fabsf(t));
+      if (fabsf(u) < 30.f) b0 += softplus_tail(fabsf(u));
+    }
+  }
+  a0 += b0;
+  a1 += b1;
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+}
+
 __device__ __forceinline__ float mc_finalize(const bb_acq_spec& a, float mu, float var, float s0,
                                              float s1, int S, float z_mean, float zabs_mean) {
   const float sd = sqrtf(var);

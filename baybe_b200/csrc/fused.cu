@@ -1,4 +1,5 @@
-// fused.cu -- the hot path: per tile of 128 candidates
+// fused.cu -- the general-shape scoring kernel (fused_tc.cu is the headline kernel for n_pad <= 256, d_pad <= 64)
+// and the launcher that picks between the three paths: per tile of 128 candidates
 //   K* = k(X*, X)                       CUDA cores (fp32, GEMM-form distance + Matern/RBF epilogue)
 //   mu~ = c + K* alpha                  CUDA cores (fp32, folded into the K* pass)
 //   V = K* L^-T                         tcgen05 tensor cores, fp16 hi/lo split x3, fp32 accum in TMEM,
@@ -168,6 +169,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
     }
   }
 
+  // qLogEI: tabulated fat-tail sum (acq_math.cuh), as in fused_tc.cu.  Not in the K*-reading variant: the wide path
+  // launches it once per 37,888-row block, and rebuilding the table in every CTA of every short launch costs
+  // more than the per-sample loop it replaces (measured: config-4 shard 5.3 -> 5.7 ms).
+  const bool fast_mc = !PRE && mc_table_applicable(p.has_acq, p.acq, p.S);
+  if (fast_mc) mc_table_setup(s.mc_part, s.z_s, p.S, p.acq.obj_scale < 0.f ? -1.f : 1.f);
+
   if (warp < kComputeWarps) {
     // =====================================================================================
     // compute warps
@@ -249,7 +256,28 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
       }
       if (p.has_acq) {
         const bool is_mc = p.acq.kind <= BB_ACQ_QPI;
-        if (is_mc) {
+        float s0f = 0.f, s1f = 0.f;
+        bool fast_ok = true;
+        if (is_mc && fast_mc) {
+          // every thread of the row evaluates the table; rows outside its envelope get the exact sum from one
+          // of the four warps that share the row group (they see the same ballot; rank % 4 picks the warp)
+          float c0, c1;
+          mc_coef(p.acq, mu, var, c0, c1);
+          fast_ok = mc_row_fast(s.mc_part, c0, c1, s0f, s1f);
+          unsigned need = __ballot_sync(0xffffffffu, !fast_ok);
+          for (int rank = 0; need != 0u; ++rank) {
+            const int b = __ffs(need) - 1;
+            need &= need - 1u;
+            if ((rank & 3) != sg) continue;
+            const float cb0 = __shfl_sync(0xffffffffu, c0, b), cb1 = __shfl_sync(0xffffffffu, c1, b);
+            float a0, a1;
+            mc_row_exact_warp(s.z_s, p.S, cb0, cb1, lane, a0, a1);
+            if (lane == b) {
+              s.mc_part[kMcRows + row_e] = a0;
+              s.mc_part[kMcRows + kTileM + row_e] = a1;
+            }
+          }
+        } else if (is_mc) {
           float s0, s1;
           mc_partial(p.acq, mu, var, s.z_s, p.S, sg, 4, s0, s1);
           *reinterpret_cast<float2*>(s.mc_part + (sg * kTileM + row_e) * 2) = make_float2(s0, s1);
@@ -259,11 +287,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
           float score;
           if (is_mc) {
             float s0 = 0.f, s1 = 0.f;
+            if (fast_mc) {
+              s0 = fast_ok ? s0f : s.mc_part[kMcRows + row_e];
+              s1 = fast_ok ? s1f : s.mc_part[kMcRows + kTileM + row_e];
+            } else {
 #pragma unroll
-            for (int gg = 0; gg < 4; ++gg) {
-              const float2 pr = *reinterpret_cast<const float2*>(s.mc_part + (gg * kTileM + row_e) * 2);
-              s0 += pr.x;
-              s1 += pr.y;
+              for (int gg = 0; gg < 4; ++gg) {
+                const float2 pr = *reinterpret_cast<const float2*>(s.mc_part + (gg * kTileM + row_e) * 2);
+                s0 += pr.x;
+                s1 += pr.y;
+              }
             }
             score = mc_finalize(p.acq, mu, var, s0, s1, p.S, s.zstat[0], s.zstat[1]);
           } else {

@@ -1,6 +1,8 @@
-// fused_common.cuh -- parameters and helpers shared by the two fused scoring kernels
-//   fused.cu     k_fused     distances on CUDA cores (FFMA2), any n_pad <= 512, any d
-//   fused_tc.cu  k_fused_tc  distances on tcgen05 as well (fp16 hi/mid/lo split GEMM), n_pad <= 256, d_pad <= 64
+// fused_common.cuh -- parameters and helpers shared by the scoring kernels
+//   fused_tc.cu  k_fused_tc  distances AND posterior contraction on tcgen05 (n_pad <= 256, d_pad <= 64): headline
+//   fused.cu     k_fused     distances on CUDA cores (FFMA2), n_pad <= 512, training rows resident in shared
+//                            memory; its PRE variant reads a K* block instead (wide-feature path)
+//   wide.cu      k_kmat_tc   K-looped tcgen05 distance GEMM for wide / bit-packed feature spaces and n_pad > 512
 #pragma once
 
 #include "acq_math.cuh"
