@@ -70,6 +70,40 @@ def _allreduce_key(key: torch.Tensor) -> torch.Tensor:
     return key
 
 
+def merge_topk_across_ranks(vals: torch.Tensor, idx: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Global top-k from every rank's local top-k (BASELINE config 5 "NCCL top-k argmax"): one
+    all-gather of k (value, global index) pairs per rank, then a k-way merge on every rank.  Ties go to the lowest
+    global index, like ``bb_topk`` / ``torch.argmax``.  `vals`/`idx`: this rank's best k (fewer entries may be
+    padded with -inf / -1); the tensors stay on their device (NCCL for CUDA tensors, gloo on the CPU)."""
+    import torch.distributed as dist
+
+    vals = vals.reshape(-1).to(torch.float32)
+    idx = idx.reshape(-1).to(torch.int64)
+    if vals.numel() != k or idx.numel() != k:
+        raise ValueError(f"expected {k} local candidates, got {vals.numel()} values / {idx.numel()} indices")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        world = dist.get_world_size()
+        all_v = [torch.empty_like(vals) for _ in range(world)]
+        all_i = [torch.empty_like(idx) for _ in range(world)]
+        dist.all_gather(all_v, vals)
+        dist.all_gather(all_i, idx)
+        vals, idx = torch.cat(all_v), torch.cat(all_i)
+    valid = idx >= 0
+    v = torch.where(valid, vals, torch.full_like(vals, -float("inf")))
+    # order by (value desc, index asc): stable sort by index first, then by value
+    order = torch.argsort(torch.where(valid, idx, torch.full_like(idx, torch.iinfo(torch.int64).max)), stable=True)
+    order = order[torch.argsort(v[order], descending=True, stable=True)]
+    top = order[:k]
+    return v[top], torch.where(valid[top], idx[top], torch.full_like(idx[top], -1))
+
+
+def distributed_topk(scores: torch.Tensor, keep: torch.Tensor | None, k: int, offset: int = 0):
+    """Top-k of a row-sharded score vector: per-rank ``bb_topk`` on the device, then ``merge_topk_across_ranks``."""
+    v, i = torch.ops.baybe_b200.topk(scores, keep, k)
+    i = torch.where(i >= 0, i + int(offset), i)
+    return merge_topk_across_ranks(v, i, k)
+
+
 def _scores_for(gp: DeviceGP, cfg: AcqConfig, x: torch.Tensor, pending: np.ndarray | None, seed: int,
                 n_samples: int) -> torch.Tensor:
     """Per-candidate acquisition values (q=1 batches, optionally joint with pending points)."""

@@ -68,3 +68,50 @@ def test_sharded_argmax_matches_single_process_greedy():
         ref.append(j)
         s[j] = -float("inf")
     assert got == ref and got[:2] == [5, 700]
+
+
+def _topk_worker(rank: int, world: int, port: int, scores: np.ndarray, k: int, out):
+    from baybe_b200.recommenders import merge_topk_across_ranks
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_bounds(len(scores), rank, world)
+    local = torch.from_numpy(scores[lo:hi])
+    v, i = torch.topk(local, min(k, hi - lo))  # stands in for the per-rank bb_topk (a GPU op)
+    pad = k - v.numel()
+    v = torch.cat([v, torch.full((pad,), -float("inf"))])
+    i = torch.cat([i + lo, torch.full((pad,), -1, dtype=torch.int64)])
+    gv, gi = merge_topk_across_ranks(v, i, k)
+    if rank == 1:  # every rank holds the same merged result; check the non-zero rank
+        out.put((gv.tolist(), gi.tolist()))
+    dist.destroy_process_group()
+
+
+def test_topk_merge_across_ranks():
+    """SURVEY.md 8e / BASELINE config 5: all-gather of per-rank top-k, ties to the lowest global index."""
+    rng = np.random.default_rng(1)
+    scores = rng.standard_normal(777).astype(np.float32)
+    scores[[3, 500]] = scores.max() + 2.0  # tie across the two shards
+    k = 6
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_topk_worker, args=(r, 2, port, scores, k, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    gv, gi = out.get()
+    order = np.lexsort((np.arange(len(scores)), -scores))[:k]  # value descending, index ascending
+    assert gi == order.tolist() and gi[:2] == [3, 500]
+    assert np.allclose(gv, scores[order])
+
+
+def test_topk_merge_single_process_and_padding():
+    from baybe_b200.recommenders import merge_topk_across_ranks
+
+    v = torch.tensor([2.0, 2.0, -float("inf")])
+    i = torch.tensor([9, 4, -1])
+    gv, gi = merge_topk_across_ranks(v, i, 3)
+    assert gi.tolist() == [4, 9, -1] and gv[:2].tolist() == [2.0, 2.0]
