@@ -58,7 +58,7 @@ class Model(C.Structure):
         ("d_rimg4", C.c_void_p), ("d_rimg2g", C.c_void_p),
         ("d_pend_img", C.c_void_p), ("d_pend_norm", C.c_void_p), ("d_pend_task", C.c_void_p),
         ("d_kpend_ws", C.c_void_p), ("dist_scale_p", C.c_float), ("dist_scale_wp", C.c_float),
-        ("d_wide_vacc", C.c_void_p),
+        ("d_mc_table", C.c_void_p), ("d_wide_vacc", C.c_void_p),
     ]
 
 

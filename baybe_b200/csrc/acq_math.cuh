@@ -129,7 +129,7 @@ __device__ __forceinline__ void mc_accumulate(int kind, float c0, float c1, cons
 // ------------------------------------------------------------------------------------------
 constexpr int kMcNT = 512, kMcTop = 520, kMcOk = 536, kMcRows = 544, kMcK = 16, kMcJ = 8;
 
-__device__ __forceinline__ bool mc_table_applicable(int has_acq, const bb_acq_spec& a, int S) {
+__host__ __device__ __forceinline__ bool mc_table_applicable(int has_acq, const bb_acq_spec& a, int S) {
   return has_acq && a.kind == BB_ACQ_QLOGEI && S >= 64 && (S & 63) == 0 && S <= 512;
 }
 

@@ -169,11 +169,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
     }
   }
 
-  // qLogEI: tabulated fat-tail sum (acq_math.cuh), as in fused_tc.cu.  Not in the K*-reading variant: the wide path
-  // launches it once per 37,888-row block, and rebuilding the table in every CTA of every short launch costs
-  // more than the per-sample loop it replaces (measured: config-4 shard 5.3 -> 5.7 ms).
-  const bool fast_mc = !PRE && mc_table_applicable(p.has_acq, p.acq, p.S);
-  if (fast_mc) mc_table_setup(s.mc_part, s.z_s, p.S, p.acq.obj_scale < 0.f ? -1.f : 1.f);
+  // qLogEI: tabulated fat-tail sum (acq_math.cuh), as in fused_tc.cu.  The K*-reading variant is launched once per
+  // 37,888-row block of the wide path: rebuilding the table in every CTA of every short launch cost more than it
+  // saved (config-4 shard 5.3 -> 5.7 ms), so there the table is built once per call by k_mc_table and only copied.
+  const bool fast_mc = PRE ? (p.mc_table != nullptr) : mc_table_applicable(p.has_acq, p.acq, p.S);
+  if (fast_mc) {
+    if constexpr (PRE) {
+      for (int e = tid; e < kMcRows; e += kFusedThreads) s.mc_part[e] = __ldg(p.mc_table + e);
+      __syncthreads();
+    } else {
+      mc_table_setup(s.mc_part, s.z_s, p.S, p.acq.obj_scale < 0.f ? -1.f : 1.f);
+    }
+  }
 
   if (warp < kComputeWarps) {
     // =====================================================================================
@@ -526,6 +533,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
   if (warp == kWarpProducer) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// The qLogEI table of acq_math.cuh for one set of base samples, built once per call (one CTA) into the model blob.
+__global__ void __launch_bounds__(kFusedThreads) k_mc_table(const float* __restrict__ z, int S, float sgn,
+                                                            float* __restrict__ out) {
+  __shared__ float z_s[512];
+  __shared__ float tab[kMcRows];
+  for (int e = threadIdx.x; e < S; e += blockDim.x) z_s[e] = __ldg(z + e);
+  __syncthreads();
+  mc_table_setup(tab, z_s, S, sgn);
+  for (int e = threadIdx.x; e < kMcRows; e += blockDim.x) out[e] = tab[e];
+}
+
 template <int FAMILY, int LAG, bool PRE = false, int GMAX = 1>
 static int launch_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
   BB_CUDA(cudaFuncSetAttribute(k_fused<FAMILY, LAG, PRE, GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -550,6 +568,12 @@ static int launch_wide_blocks(const bb_model* m, const FusedParams& full, int sm
   if (wc != nullptr) {
     const int rcp = launch_pend_images(m, full.layout, wc->pend_x, wc->P, stream);
     if (rcp != BB_OK) return rcp;
+  }
+  const float* mc_table = nullptr;
+  if (m->d_mc_table != nullptr && mc_table_applicable(full.has_acq, full.acq, full.S)) {
+    k_mc_table<<<1, kFusedThreads, 0, stream>>>(full.z, full.S, full.acq.obj_scale < 0.f ? -1.f : 1.f, m->d_mc_table);
+    BB_LAUNCH_CHECK();
+    mc_table = m->d_mc_table;
   }
   const int64_t es = (full.layout == BB_ROW_MAJOR_F64 || full.layout == BB_COL_MAJOR_F64) ? 8 : 4;
   const bool col_major = (full.layout == BB_COL_MAJOR_F32 || full.layout == BB_COL_MAJOR_F64);
@@ -578,6 +602,7 @@ static int launch_wide_blocks(const bb_model* m, const FusedParams& full, int sm
       p.num_tiles = (int)((nb + kTileM - 1) / kTileM);
       p.kpre = m->d_wide_ws;
       p.ldk = m->n_pad;
+      p.mc_table = mc_table;
       p.d = 0;
       p.d_pad = 0;  // nothing of the feature dimension is staged by the K*-reading kernel
       p.sb_lo = pass == 0 ? 0 : 8;

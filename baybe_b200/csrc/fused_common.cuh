@@ -59,6 +59,7 @@ struct FusedParams {
   int sb_lo, sb_hi, c_count;
   const float* vacc_in;   // |V|^2 partial of the earlier panels (null: none)
   float* vacc_out;        // non-null: this is not the last panel -- store the partial and stop
+  const float* mc_table;  // K*-reading variant: qLogEI table built once per call by k_mc_table (null: per-sample loop)
   const float* kpre;  // wide-feature path: K* block already materialised by k_kmat_tc (else null)
   int64_t ldk;
   long long* trace;  // test-only event trace (bb_debug_set_trace); null in normal operation

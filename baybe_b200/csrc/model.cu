@@ -31,7 +31,7 @@ const char* last_error() { return g_err; }
 struct BlobLayout {
   size_t cand_scale, cand_shift, train_m2, train_sq, alpha, train_task, task_covar, mean_const,
       rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, bimg, rimg2, flags,
-      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, rimg2g, pend_img, pend_norm2, pend_task, kpend_ws, vacc, total;
+      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, rimg2g, pend_img, pend_norm2, pend_task, kpend_ws, vacc, mc_table, total;
   int n_pad, d_pad, n_chunks, n_tiles;
   int wide, d_wide;
   int64_t wide_ws_rows;
@@ -83,7 +83,7 @@ static BlobLayout make_layout(int n, int d, int T) {
   L.wide = ((size_t)L.n_pad * L.d_pad * 4 > kResidentTrainBytes || L.n_pad > 512) ? 1 : 0;
   L.d_wide = round_up(d, 32);
   L.wimg = L.wimg_bits = L.wnorm_bits = L.wsrc = L.wide_ws = L.rimg4 = 0;
-  L.pend_img = L.pend_norm2 = L.pend_task = L.kpend_ws = L.vacc = 0;
+  L.pend_img = L.pend_norm2 = L.pend_task = L.kpend_ws = L.vacc = L.mc_table = 0;
   L.wide_ws_rows = 0;
   if (L.wide) {
     const size_t img = (size_t)L.n_pad * L.d_wide * 2 * 3;
@@ -99,6 +99,7 @@ static BlobLayout make_layout(int n, int d, int T) {
     L.pend_task = take(sizeof(int32_t) * 64);
     L.kpend_ws = take(sizeof(float) * (size_t)L.wide_ws_rows * 64);
     L.vacc = take(sizeof(float) * (size_t)L.wide_ws_rows);
+    L.mc_table = take(sizeof(float) * 1024);
   }
   L.total = off;
   return L;
@@ -896,6 +897,7 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
     out->d_pend_task = (int32_t*)(B + L.pend_task);
     out->d_kpend_ws = (float*)(B + L.kpend_ws);
     out->d_wide_vacc = (float*)(B + L.vacc);
+    out->d_mc_table = (float*)(B + L.mc_table);
     out->dist_scale_p = dist_scale_p;
     out->dist_scale_wp = dist_scale_wp;
     out->wide_ws_rows = L.wide_ws_rows;

@@ -160,6 +160,7 @@ typedef struct bb_model {
   float* d_kpend_ws;         /* [wide_ws_rows * 64] k(x*, pending) block                                */
   float dist_scale_p;        /* power-of-two scales of the pending images (float form / bit-linear form) */
   float dist_scale_wp;
+  float* d_mc_table;         /* [1024] per-call qLogEI table of the K*-reading kernel (acq_math.cuh)             */
   float* d_wide_vacc;        /* [wide_ws_rows] |V|^2 partial between the two column-panel passes (n_pad > 512) */
 } bb_model;
 

@@ -194,6 +194,31 @@ def test_fused_matches_two_step_path_and_keep_mask(cuda_device):
     assert decode_best(key3)[1] == idx + 1_000_000
 
 
+@pytest.mark.parametrize("minimize", [False, True])
+@pytest.mark.parametrize("S", [64, 128, 256, 512])
+def test_tabulated_qlogei_matches_exact_sample_loop(S, minimize, cuda_device):
+    """The fused kernels evaluate qLogEI through the shared-table form (16 exact terms + tabulated fat tail, exact
+    fallback rows); bb_acq_score sums every sample.  Both see the same (mu, var) and base samples."""
+    w = WORKLOADS["cfg2_small"]()
+    gp = _gp(w, cuda_device)
+    a = -1.0 if minimize else 1.0
+    z = sobol_normal_samples(S, 1, seed=11)[:, 0]
+    acq = AcqConfig(kind="qLogEI", obj_scale=a, best_f=0.0)
+    acq = AcqConfig(kind="qLogEI", obj_scale=a, best_f=gp.best_f(acq))
+    x = torch.from_numpy(w.candidates).to(cuda_device, torch.float32)
+    scores, key = gp.score(acq, x, z)
+    mu, var = gp.posterior(x)
+    exact = torch.ops.baybe_b200.acq_score(mu, var, z.to(cuda_device, torch.float32), 0, acq.params())
+    assert torch.allclose(scores, exact, rtol=2e-4, atol=2e-4), float((scores - exact).abs().max())
+    assert decode_best(key)[1] == int(torch.argmax(scores).item())
+    # a much better incumbent pushes every row into the tabulated regime, a much worse one into the exact rows
+    for shift in (-3.0, 3.0):
+        acq2 = AcqConfig(kind="qLogEI", obj_scale=a, best_f=acq.best_f + shift)
+        s2, _ = gp.score(acq2, x, z)
+        e2 = torch.ops.baybe_b200.acq_score(mu, var, z.to(cuda_device, torch.float32), 0, acq2.params())
+        assert torch.allclose(s2, e2, rtol=2e-4, atol=2e-4), (shift, float((s2 - e2).abs().max()))
+
+
 def test_topk_and_argmax_ops(cuda_device):
     g = torch.Generator().manual_seed(0)
     s = torch.randn(100_000, generator=g).to(cuda_device)

@@ -132,6 +132,20 @@ def test_wide_joint_scores_with_pending_points(name, P, cuda_device):
     assert float(ref[int(torch.argmax(got))]) >= float(ref.max()) - 4 * (5e-3 + 2e-3 * abs(float(ref.max())))
 
 
+@pytest.mark.parametrize("S", [128, 512])
+def test_wide_tabulated_qlogei_matches_exact_sample_loop(S, cuda_device):
+    """K*-reading kernel: the qLogEI table is built once per call (k_mc_table) and shared by all blocks."""
+    w = numeric_grid_workload(N=50_000, d=72, n=200, seed=23, lengthscale=2.5)
+    gp = _gp(w, cuda_device)
+    x = torch.from_numpy(w.candidates).to(cuda_device, torch.float32)
+    z = sobol_normal_samples(S, 1, seed=5)[:, 0]
+    acq = AcqConfig(kind="qLogEI", best_f=gp.best_f(AcqConfig(kind="qLogEI")))
+    scores, _ = gp.score(acq, x, z)
+    mu, var = gp.posterior(x)
+    exact = torch.ops.baybe_b200.acq_score(mu, var, z.to(cuda_device, torch.float32), 0, acq.params())
+    assert torch.allclose(scores, exact, rtol=2e-4, atol=2e-4), float((scores - exact).abs().max())
+
+
 def test_bits_and_float_layouts_agree(cuda_device):
     """The bit-linear form and the generic float form are two roundings of the same distances."""
     w = WIDE["fp2048_n512"]()
