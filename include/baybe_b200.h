@@ -264,7 +264,9 @@ int bb_topk(const float* d_score, const uint8_t* d_keep, int64_t N, int32_t k, f
 int bb_debug_posterior_simt(const bb_model* m, const void* d_x, int32_t layout, int64_t N,
                             int64_t ldx, float* d_mu, float* d_var, void* stream);
 /* test-only: record pipeline events of CTA 0 of the following fused launches into d_buf
- * ([0] = count, then (tile*1000 + event id, SM clock) int64 pairs); NULL switches it off. */
+ * ([0] = count, then capacity_pairs (tile*1000 + event id, SM clock) int64 pairs, then two counters:
+ * [1 + 2*capacity_pairs] rows that took the exact qLogEI sum, [2 + 2*capacity_pairs] rows served by the
+ * table -- so d_buf holds 2*capacity_pairs + 3 entries); NULL switches it off. */
 int bb_debug_set_trace(int64_t* d_buf, int64_t capacity_pairs);
 
 #ifdef __cplusplus
