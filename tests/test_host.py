@@ -217,3 +217,43 @@ def test_host_fit_with_presets_improves_on_the_start_point():
             (cfg.lengthscale_prior, np.full(3, cfg.lengthscale_initial_value)), (cfg.noise_prior, cfg.noise_initial_value),
             (cfg.outputscale_prior if cfg.outputscale else None, os0)] if p is not None)
         assert ok and hp["objective"] <= -(v0 + lp0) / 30 + 1e-9
+
+
+def test_packed_keys_and_topk_merge_properties():
+    """Property tests (hypothesis): the int64 key order is (score, then lowest index) for any finite floats, and the
+    cross-rank top-k merge equals a global sort."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from baybe_b200.engine import pack_best, unpack_best
+    from baybe_b200.recommenders import merge_topk_across_ranks
+
+    f32 = st.floats(width=32, allow_nan=False, allow_infinity=False)
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.tuples(f32, st.integers(0, 2**31 - 1)), min_size=1, max_size=20))
+    def keys(pairs):
+        best_key = max(pack_best(s, i) for s, i in pairs)
+        smax = max(np.float32(s) for s, _ in pairs)
+        want_idx = min(i for s, i in pairs if np.float32(s) == smax or (smax == 0 and np.float32(s) == 0))
+        val, idx = unpack_best(best_key)
+        assert np.float32(val) == smax or (smax == 0 and val == 0)
+        if not (smax == 0):  # +0.0 / -0.0 are distinct keys (bitwise order); everything else ties on equal floats
+            assert idx == want_idx
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.lists(f32, min_size=1, max_size=40), st.integers(1, 8))
+    def merge(scores, k):
+        s = torch.tensor(scores, dtype=torch.float32)
+        kk = min(k, len(scores))
+        v, i = torch.topk(s, kk)
+        pad = k - kk
+        v = torch.cat([v, torch.full((pad,), -float("inf"))])
+        i = torch.cat([i, torch.full((pad,), -1, dtype=torch.int64)])
+        gv, gi = merge_topk_across_ranks(v, i, k)
+        order = np.lexsort((np.arange(len(scores)), -np.asarray(scores, dtype=np.float32)))[:kk]
+        assert np.array_equal(gv[:kk].numpy(), np.asarray(scores, dtype=np.float32)[order])
+        assert (gi[kk:] == -1).all()
+
+    keys()
+    merge()
