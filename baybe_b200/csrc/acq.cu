@@ -49,13 +49,15 @@ __global__ void __launch_bounds__(256) k_acq_moments(const bb_acq_spec a, const 
     const int s = k * 32 + lane;
     z[k] = (s < S) ? __ldg(zg + s) : 0.f;
     sz += z[k];
-    sa += fabsf(z[k]);
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    sz += __shfl_xor_sync(0xffffffffu, sz, o);
-    sa += __shfl_xor_sync(0xffffffffu, sa, o);
-  }
-  const float z_mean = sz / (float)S, zabs_mean = sa / (float)S;
+  for (int o = 16; o > 0; o >>= 1) sz += __shfl_xor_sync(0xffffffffu, sz, o);
+  const float z_mean = sz / (float)S;
+  // qUCB centres on the SAMPLE mean (botorch qUpperConfidenceBound._sample_forward: mean = obj.mean(dim=0))
+#pragma unroll
+  for (int k = 0; k < kZPerLane; ++k)
+    if (k * 32 + lane < S) sa += fabsf(z[k] - z_mean);
+  for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+  const float zdev_mean = sa / (float)S;
   for (int64_t i = warp_global; i < N; i += nwarps) {
     const float m = __ldg(mu + i), v = __ldg(var + i);
     float c0, c1, s0 = 0.f, s1 = 0.f;
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(256) k_acq_moments(const bb_acq_spec a, const 
       s0 += __shfl_xor_sync(0xffffffffu, s0, o);
       s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     }
-    if (lane == 0) score[i] = mc_finalize(a, m, v, s0, s1, S, z_mean, zabs_mean);
+    if (lane == 0) score[i] = mc_finalize(a, m, v, s0, s1, S, z_mean, zdev_mean);
   }
 }
 
@@ -99,10 +101,11 @@ __global__ void __launch_bounds__(256) k_acq_joint(const JointParams p) {
   float* z_s = smem_j;                      // [S][zs]
   float* wbase = z_s + (size_t)p.S * zs;    // per warp: L [P][P], l [P], muP [P]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_warp = P * P + 2 * P + 2;
+  const int per_warp = P * P + 3 * P + 2;
   float* Lw = wbase + warp * per_warp;
   float* lv = Lw + P * P;
   float* mP = lv + P;
+  float* moP = mP + P;  // qUCB: sample mean of every pending point's objective
   for (int e = threadIdx.x; e < p.S * Q; e += blockDim.x) {
     int s = e / Q, k = e - s * Q;
     z_s[s * zs + k] = __ldg(p.z + e);
@@ -110,6 +113,12 @@ __global__ void __launch_bounds__(256) k_acq_joint(const JointParams p) {
   __syncthreads();
   const bb_acq_spec a = p.a;
   const float ucb_c = sqrtf(a.beta * 1.5707963267948966f);
+  // column means of the base samples (lane k: column k): the sample mean of an objective is affine in them
+  float zb = 0.f;
+  if (lane < Q) {
+    for (int s = 0; s < p.S; ++s) zb += z_s[s * zs + lane];
+    zb /= (float)p.S;
+  }
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t c = warp_global; c < p.N; c += nwarps) {
@@ -157,6 +166,18 @@ __global__ void __launch_bounds__(256) k_acq_joint(const JointParams p) {
     __syncwarp();
     // ---- Monte-Carlo over the shared base samples ----
     const float a1 = a.obj_scale, a0 = a.obj_shift;
+    // qUCB: botorch centres |o_s - mean| on the sample mean over s (obj.mean(dim=0)) of every point
+    const float zb0 = __shfl_sync(0xffffffffu, zb, 0);
+    {
+      float ym = (lane < P) ? fmaf(lv[lane], zb0, mP[lane]) : 0.f;
+      for (int j = 0; j < P; ++j) {
+        const float zbj = __shfl_sync(0xffffffffu, zb, 1 + j);
+        if (lane < P && j <= lane) ym = fmaf(Lw[lane * P + j], zbj, ym);
+      }
+      if (lane < P) moP[lane] = fmaf(a1, ym, a0);
+      __syncwarp();
+    }
+    const float mo_c = fmaf(a1, fmaf(sd, zb0, mu_c), a0);
     float run_max = -INFINITY, run_sum = 0.f;  // qLogEI: online logsumexp; others: plain sum
     for (int s = lane; s < p.S; s += 32) {
       const float* zr = z_s + s * zs;
@@ -164,7 +185,6 @@ __global__ void __launch_bounds__(256) k_acq_joint(const JointParams p) {
       float o = fmaf(a1, fmaf(sd, z0, mu_c), a0);
       float li_arr[BB_MAX_PENDING + 1];
       float red;  // per-sample reduction over the q = 1+P points
-      const float mo_c = fmaf(a1, mu_c, a0);
       if (a.kind == BB_ACQ_QLOGEI) {
         li_arr[0] = log_fatplus_f(o - a.best_f, a.tau_relu);
         red = li_arr[0];
@@ -185,7 +205,7 @@ __global__ void __launch_bounds__(256) k_acq_joint(const JointParams p) {
         else if (a.kind == BB_ACQ_QSR) val = o;
         else if (a.kind == BB_ACQ_QPI) val = 1.0f / (1.0f + __expf(-(o - a.best_f) / a.tau_pi));
         else {
-          const float mo_i = fmaf(a1, mP[i], a0);
+          const float mo_i = moP[i];
           val = mo_i + ucb_c * fabsf(o - mo_i);
         }
         red = fmaxf(red, val);
@@ -363,7 +383,7 @@ extern "C" int bb_acq_score_joint(const bb_acq_spec* a, const float* d_mu, const
   p.S = S;
   p.score = d_score;
   const int zs = (P + 1) | 1;
-  size_t smem = ((size_t)S * zs + 8 * (size_t)(P * P + 2 * P + 2)) * 4;
+  size_t smem = ((size_t)S * zs + 8 * (size_t)(P * P + 3 * P + 2)) * 4;
   int dev = 0, max_smem = 0;
   BB_CUDA(cudaGetDevice(&dev));
   BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

@@ -23,7 +23,7 @@ __device__ __forceinline__ float softplus_tail(float abs_t) {
 //   qLogEI: t = (o_s - best_f)/tau_relu ; s0 += softplus(t) ; s1 += 1/(1+t^2)
 //   qEI   : t = o_s - best_f            ; s0 += relu(t)
 //   qPI   : t = (o_s - best_f)/tau_pi   ; s0 += sigmoid(t)
-//   qUCB, qSR: closed form from the sample statistics mean(z), mean(|z|); no per-sample work.
+//   qUCB, qSR: closed form from the sample statistics mean(z), mean(|z - mean z|); no per-sample work.
 __device__ __forceinline__ void mc_coef(const bb_acq_spec& a, float mu, float var, float& c0,
                                         float& c1) {
   const float mo = fmaf(a.obj_scale, mu, a.obj_shift);
@@ -255,7 +255,7 @@ __device__ __forceinline__ void mc_row_exact_warp(const float* __restrict__ z_s,
 }
 
 __device__ __forceinline__ float mc_finalize(const bb_acq_spec& a, float mu, float var, float s0,
-                                             float s1, int S, float z_mean, float zabs_mean) {
+                                             float s1, int S, float z_mean, float zdev_mean) {
   const float sd = sqrtf(var);
   const float mo = fmaf(a.obj_scale, mu, a.obj_shift);
   const float so = a.obj_scale * sd;
@@ -267,8 +267,9 @@ __device__ __forceinline__ float mc_finalize(const bb_acq_spec& a, float mu, flo
       return s0 / (float)S;
     case BB_ACQ_QSR:
       return fmaf(so, z_mean, mo);
-    default:  // qUCB: mean_s( mo + sqrt(beta*pi/2) |o_s - mo| )
-      return fmaf(sqrtf(a.beta * 1.5707963267948966f) * fabsf(so), zabs_mean, mo);
+    default:  // qUCB: mean_s( m + sqrt(beta*pi/2) |o_s - m| ) with m = mean_s o_s, the SAMPLE mean (botorch
+              // qUpperConfidenceBound._sample_forward: mean = obj.mean(dim=0)); zdev_mean = mean_s |z_s - mean z|
+      return fmaf(sqrtf(a.beta * 1.5707963267948966f) * fabsf(so), zdev_mean, fmaf(so, z_mean, mo));
   }
 }
 

@@ -81,7 +81,7 @@ __device__ __forceinline__ FusedSmem carve_fused(uint8_t* base, const FusedParam
   s.best_red = reinterpret_cast<long long*>(cur);  // [4]
   cur += 32;
   s.tmem_ptr = reinterpret_cast<uint32_t*>(cur);
-  s.zstat = reinterpret_cast<float*>(cur + 8);  // mean z, mean |z|
+  s.zstat = reinterpret_cast<float*>(cur + 8);  // mean z, mean |z - mean z|
   return s;
 }
 
@@ -155,16 +155,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
   const uint32_t tmem_base = *s.tmem_ptr;
   if (p.has_acq && warp == 0) {
     float sz = 0.f, sa = 0.f;
-    for (int e = lane; e < p.S; e += 32) {
-      sz += s.z_s[e];
-      sa += fabsf(s.z_s[e]);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      sz += __shfl_xor_sync(0xffffffffu, sz, o);
-      sa += __shfl_xor_sync(0xffffffffu, sa, o);
-    }
+    for (int e = lane; e < p.S; e += 32) sz += s.z_s[e];
+    for (int o = 16; o > 0; o >>= 1) sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    const float zm = sz / (float)p.S;
+    for (int e = lane; e < p.S; e += 32) sa += fabsf(s.z_s[e] - zm);  // qUCB: deviations from the SAMPLE mean
+    for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
     if (lane == 0) {
-      s.zstat[0] = sz / (float)p.S;
+      s.zstat[0] = zm;
       s.zstat[1] = sa / (float)p.S;
     }
   }

@@ -14,6 +14,7 @@ import ctypes as C
 import itertools
 import math
 import threading
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -24,7 +25,9 @@ from baybe_b200 import _lib
 __all__ = ["AcqConfig", "DeviceGP", "sobol_normal_samples", "pack_best", "unpack_best", "decode_best", "DEFAULT_MC_SAMPLES"]
 
 DEFAULT_MC_SAMPLES = 512  # botorch MC acquisition default sample shape
-_registry: dict[int, "DeviceGP"] = {}
+# handle -> model; weak, so a model dropped without close() (a new recommender per BO iteration) frees its device
+# blob with the last strong reference instead of living as long as the process
+_registry: "weakref.WeakValueDictionary[int, DeviceGP]" = weakref.WeakValueDictionary()
 _registry_lock = threading.Lock()
 _handle_counter = itertools.count(1)
 
@@ -109,13 +112,15 @@ def _layout_of(x: torch.Tensor) -> tuple[int, int]:
         raise ValueError(f"candidate dtype must be float32, float64 or uint8 (bit-packed), got {x.dtype}")
     f64 = x.dtype == torch.float64
     s0, s1 = x.stride()
-    if n <= 1 or d <= 1 or (s1 == 1 and s0 >= d):
-        if s1 != 1 and d > 1:
-            x = x.contiguous()
-            s0 = d
-        return (_lib.LAYOUT["row_f64" if f64 else "row_f32"], max(int(s0), d) if n > 1 else d)
-    if s0 == 1 and s1 >= n:
+    # a single row / single column carries no layout of its own: it is whatever its strides say.  The
+    # column-major test comes FIRST so that a one-row slice of a column-major matrix (strides (1, N), what the
+    # reference hands over) is read with ld = N, and nothing here ever copies: the caller passes x.data_ptr().
+    if s0 == 1 and s1 >= n and not (s1 == 1 and s0 >= d):
         return (_lib.LAYOUT["col_f64" if f64 else "col_f32"], int(s1))
+    if s1 == 1 and (s0 >= d or n <= 1):
+        return (_lib.LAYOUT["row_f64" if f64 else "row_f32"], max(int(s0), d) if n > 1 else d)
+    if d <= 1 and s0 >= 1:  # one column, rows s0 apart: row-major with ld = s0
+        return (_lib.LAYOUT["row_f64" if f64 else "row_f32"], int(s0))
     raise ValueError("candidate matrix must be row-major or column-major (call .contiguous())")
 
 
@@ -134,9 +139,9 @@ def _as_device_matrix(x, device: torch.device, d: int) -> torch.Tensor:
         x = x.to(device, non_blocking=True)
     s0, s1 = x.stride()
     n = x.shape[0]
-    ok_row = s1 == 1 and s0 >= d
+    ok_row = s1 == 1 and (s0 >= d or n <= 1)
     ok_col = s0 == 1 and s1 >= n
-    if not (ok_row or ok_col or n <= 1):
+    if not (ok_row or ok_col):  # anything else (e.g. x[:1, ::2]) is copied HERE, where the caller sees it
         x = x.contiguous()
     return x
 

@@ -62,6 +62,19 @@ def _dist_info() -> tuple[int, int]:
     return 0, 1
 
 
+def _broadcast_seed(seed: int, device) -> int:
+    """Every rank must score its shard with the SAME base samples, or the all-reduced arg-max compares values
+    that are not comparable (ranks are usually seeded seed+rank): rank 0's draw wins."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([seed], dtype=torch.int64,
+                         device=device if dist.get_backend() == "nccl" else torch.device("cpu"))
+        dist.broadcast(t, src=0)
+        seed = int(t.item())
+    return seed
+
+
 def _allreduce_key(key: torch.Tensor) -> torch.Tensor:
     import torch.distributed as dist
 
@@ -248,7 +261,7 @@ class B200Recommender:
         pend = None
         if pending_experiments is not None and len(pending_experiments) > 0:
             pend = searchspace.transform(pending_experiments, allow_extra=True).to_numpy(dtype=np.float64)
-        seed = _draw_sampler_seed()
+        seed = _broadcast_seed(_draw_sampler_seed(), gp.device)
         positions, vals = greedy_select(gp, cfg, x_dev, x_host, batch_size, pend, seed,
                                         self.n_mc_samples, offset=lo, keep_init=keep_init)
         self._last_acq_values = vals

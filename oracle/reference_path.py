@@ -409,7 +409,7 @@ def _fatmax(x: torch.Tensor, tau: float, dim: int = -1) -> torch.Tensor:
     return (M + tau * par.sum(dim=dim, keepdim=True).log()).squeeze(dim)
 
 
-def _mc_reduce(acq: AcqSpec, obj: torch.Tensor, mean_obj: torch.Tensor | None) -> torch.Tensor:
+def _mc_reduce(acq: AcqSpec, obj: torch.Tensor, mean_obj: torch.Tensor | None = None) -> torch.Tensor:
     """obj: (S, B, q) objective samples -> (B,) acquisition values."""
     S = obj.shape[0]
     k = acq.kind
@@ -424,9 +424,11 @@ def _mc_reduce(acq: AcqSpec, obj: torch.Tensor, mean_obj: torch.Tensor | None) -
     if k == "qPI":
         return torch.sigmoid((obj - acq.best_f) / acq.tau_pi).amax(-1).mean(0)
     if k == "qUCB":
-        assert mean_obj is not None
+        # botorch qUpperConfidenceBound._sample_forward: ``mean = obj.mean(dim=0)`` -- the SAMPLE mean over
+        # the MC dimension, not the posterior mean (they differ by so*mean(z) for scrambled Sobol samples)
         c = math.sqrt(acq.beta * math.pi / 2.0)
-        return (mean_obj + c * (obj - mean_obj).abs()).amax(-1).mean(0)
+        m = obj.mean(dim=0, keepdim=True)
+        return (m + c * (obj - m).abs()).amax(-1).mean(0)
     raise ValueError(k)
 
 
@@ -453,6 +455,20 @@ def _analytic(acq: AcqSpec, mu: torch.Tensor, var: torch.Tensor) -> torch.Tensor
     raise ValueError(k)
 
 
+def acq_from_moments(acq: AcqSpec, mu: torch.Tensor, var: torch.Tensor, z: torch.Tensor | None = None) -> torch.Tensor:
+    """q=1 acquisition values from marginal posterior moments (original units): the step after
+    ``model.posterior`` inside the acquisition function's forward.  z: (S,) base samples for the MC kinds."""
+    mu = torch.as_tensor(mu, dtype=DTYPE).reshape(-1)
+    var = torch.as_tensor(var, dtype=DTYPE).reshape(-1)
+    if not acq.is_mc:
+        return _analytic(acq, mu, var)
+    assert z is not None, "MC acquisition functions need base samples"
+    zc = z.reshape(-1, 1).to(DTYPE)  # (S,1)
+    y = mu.unsqueeze(0) + var.sqrt().unsqueeze(0) * zc  # (S,B)
+    obj = (acq.obj_scale * y + acq.obj_shift).unsqueeze(-1)
+    return _mc_reduce(acq, obj, None)
+
+
 def acq_values(
     model: GPModel, acq: AcqSpec, X: np.ndarray | torch.Tensor, z: torch.Tensor | None = None,
     chunk: int | None = MAX_BATCH_SIZE,
@@ -464,18 +480,9 @@ def acq_values(
     N = X.shape[0]
     out = torch.empty(N, dtype=DTYPE)
     step = N if not chunk else chunk
-    if acq.is_mc:
-        assert z is not None, "MC acquisition functions need base samples"
-        zc = z.reshape(-1, 1).to(DTYPE)  # (S,1)
     for s in range(0, N, max(step, 1)):
         mu, var = posterior(model, X[s : s + step])
-        if acq.is_mc:
-            y = mu.unsqueeze(0) + var.sqrt().unsqueeze(0) * zc  # (S,B)
-            obj = (acq.obj_scale * y + acq.obj_shift).unsqueeze(-1)
-            mo = (acq.obj_scale * mu + acq.obj_shift).reshape(1, -1, 1)
-            out[s : s + step] = _mc_reduce(acq, obj, mo)
-        else:
-            out[s : s + step] = _analytic(acq, mu, var)
+        out[s : s + step] = acq_from_moments(acq, mu, var, z)
     return out
 
 
@@ -539,8 +546,7 @@ def acq_values_joint(
         Lc = _chol_with_jitter(cov)  # (B,1+p,1+p)
         y = mean.unsqueeze(0) + torch.einsum("bij,sj->sbi", Lc, z)  # (S,B,1+p)
         obj = acq.obj_scale * y + acq.obj_shift
-        mo = (acq.obj_scale * mean + acq.obj_shift).unsqueeze(0)
-        out[s : s + step] = _mc_reduce(acq, obj, mo)
+        out[s : s + step] = _mc_reduce(acq, obj, None)
     return out
 
 

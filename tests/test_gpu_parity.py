@@ -6,10 +6,11 @@ Stated tolerances (float32 engine vs float64 oracle, standardised-target units ~
   posterior mean  |dmu|       <= 5e-5 * max(1, |mu|_inf)   (fp32 dot product against alpha)
   posterior var   |dvar|      <= 2e-5 * prior variance     (fp16x3 tensor-core contraction)
   acquisition     rtol 1e-4 / atol 0.1 is what the reference itself accepts
-                  (/root/reference/tests/integration/test_minimization.py:78); we hold
-                  |d score| <= 2e-3 + 2e-3*|score| for MC kinds on log scale.
-  recommended index: identical to the oracle when the oracle's top-2 gap exceeds the score
-                  tolerance, else the GPU winner must be within tolerance of the oracle's best.
+                  (/root/reference/tests/integration/test_minimization.py:78); we hold, for EVERY row,
+                  |d score| <= 2e-4 + 1e-4*|score| + 1.5 * (score change the posterior tolerance above can
+                  cause at that row, evaluated by the oracle) -- tests/helpers.py::score_bounds.
+  recommended index: identical to the oracle whenever no other row's score interval overlaps the
+                  oracle winner's; otherwise the GPU winner's oracle score lies within the two bounds.
 """
 from __future__ import annotations
 
@@ -21,7 +22,7 @@ import oracle
 from baybe_b200 import AcqConfig, DeviceGP, sobol_normal_samples
 from baybe_b200.engine import decode_best
 from baybe_b200.synthetic import (mixed_small_workload, numeric_grid_workload, task_workload)
-from tests.helpers import oracle_model
+from tests.helpers import oracle_model, score_bounds
 
 pytestmark = pytest.mark.gpu
 
@@ -148,25 +149,23 @@ def test_fused_scores_and_argmax(kind, name, minimize, cuda_device):
     assert abs(acq.best_f - oacq.best_f) <= 5e-5 * max(1.0, abs(oacq.best_f))
     x = torch.from_numpy(w.candidates).to(cuda_device, torch.float32)
     scores, key = gp.score(acq, x, z[:, 0] if acq.is_mc else None)
-    ref = oracle.acq_values(om, oacq, w.candidates, z[:, 0] if oacq.is_mc else None)
+    # hard per-row bound: float32 acquisition arithmetic + what the stated posterior tolerance can move the score
+    ref, bound = score_bounds(om, oacq, w.candidates, z[:, 0] if oacq.is_mc else None)
     got = scores.double().cpu()
-    atol, rtol = _score_tols(kind)
-    if kind == "qPI":
-        # sigmoid((o - best_f)/1e-3) amplifies posterior errors by 1/tau
-        atol = 5e-2
     err = (got - ref).abs()
-    bound = atol + rtol * ref.abs()
-    frac_bad = float((err > bound).double().mean())
-    assert frac_bad <= 0.002, f"{kind}: {frac_bad:.4f} of scores outside tolerance, max err {float(err.max()):.3e}"
+    worst = int(torch.argmax(err - bound))
+    assert bool((err <= bound).all()), (f"{kind}: row {worst} |err| {float(err[worst]):.3e} > bound "
+                                        f"{float(bound[worst]):.3e} (ref {float(ref[worst]):.5f})")
     val, idx = decode_best(key)
     assert idx == int(torch.argmax(scores).item())  # first maximum, like torch.argmax
     assert val == float(scores[idx].item())
-    ref_best = float(ref.max())
-    # winner parity: GPU winner is (within tolerance) as good as the oracle's winner
-    assert float(ref[idx]) >= ref_best - (atol + rtol * abs(ref_best))
-    top2 = torch.topk(ref, 2).values
-    if float(top2[0] - top2[1]) > 4 * (atol + rtol * abs(ref_best)):
-        assert idx == int(torch.argmax(ref).item())
+    # winner parity: identical to the oracle's winner unless the oracle's runner-up is within the winner's own bound
+    ref_idx = int(torch.argmax(ref).item())
+    ref_best = float(ref[ref_idx])
+    assert float(ref[idx]) >= ref_best - float(bound[ref_idx] + bound[idx])
+    contenders = torch.nonzero(ref + bound >= ref_best - float(bound[ref_idx])).reshape(-1)
+    if contenders.numel() == 1:
+        assert idx == ref_idx
 
 
 def test_fused_matches_two_step_path_and_keep_mask(cuda_device):
@@ -255,10 +254,15 @@ def test_joint_scores_with_pending_points(kind, P, cuda_device):
     z = sobol_normal_samples(512, 1 + P, seed=99)
     got = gp.score_joint(acq, torch.from_numpy(cand), pending, z).double().cpu()
     ref = oracle.acq_values_joint(om, oacq, cand, pending, z)
-    atol, rtol = _score_tols(kind)
+    # joint scores see the candidate's moments AND its covariance with the pending points; the q=1 bound of the
+    # candidate's own row, doubled for the cross terms, holds for every row (no outlier allowance)
+    _, bound = score_bounds(om, oacq, cand, z[:, 0])
+    bound = 2.0 * bound + 2e-3
     err = (got - ref).abs()
-    assert float((err > 4 * atol + 4 * rtol * ref.abs()).double().mean()) <= 0.005, float(err.max())
-    assert float(ref[int(torch.argmax(got))]) >= float(ref.max()) - 4 * (atol + rtol * abs(float(ref.max())))
+    worst = int(torch.argmax(err - bound))
+    assert bool((err <= bound).all()), (kind, P, worst, float(err[worst]), float(bound[worst]))
+    win = int(torch.argmax(got))
+    assert float(ref[win]) >= float(ref.max()) - float(bound[win] + bound[int(torch.argmax(ref))])
 
 
 def test_errors_are_loud(cuda_device):

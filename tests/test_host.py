@@ -257,3 +257,49 @@ def test_packed_keys_and_topk_merge_properties():
 
     keys()
     merge()
+
+
+def test_layout_detection_never_copies_and_reads_strides():
+    """a one-row slice of a column-major matrix -- the layout the reference hands over,
+    baybe/utils/dataframe.py:68-81 -- must be reported as column-major with ld = N (it used to be taken for a
+    row, and a local .contiguous() hid the mismatch from the caller's data_ptr)."""
+    from baybe_b200 import _lib
+    from baybe_b200.engine import _as_device_matrix, _layout_of
+
+    L = _lib.LAYOUT
+    N, d = 7, 5
+    row = torch.arange(N * d, dtype=torch.float32).reshape(N, d)
+    col = row.t().contiguous().t()  # strides (1, N)
+    assert _layout_of(row) == (L["row_f32"], d)
+    assert _layout_of(col) == (L["col_f32"], N)
+    assert _layout_of(col[:1]) == (L["col_f32"], N)      # one row of a column-major matrix
+    assert _layout_of(row[:1]) == (L["row_f32"], d)
+    assert _layout_of(row.double()[:, :3]) == (L["row_f64"], d)  # padded leading dimension
+    assert _layout_of(row[:, :1]) == (L["row_f32"], d)   # one column, rows d apart
+    assert _layout_of(torch.zeros(1, 1)) == (L["row_f32"], 1)
+    with pytest.raises(ValueError):
+        _layout_of(row[:, ::2])
+    # the only place a copy may happen is _as_device_matrix, whose result the caller uses
+    fixed = _as_device_matrix(row[:1, ::2], torch.device("cpu"), 3)
+    assert fixed.is_contiguous() and _layout_of(fixed) == (L["row_f32"], 3)
+    same = _as_device_matrix(col[:1], torch.device("cpu"), d)
+    assert same.data_ptr() == col.data_ptr() and _layout_of(same) == (L["col_f32"], N)
+
+
+def test_model_registry_holds_models_weakly():
+    """the handle registry must not keep a dropped DeviceGP (and its device blob) alive."""
+    import gc
+    import weakref
+
+    from baybe_b200 import engine
+
+    class Dummy:
+        pass
+
+    assert isinstance(engine._registry, weakref.WeakValueDictionary)
+    obj = Dummy()
+    engine._registry[-1] = obj
+    assert engine._registry.get(-1) is obj
+    del obj
+    gc.collect()
+    assert engine._registry.get(-1) is None

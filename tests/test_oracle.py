@@ -208,3 +208,110 @@ def test_golden_fixtures(name):
     fresh = evaluate(WORKLOADS[name]())
     for key, ref in data["values"].items():
         assert np.allclose(np.asarray(fresh[key]), np.asarray(ref), rtol=1e-9, atol=1e-12), key
+
+
+# --------------------------------------------------------------------------------------
+# Independent checks of the parts no second implementation covers
+# --------------------------------------------------------------------------------------
+def test_qlogei_matches_arbitrary_precision_definition():
+    """qLogEI restated from its published definition in 60-digit arithmetic (mpmath), independent of the
+    oracle's float64 branches (log-softplus tail switch at t < -30, logaddexp, logsumexp):
+        fatplus(x; tau) = tau * ( log(1 + e^{x/tau}) + 0.1 / (1 + (x/tau)^2) ),   tau = 1e-6
+        qLogEI          = log( (1/S) sum_s fatplus(o_s - best_f) )                (q = 1: fatmax is the identity)."""
+    import mpmath as mp
+
+    mp.mp.dps = 60
+    z = oracle.sobol_normal_samples(128, 1, 77)[:, 0]
+    cases = [(0.3, 0.04, 0.9), (1.2, 0.25, 1.0), (-0.5, 1e-4, 0.1), (2.0, 1e-10, 1.0), (0.999999, 1e-6, 1.0),
+             (0.0, 9.0, 0.5), (5.0, 0.01, -3.0)]
+    for mu, var, best in cases:
+        for a in (1.0, -1.0):
+            acq = oracle.AcqSpec("qLogEI", best_f=best, obj_scale=a)
+            got = float(oracle.reference_path.acq_from_moments(acq, np.array([mu]), np.array([var]), z))
+            tau = mp.mpf(10) ** -6
+            tot = mp.mpf(0)
+            for zs in z.tolist():
+                x = (mp.mpf(a) * (mp.mpf(mu) + mp.sqrt(mp.mpf(var)) * mp.mpf(zs)) - mp.mpf(best)) / tau
+                tot += tau * (mp.log1p(mp.e**x) + mp.mpf("0.1") / (1 + x * x))
+            want = float(mp.log(tot / len(z)))
+            assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (mu, var, best, a, got, want)
+
+
+def test_fatmax_matches_arbitrary_precision_definition():
+    """fatmax(x; tau) = M + tau * log sum_i (1 + (M - x_i)/(alpha tau))^-alpha, alpha = 2 (q > 1 reduction of qLogEI)."""
+    import mpmath as mp
+
+    mp.mp.dps = 50
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 4, generator=g, dtype=torch.float64) * 3.0 - 12.0
+    got = oracle.reference_path._fatmax(x, 1e-2, dim=-1)
+    for r in range(5):
+        xs = [mp.mpf(v) for v in x[r].tolist()]
+        M = max(xs)
+        tau = mp.mpf("0.01")
+        want = M + tau * mp.log(sum((1 + (M - v) / (2 * tau)) ** -2 for v in xs))
+        assert abs(float(got[r]) - float(want)) < 1e-12
+
+
+def test_qucb_centres_on_the_sample_mean():
+    """botorch ``qUpperConfidenceBound._sample_forward``: ``mean = obj.mean(dim=0)`` (the MC sample mean) and
+    ``mean + sqrt(beta*pi/2) * |obj - mean|``; with scrambled Sobol samples mean(z) != 0, so this differs from
+    centring on the posterior mean.  Brute force over the samples, both orientations."""
+    z = oracle.sobol_normal_samples(512, 1, 1234)[:, 0]
+    assert abs(float(z.mean())) > 1e-6  # the distinction is observable
+    mu, var = torch.tensor([0.7, -1.3], dtype=torch.float64), torch.tensor([0.09, 2.0], dtype=torch.float64)
+    for a in (1.0, -1.0):
+        acq = oracle.AcqSpec("qUCB", beta=0.2, obj_scale=a, obj_shift=0.25)
+        got = oracle.reference_path.acq_from_moments(acq, mu, var, z)
+        obj = a * (mu[None, :] + var.sqrt()[None, :] * z[:, None]) + 0.25  # (S, B)
+        m = obj.mean(0)
+        want = (m + math.sqrt(0.2 * math.pi / 2) * (obj - m).abs()).mean(0)
+        assert torch.allclose(got, want, rtol=0, atol=1e-13)
+        # closed form used by the CUDA kernels: mo + so*mean(z) + c*|so|*mean|z - mean z|
+        mo, so = a * mu + 0.25, a * var.sqrt()
+        closed = mo + so * z.mean() + math.sqrt(0.2 * math.pi / 2) * so.abs() * (z - z.mean()).abs().mean()
+        assert torch.allclose(got, closed, rtol=0, atol=1e-12)
+
+
+def test_sobol_normal_recipe_against_scipy():
+    """The base-sample recipe: torch SobolEngine(scramble=True, seed) uniforms ->
+    v = 0.5 + (1 - eps)(u - 0.5) -> Phi^-1(v).  The uniforms come from the same torch engine botorch uses (its
+    scrambling is torch's own, so no second library reproduces it bit for bit); checked here are (i) the
+    unscrambled engine against scipy's Joe-Kuo Sobol points, (ii) the inverse-CDF transform against scipy's
+    norm.ppf, (iii) the 2-D draw used for q = 2 rounds keeps column 0 a valid 1-D normal sample set."""
+    from scipy.stats import qmc
+
+    u_t = torch.quasirandom.SobolEngine(dimension=3, scramble=False).draw(64, dtype=torch.float64).numpy()
+    u_s = qmc.Sobol(d=3, scramble=False, bits=30).random(64)
+    assert np.allclose(np.sort(u_t, axis=0), np.sort(u_s, axis=0), atol=1e-9)
+    eng = torch.quasirandom.SobolEngine(dimension=1, scramble=True, seed=1234)
+    u = eng.draw(512, dtype=torch.float64)
+    v = 0.5 + (1.0 - np.finfo(np.float64).eps) * (u.numpy() - 0.5)
+    z = oracle.sobol_normal_samples(512, 1, 1234).numpy()
+    assert np.allclose(z, norm.ppf(v), rtol=1e-11, atol=1e-12)
+    assert 0.0 <= float(u.min()) and float(u.max()) < 1.0
+    z2 = oracle.sobol_normal_samples(512, 2, 1234)
+    assert z2.shape == (512, 2) and torch.isfinite(z2).all()
+
+
+def test_standardize_and_noise_conventions():
+    """botorch ``Standardize(m=1)``: unbiased std, std < 1e-8 -> 1; homoskedastic noise floored at 1e-4
+    (MIN_INFERRED_NOISE_LEVEL, presets/baybe.py:129-144); posterior un-transform mu = ybar + s mu~, var = s^2 var~."""
+    spec = oracle.KernelSpec("matern52", [0.5], [0])
+    X = np.array([[0.1], [0.4], [0.8]])
+    y = np.array([1.0, 3.0, 8.0])
+    m = oracle.build_model(spec, X, y, np.array([[0.0], [1.0]]), noise=1e-3)
+    assert abs(m.y_mean - 4.0) < 1e-15 and abs(m.y_std - float(np.std(y, ddof=1))) < 1e-15
+    const = oracle.build_model(spec, X, np.array([2.0, 2.0, 2.0]), np.array([[0.0], [1.0]]), noise=1e-3)
+    assert const.y_std == 1.0
+    # explicit K^-1 formulas (no Cholesky) for the posterior in original units
+    Xn = torch.tensor(X)
+    K = oracle.kernel_matrix(spec, Xn, Xn) + 1e-3 * torch.eye(3, dtype=torch.float64)
+    xs = np.array([[0.55]])
+    ks = oracle.kernel_matrix(spec, torch.tensor(xs), Xn)
+    yt = torch.tensor((y - 4.0) / np.std(y, ddof=1))
+    Kinv = torch.linalg.inv(K)
+    mu_ref = 4.0 + np.std(y, ddof=1) * float(ks @ Kinv @ yt)
+    var_ref = np.var(y, ddof=1) * float(1.0 - ks @ Kinv @ ks.T)
+    mu, var = oracle.posterior(m, xs)
+    assert abs(float(mu) - mu_ref) < 1e-10 and abs(float(var) - var_ref) < 1e-10
