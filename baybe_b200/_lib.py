@@ -9,7 +9,7 @@ import ctypes as C
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "_C" / "libbaybe_b200.so"
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums (mirror include/baybe_b200.h)
 KERNEL_FAMILY = {"matern12": 0, "matern32": 1, "matern52": 2, "rbf": 3}
@@ -59,6 +59,9 @@ class Model(C.Structure):
         ("d_pend_img", C.c_void_p), ("d_pend_norm", C.c_void_p), ("d_pend_task", C.c_void_p),
         ("d_kpend_ws", C.c_void_p), ("dist_scale_p", C.c_float), ("dist_scale_wp", C.c_float),
         ("d_mc_table", C.c_void_p), ("d_wide_vacc", C.c_void_p),
+        ("d_timg_l", C.c_void_p), ("d_timg_b", C.c_void_p), ("d_ts_alpha", C.c_void_p),
+        ("ts_sa", C.c_float), ("ts_aug_sq", C.c_float), ("ts_aug_one", C.c_float), ("ts_g", C.c_float),
+        ("ts_kscale", C.c_float), ("pad3_", C.c_int32),
     ]
 
 

@@ -18,7 +18,7 @@ OUT_DIR = PKG / "_C"
 LIB_PATH = OUT_DIR / "libbaybe_b200.so"
 STAMP = OUT_DIR / "build.stamp"
 
-SOURCES = ["model.cu", "fused.cu", "fused_tc.cu", "wide.cu", "aux_kernels.cu", "acq.cu"]
+SOURCES = ["model.cu", "fused.cu", "fused_tc.cu", "fused_ts.cu", "wide.cu", "aux_kernels.cu", "acq.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -62,10 +62,12 @@ def build(force: bool = False, verbose: bool = True) -> Path:
         out, _ = pr.communicate()
         if pr.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out.decode()}")
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs]
+    tmp = LIB_PATH.with_suffix(".so.tmp")  # link aside, then rename: a concurrent reader never sees half a library
+    cmd = [nvcc, "-shared", "-o", str(tmp), *objs]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB_PATH)
     STAMP.write_text(digest)
     return LIB_PATH
 

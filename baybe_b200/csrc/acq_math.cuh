@@ -228,6 +228,41 @@ __device__ __forceinline__ bool mc_row_fast(const float* __restrict__ tab, float
   return fast;
 }
 
+// mc_row_fast split over the four lanes that share a row in fused_ts.cu: lane `sub` (0..3) evaluates the exact
+// terms k = sub, sub+4, sub+8, sub+12 of the sixteen, lane 0 adds the tabulated tail; the caller sums (s0, s1) over
+// the four lanes (fixed order: the value of a row does not depend on where it is evaluated).  The envelope test
+// is identical in the four lanes.
+__device__ __forceinline__ bool mc_row_fast_part(const float* __restrict__ tab, float c0, float c1, int sub,
+                                                 float& s0, float& s1) {
+  const float ac1 = fabsf(c1);
+  const float t9 = fmaf(ac1, tab[kMcTop + kMcJ], c0);
+  const float t17 = fmaf(ac1, tab[kMcTop + kMcK - 1], c0);
+  const bool fast = tab[kMcOk] != 0.f && ac1 > 1e-30f && t9 <= 0.f && t17 <= -1024.f;
+  s0 = 0.f;
+  s1 = 0.f;
+  if (fast) {
+#pragma unroll
+    for (int k = 0; k < kMcK / 4; ++k) {
+      const float t = fmaf(ac1, tab[kMcTop + sub + 4 * k], c0);
+      s0 += fmaxf(t, 0.f);
+      s1 += fast_rcp(fmaf(t, t, 1.0f));
+      if (fabsf(t) < 30.f) s0 += softplus_tail(fabsf(t));  // within 30 tau of the incumbent (rare)
+    }
+    if (sub == 0) {
+      const float inv = 1.0f / ac1;
+      const float a = fmaf(-t9, inv, 1.0f);  // w - zeta_(9) + 1 >= 1, no cancellation
+      const float v = 1.0f / a;
+      const float x = v * (float)kMcNT;
+      const int i = min((int)x, kMcNT - 1);
+      const float fr = x - (float)i;
+      const float f0 = tab[i], f1 = tab[i + 1];
+      const float q = v * inv;
+      s1 = fmaf(fmaf(fr, f1 - f0, f0), q * q, s1);
+    }
+  }
+  return fast;
+}
+
 // Exact (s0, s1) of one row by a whole warp: lane l takes samples l, l+32, ...; fixed reduction order, so a row's
 // value does not depend on where it is evaluated.  Result in every lane.
 __device__ __forceinline__ void mc_row_exact_warp(const float* __restrict__ z_s, int S, float c0, float c1, int lane,

@@ -727,6 +727,14 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   p.stage_b_bytes = kStageBBytes;
   p.trace = g_trace_buf;
   p.trace_cap = g_trace_cap;
+  p.timg_l = reinterpret_cast<const uint8_t*>(m->d_timg_l);
+  p.timg_b = reinterpret_cast<const uint8_t*>(m->d_timg_b);
+  p.ts_alpha = m->d_ts_alpha;
+  p.ts_sa = m->ts_sa;
+  p.ts_aug_sq = m->ts_aug_sq;
+  p.ts_aug_one = m->ts_aug_one;
+  p.ts_g = m->ts_g;
+  p.ts_kscale = m->ts_kscale;
   BB_CHECK_SUPPORTED(p.n_pad <= 512 || m->wide, "n_pad=%d exceeds the 512 TMEM columns", p.n_pad);
   const int lag = (2 * p.n_pad <= 512) ? 1 : 0;  // two accumulators fit: defer the epilogue
   uint32_t cols = 32;
@@ -738,6 +746,10 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (m->wide) return launch_wide_blocks(m, p, sms, max_smem, wc, stream);
+  if (g_trace_buf == nullptr && fused_ts_supported(p, max_smem)) {  // headline kernel (fused_ts.cu); tracing is a fused_tc feature
+    const int grid_ts = p.num_tiles < sms ? p.num_tiles : sms;
+    return launch_fused_ts(p, grid_ts, stream);
+  }
   if (fused_tc_supported(p, max_smem)) {
     const int grid_tc = p.num_tiles < sms ? p.num_tiles : sms;
     return launch_fused_tc(p, grid_tc, stream);

@@ -64,6 +64,15 @@ struct FusedParams {
   int64_t ldk;
   long long* trace;  // test-only event trace (bb_debug_set_trace); null in normal operation
   int trace_cap;
+  // fused_ts.cu (A operand of the V contraction in tensor memory): operand images and folded constants
+  const uint8_t* timg_l;   // L^-1 image: [hi tiles, chunk c = 0..C-1][lo tiles], tile c = (n_pad - 64c) rows x 64 k, SW128
+  const uint8_t* timg_b;   // augmented training-row image: 3 splits x n_pad rows x 32 k (|b|^2 and 1 in k = 31, 30), SW64
+  const float* ts_alpha;   // alpha / ts_kscale
+  float ts_sa;             // power of two folded into the candidate rows of the A2 image
+  float ts_aug_sq;         // A2 column 30 = |a|^2 * ts_aug_sq
+  float ts_aug_one;        // A2 column 31 = ts_aug_one
+  float ts_g;              // D2 * ts_g = scaled squared distance t (family constant folded in)
+  float ts_kscale;         // power of two folded into K* before the fp16 hi/lo split
 };
 
 // test-only: (event id, SM clock) pairs of CTA 0 for a few tiles, to reconstruct the pipeline timeline
@@ -125,6 +134,20 @@ __device__ __forceinline__ void split3_quad(const float (&x)[4], uint2& hi, uint
 }
 
 int launch_fused_tc(FusedParams& p, int grid, cudaStream_t stream);
+int launch_fused_ts(FusedParams& p, int grid, cudaStream_t stream);
+bool fused_ts_supported(const FusedParams& p, int max_smem);
+// elect.sync: true in exactly one lane of a converged warp.  tcgen05.mma / cp.async.bulk / tcgen05.commit issued
+// under this predicate compile to straight uniform-datapath code; the same instructions under `if (lane == 0)` are
+// wrapped by ptxas in an ELECT / R2UR / BRA.U.ANY loop that costs ~106 cycles per MMA (scripts/ubench/mma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 bool fused_tc_supported(FusedParams& p, int max_smem);
 int launch_pend_images(const bb_model* m, int32_t layout, const float* d_pend_x, int32_t P, cudaStream_t stream);
 int launch_cross_wide(const bb_model* m, const void* d_x, int32_t layout, int64_t nb, int64_t ldx,

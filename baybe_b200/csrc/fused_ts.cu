@@ -1,0 +1,691 @@
+// fused_ts.cu -- fused scoring kernel, round-2 headline (n_pad <= 256, d <= 30, S <= 512, Matern-3/2, -5/2, RBF).
+//
+// Same mathematics as fused_tc.cu (GEMM-form distances like gpytorch's Distance._sq_dist, closed-form kernel,
+// V = K* L^-T on tcgen05, sigma^2 = k** - |V|^2, q = 1 acquisition, packed-key arg-max); what changed is how the
+// tensor pipe and the CUDA cores are fed -- every change follows a measurement (scripts/ubench/mma_rate.cu,
+// profiles/r02_*):
+//   * MMAs are issued by a CONVERGED warp under elect.sync.  Issued under `if (lane == 0)` every tcgen05.mma is
+//     wrapped by ptxas in an ELECT/R2UR/BRA.U.ANY loop: ~106 cycles per instruction whatever its shape, which is
+//     what bounded fused_tc.cu (146-182 cycles per MMA against 32-128 of math).
+//   * The A operand of the V contraction (the converted K* chunk, fp16 hi/lo) lives in TENSOR MEMORY (TS form):
+//     each thread overwrites the 16 D2 columns it just read with 8 packed hi + 8 packed lo columns.  No A ring in
+//     shared memory, no per-MMA re-read of A from shared memory, no "slot empty" wait in the conversion loop.
+//   * One MMA spans every output column a K step can reach (N = n_pad - 64c - 16kk <= 256): 68 MMAs per 128-row
+//     tile instead of 84, and the triangular skip at 16-column granularity (8.5/16 of n^2 instead of 10/16).
+//   * |a|^2 + |b|^2 ride in two spare K columns of the distance GEMM (A2 = [a, |a|^2 P, P1], Bt = [-2b, Q1, |b|^2 Q]),
+//     so the accumulator holds the scaled squared distance itself and the per-value epilogue is
+//     FMNMX, MUFU.SQRT, MUFU.EX2 and packed f32x2 arithmetic: 8 instructions per kernel value (19 before).
+//   * The hi image of L^-1 and the training rows are RESIDENT in shared memory; only the lo image (80 KB per tile at
+//     n_pad = 256) streams from L2 through a 3-stage bulk-copy ring.
+//   * The acquisition of a row is evaluated by four lanes of ONE warp (rows are redistributed after the
+//     |V|^2 / mean partials meet in shared memory), not redundantly by the four warps that share the row.
+//
+// Tensor memory: columns [0, n_pad) V accumulator; [256, 256 + n_pad) D2, overwritten in place by the A operand.
+// Reference path replaced: see fused.cu.
+#include "assemble.cuh"
+#include "fused_common.cuh"
+
+namespace bb {
+
+constexpr int kTsK2 = 32;                    // K extent of the augmented distance GEMM: d data columns + 2
+constexpr int kTsColSq = 30, kTsColOne = 31; // A2 columns holding |a|^2 * P and P1 (Bt holds Q1 and |b|^2 * Q there)
+constexpr uint32_t kTsLoStage = 16384;       // one streamed piece of the lo image: <= 128 rows x 64 k fp16
+constexpr int kTsLoStages = 3;
+constexpr uint32_t kTsD2Col0 = 256;
+constexpr uint32_t kTsA2Split = 128u * kTsK2 * 2u;  // one fp16 panel of the candidate tile: 8 KB
+
+struct TsSmem {
+  uint8_t *lh, *ring, *bt, *a2;
+  float *alpha_s, *z_s, *mc_tab, *tcov, *meanc, *cscale_s, *cshift_s, *an_part, *mean_part, *var_part;
+  int32_t *ttask, *cand_task;
+  uint64_t *a_full, *vsub_full, *r_full, *r_empty, *d2_full, *a2_full, *v_empty, *res_full;
+  long long* best_red;
+  uint32_t* tmem_ptr;
+  float* zstat;
+};
+
+__host__ __device__ inline uint32_t ts_hi_bytes(int n_pad) {  // sum over chunks of (n_pad - 64c) rows x 128 B
+  uint32_t b = 0;
+  for (int r = n_pad; r > 0; r -= kChunk) b += (uint32_t)r * 128u;
+  return b;
+}
+
+__host__ __device__ inline size_t ts_carve(uint8_t* base, int n_pad, int n_tasks, TsSmem* s) {
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t align) {
+    off = (off + align - 1) / align * align;
+    size_t o = off;
+    off += bytes;
+    return o;
+  };
+  const size_t o_lh = take(ts_hi_bytes(n_pad), 1024);
+  const size_t o_ring = take((size_t)kTsLoStages * kTsLoStage, 1024);
+  const size_t o_bt = take((size_t)3 * n_pad * kTsK2 * 2, 1024);
+  const size_t o_a2 = take((size_t)3 * kTsA2Split, 1024);
+  const size_t o_al = take((size_t)n_pad * 4, 16), o_tt = take((size_t)n_pad * 4, 16);
+  const size_t o_z = take(512 * 4, 16), o_mc = take(1024 * 4, 16);
+  const size_t o_tc = take((size_t)kMaxTasks * kMaxTasks * 4, 16), o_mcn = take(kMaxTasks * 4, 16);
+  const size_t o_cs = take(32 * 4, 16), o_sh = take(32 * 4, 16);
+  const size_t o_an = take(4 * kTileM * 4, 16);
+  const size_t o_mp = take(2 * 4 * kTileM * 4, 16), o_vp = take(2 * 4 * kTileM * 4, 16);
+  const size_t o_ct = take(2 * kTileM * 4, 16);
+  const size_t o_bar = take(32 * 8, 16);
+  const size_t o_best = take(16 * 8, 16), o_misc = take(32, 16);
+  (void)n_tasks;
+  if (s) {
+    s->lh = base + o_lh;
+    s->ring = base + o_ring;
+    s->bt = base + o_bt;
+    s->a2 = base + o_a2;
+    s->alpha_s = reinterpret_cast<float*>(base + o_al);
+    s->ttask = reinterpret_cast<int32_t*>(base + o_tt);
+    s->z_s = reinterpret_cast<float*>(base + o_z);
+    s->mc_tab = reinterpret_cast<float*>(base + o_mc);
+    s->tcov = reinterpret_cast<float*>(base + o_tc);
+    s->meanc = reinterpret_cast<float*>(base + o_mcn);
+    s->cscale_s = reinterpret_cast<float*>(base + o_cs);
+    s->cshift_s = reinterpret_cast<float*>(base + o_sh);
+    s->an_part = reinterpret_cast<float*>(base + o_an);
+    s->mean_part = reinterpret_cast<float*>(base + o_mp);
+    s->var_part = reinterpret_cast<float*>(base + o_vp);
+    s->cand_task = reinterpret_cast<int32_t*>(base + o_ct);
+    uint64_t* b = reinterpret_cast<uint64_t*>(base + o_bar);
+    s->a_full = b;          // [4]
+    s->vsub_full = b + 4;   // [4]
+    s->r_full = b + 8;      // [kTsLoStages]
+    s->r_empty = b + 12;    // [kTsLoStages]
+    s->d2_full = b + 16;
+    s->a2_full = b + 17;
+    s->v_empty = b + 18;
+    s->res_full = b + 19;
+    s->best_red = reinterpret_cast<long long*>(base + o_best);
+    s->tmem_ptr = reinterpret_cast<uint32_t*>(base + o_misc);
+    s->zstat = reinterpret_cast<float*>(base + o_misc + 8);
+  }
+  return off;
+}
+
+// ---- PTX used only here ------------------------------------------------------------------------------------
+// D[tmem] (+)= A[tmem] * B[smem]^T: A = 128 lanes x 8 columns of packed fp16 pairs (16 K values) per instruction.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 8 consecutive 32-bit columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {  // cvt.rn.f16x2.f32: first source -> upper half
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float h_lo_f32(uint32_t h2) {
+  float f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f) : "r"(h2));
+  return f;
+}
+__device__ __forceinline__ float h_hi_f32(uint32_t h2) {
+  float f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(h2));
+  return f;
+}
+__device__ __forceinline__ void bar_quarter_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_quarter_arrive(int id) { asm volatile("bar.arrive %0, 128;" ::"r"(id) : "memory"); }
+
+struct TsStageRegs {
+  float4 v[2];
+};
+
+__device__ __forceinline__ float4 ts_load_quad(const FusedParams& p, int64_t row, int jq) {
+  const int j0 = jq * 4;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row >= p.N || j0 >= p.d) return q;
+  switch (p.layout) {
+    case BB_ROW_MAJOR_F32: {
+      const float* ptr = reinterpret_cast<const float*>(p.x) + row * p.ldx + j0;
+      if (j0 + 3 < p.d && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)) return __ldg(reinterpret_cast<const float4*>(ptr));
+      q.x = __ldg(ptr);
+      if (j0 + 1 < p.d) q.y = __ldg(ptr + 1);
+      if (j0 + 2 < p.d) q.z = __ldg(ptr + 2);
+      if (j0 + 3 < p.d) q.w = __ldg(ptr + 3);
+      return q;
+    }
+    case BB_COL_MAJOR_F32:
+      q.x = load_x<BB_COL_MAJOR_F32>(p.x, row, j0, p.ldx);
+      if (j0 + 1 < p.d) q.y = load_x<BB_COL_MAJOR_F32>(p.x, row, j0 + 1, p.ldx);
+      if (j0 + 2 < p.d) q.z = load_x<BB_COL_MAJOR_F32>(p.x, row, j0 + 2, p.ldx);
+      if (j0 + 3 < p.d) q.w = load_x<BB_COL_MAJOR_F32>(p.x, row, j0 + 3, p.ldx);
+      return q;
+    case BB_ROW_MAJOR_F64:
+      q.x = load_x<BB_ROW_MAJOR_F64>(p.x, row, j0, p.ldx);
+      if (j0 + 1 < p.d) q.y = load_x<BB_ROW_MAJOR_F64>(p.x, row, j0 + 1, p.ldx);
+      if (j0 + 2 < p.d) q.z = load_x<BB_ROW_MAJOR_F64>(p.x, row, j0 + 2, p.ldx);
+      if (j0 + 3 < p.d) q.w = load_x<BB_ROW_MAJOR_F64>(p.x, row, j0 + 3, p.ldx);
+      return q;
+    default:
+      q.x = load_x<BB_COL_MAJOR_F64>(p.x, row, j0, p.ldx);
+      if (j0 + 1 < p.d) q.y = load_x<BB_COL_MAJOR_F64>(p.x, row, j0 + 1, p.ldx);
+      if (j0 + 2 < p.d) q.z = load_x<BB_COL_MAJOR_F64>(p.x, row, j0 + 2, p.ldx);
+      if (j0 + 3 < p.d) q.w = load_x<BB_COL_MAJOR_F64>(p.x, row, j0 + 3, p.ldx);
+      return q;
+  }
+}
+
+// Sixteen kernel values (scaled by ts_kscale) from sixteen accumulator values D = t / g, two at a time in packed
+// f32x2 arithmetic.  Matern-5/2: k = (1 + s + t/3) e^-s, s = sqrt(t) = sqrt(g) sqrt(D); Matern-3/2: (1 + s) e^-s;
+// RBF: 2^-t (the family constants 5 / 3 / log2(e)/2 are folded into the lengthscales by bb_model_build).
+struct TsConsts {
+  unsigned long long k0, c1, c2, c3;  // packed pairs: ks, ks*sqrt(g), ks*g/3, -log2(e)*sqrt(g) (RBF: c3 = -g)
+};
+
+template <int FAMILY>
+__device__ __forceinline__ unsigned long long ts_kernel_pair(float d0, float d1, const TsConsts& cst) {
+  d0 = fmaxf(d0, 0.f);
+  d1 = fmaxf(d1, 0.f);
+  if constexpr (FAMILY == BB_KERNEL_RBF) {
+    const unsigned long long ea = mul2(pack2(d0, d1), cst.c3);
+    return mul2(pack2(fast_ex2(lo_of(ea)), fast_ex2(hi_of(ea))), cst.k0);
+  } else {
+    const unsigned long long q = pack2(fast_sqrt(d0), fast_sqrt(d1));
+    const unsigned long long ea = mul2(q, cst.c3);
+    unsigned long long poly = fma2(q, cst.c1, cst.k0);
+    if constexpr (FAMILY == BB_KERNEL_MATERN52) poly = fma2(pack2(d0, d1), cst.c2, poly);
+    return mul2(poly, pack2(fast_ex2(lo_of(ea)), fast_ex2(hi_of(ea))));
+  }
+}
+
+template <int FAMILY, bool TASKS>
+__global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TsSmem s;
+  ts_carve(smem_raw, p.n_pad, p.n_tasks, &s);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = p.n_chunks;
+  const uint32_t hi_bytes = ts_hi_bytes(p.n_pad);
+  const uint32_t bt_split = (uint32_t)p.n_pad * kTsK2 * 2u;
+  if (tid == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
+
+  // ---- one-time setup ----
+  if (warp == kWarpMma && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s.a_full[i], kComputeWarps);
+      mbar_init(&s.vsub_full[i], 1);
+    }
+    for (int i = 0; i < kTsLoStages; ++i) {
+      mbar_init(&s.r_full[i], 1);
+      mbar_init(&s.r_empty[i], 1);
+    }
+    mbar_init(s.d2_full, 1);
+    mbar_init(s.a2_full, kComputeWarps);
+    mbar_init(s.v_empty, kComputeWarps);
+    mbar_init(s.res_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kWarpProducer) {
+    tmem_alloc(s.tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  for (int e = tid; e < (int)(3 * kTsA2Split / 16); e += kFusedThreads)  // unused K columns stay zero for good
+    reinterpret_cast<uint4*>(s.a2)[e] = make_uint4(0u, 0u, 0u, 0u);
+  for (int e = tid; e < 32; e += kFusedThreads) {
+    s.cscale_s[e] = e < p.d_pad ? __ldg(p.cand_scale + e) : 0.f;
+    s.cshift_s[e] = e < p.d_pad ? __ldg(p.cand_shift + e) : 0.f;
+  }
+  for (int e = tid; e < p.n_pad; e += kFusedThreads) {
+    s.alpha_s[e] = __ldg(p.ts_alpha + e);
+    s.ttask[e] = TASKS ? __ldg(p.train_task + e) : 0;
+  }
+  for (int e = tid; e < p.n_tasks * p.n_tasks; e += kFusedThreads) s.tcov[e] = __ldg(p.task_covar + e);
+  for (int e = tid; e < p.n_tasks; e += kFusedThreads) s.meanc[e] = __ldg(p.mean_const + e);
+  for (int e = tid; e < 2 * kTileM; e += kFusedThreads) s.cand_task[e] = 0;
+  if (p.has_acq && p.z != nullptr)
+    for (int e = tid; e < p.S; e += kFusedThreads) s.z_s[e] = __ldg(p.z + e);
+  fence_proxy_async();  // the zero-filled A2 tile is read by the tensor-core (async) proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_ptr;
+  if (p.has_acq && warp == 0) {
+    float sz = 0.f, sa = 0.f;
+    for (int e = lane; e < p.S; e += 32) sz += s.z_s[e];
+    for (int o = 16; o > 0; o >>= 1) sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    const float zm = sz / (float)p.S;
+    for (int e = lane; e < p.S; e += 32) sa += fabsf(s.z_s[e] - zm);  // qUCB: deviations from the SAMPLE mean
+    for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    if (lane == 0) {
+      s.zstat[0] = zm;
+      s.zstat[1] = sa / (float)p.S;
+    }
+  }
+  const bool fast_mc = mc_table_applicable(p.has_acq, p.acq, p.S);
+  if (fast_mc) mc_table_setup(s.mc_tab, s.z_s, p.S, p.acq.obj_scale < 0.f ? -1.f : 1.f);  // contains __syncthreads
+  else __syncthreads();                                                                  // zstat visible to everyone
+
+  if (warp < kComputeWarps) {
+    // =====================================================================================================
+    // compute warps.  Conversion / epilogue: thread = TMEM lane (candidate row_e of the tile) x column group cg
+    // (16 of the 64 columns of a chunk).  Acquisition: warp (quarter q, cg) takes rows 32q + 8cg .. +7, four
+    // lanes per row.
+    // =====================================================================================================
+    const int row_e = tid & 127, cg = tid >> 7, quarter = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int dq = p.d_pad >> 2;
+    TsConsts cst;
+    {
+      // without a task kernel the prior scale (ScaleKernel) is one constant: folded into the polynomial
+      const float g = p.ts_g, ks = p.ts_kscale * ((!TASKS && p.scaled) ? s.tcov[0] : 1.0f), sg = sqrtf(g);
+      cst.k0 = pack2(ks, ks);
+      cst.c1 = pack2(ks * sg, ks * sg);
+      cst.c2 = pack2(ks * g * (1.0f / 3.0f), ks * g * (1.0f / 3.0f));
+      const float c3 = (FAMILY == BB_KERNEL_RBF) ? -g : -kLog2e * sg;
+      cst.c3 = pack2(c3, c3);
+    }
+    const float inv_v_scale2 = p.inv_r_scale2 / (p.ts_kscale * p.ts_kscale);
+    long long best = kEmptyKey;
+    TsStageRegs regs;
+
+    auto prefetch = [&](int tile) {
+      const int64_t row = (int64_t)tile * kTileM + row_e;
+      regs.v[0] = (cg < dq) ? ts_load_quad(p, row, cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+      regs.v[1] = (cg + 4 < dq) ? ts_load_quad(p, row, cg + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // scaled candidate rows -> fp16 hi/mid/lo A2 panels; the thread that owns quad 7 appends |a|^2 P and P1
+    auto stage_a2 = [&](int buf) {
+      float an = 0.f;
+      float a7[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int jq = cg + 4 * u;
+        if (jq < dq) {
+          const int j0 = jq * 4;
+          const float4 q = regs.v[u];
+          if (TASKS && p.task_col >= j0 && p.task_col < j0 + 4) {
+            const float tv = (p.task_col == j0) ? q.x : (p.task_col == j0 + 1) ? q.y : (p.task_col == j0 + 2) ? q.z : q.w;
+            s.cand_task[buf * kTileM + row_e] = min(max(__float2int_rn(tv), 0), p.n_tasks - 1);
+          }
+          float a[4];
+          a[0] = fmaf(q.x, s.cscale_s[j0], s.cshift_s[j0]);
+          a[1] = fmaf(q.y, s.cscale_s[j0 + 1], s.cshift_s[j0 + 1]);
+          a[2] = fmaf(q.z, s.cscale_s[j0 + 2], s.cshift_s[j0 + 2]);
+          a[3] = fmaf(q.w, s.cscale_s[j0 + 3], s.cshift_s[j0 + 3]);
+          an = fmaf(a[0], a[0], fmaf(a[1], a[1], fmaf(a[2], a[2], fmaf(a[3], a[3], an))));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a[e] *= p.ts_sa;  // exact: power of two
+          if (jq == 7) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a7[e] = a[e];
+          } else {
+            uint2 hi, mid, lo;
+            split3_quad(a, hi, mid, lo);
+            const uint32_t off = swk_offset<kTsK2>((uint32_t)row_e, (uint32_t)(jq >> 1)) + (uint32_t)(jq & 1) * 8u;
+            *reinterpret_cast<uint2*>(s.a2 + off) = hi;
+            *reinterpret_cast<uint2*>(s.a2 + kTsA2Split + off) = mid;
+            *reinterpret_cast<uint2*>(s.a2 + 2 * kTsA2Split + off) = lo;
+          }
+        }
+      }
+      s.an_part[cg * kTileM + row_e] = an;
+      if (cg != 3) {
+        bar_quarter_arrive(2 + quarter);
+      } else {
+        bar_quarter_sync(2 + quarter);  // the four |a|^2 partials of this thread's row are in shared memory
+        const float asq = (s.an_part[row_e] + s.an_part[kTileM + row_e]) +
+                          (s.an_part[2 * kTileM + row_e] + s.an_part[3 * kTileM + row_e]);
+        a7[kTsColSq - 28] = asq * p.ts_aug_sq;
+        a7[kTsColOne - 28] = p.ts_aug_one;
+        uint2 hi, mid, lo;
+        split3_quad(a7, hi, mid, lo);
+        const uint32_t off = swk_offset<kTsK2>((uint32_t)row_e, 3u) + 8u;
+        *reinterpret_cast<uint2*>(s.a2 + off) = hi;
+        *reinterpret_cast<uint2*>(s.a2 + kTsA2Split + off) = mid;
+        *reinterpret_cast<uint2*>(s.a2 + 2 * kTsA2Split + off) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s.a2_full);
+    };
+
+    const bool is_mc = p.has_acq && p.acq.kind <= BB_ACQ_QPI;
+    int it = 0;
+    int tile = blockIdx.x;
+    if (tile < p.num_tiles) {
+      prefetch(tile);
+      stage_a2(0);
+      if (tile + (int)gridDim.x < p.num_tiles) prefetch(tile + gridDim.x);
+    }
+    for (; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t par = (uint32_t)(it & 1);
+      const int64_t row0 = (int64_t)tile * kTileM;
+      // ---- K* chunk by chunk: D2 (TMEM) -> kernel values -> fp16 hi/lo, written over the same TMEM columns ----
+      mbar_wait(s.d2_full, par);
+      tc_fence_after();
+      const int ct = TASKS ? s.cand_task[buf * kTileM + row_e] : 0;
+      const float* tcrow = s.tcov + ct * p.n_tasks;
+      unsigned long long mean2 = 0ull;
+      for (int c = 0; c < C; ++c) {
+        float v[16];
+        const uint32_t col = kTsD2Col0 + (uint32_t)(c * kChunk + cg * 16);
+        tmem_ld16(tmem_base + lane_base + col, v);
+        tmem_ld_wait();
+        const int i0 = c * kChunk + cg * 16;
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          unsigned long long k2 = ts_kernel_pair<FAMILY>(v[2 * e], v[2 * e + 1], cst);
+          if constexpr (TASKS) k2 = mul2(k2, pack2(tcrow[s.ttask[i0 + 2 * e]], tcrow[s.ttask[i0 + 2 * e + 1]]));
+          const float2 al = *reinterpret_cast<const float2*>(s.alpha_s + i0 + 2 * e);
+          mean2 = fma2(k2, pack2(al.x, al.y), mean2);
+          const uint32_t h = pack_h2(lo_of(k2), hi_of(k2));
+          const unsigned long long r2 = fma2(pack2(h_lo_f32(h), h_hi_f32(h)), pack2(-1.0f, -1.0f), k2);  // exact
+          hi[e] = h;
+          lo[e] = pack_h2(lo_of(r2), hi_of(r2));
+        }
+        tmem_st8(tmem_base + lane_base + col, hi);
+        tmem_st8(tmem_base + lane_base + col + 8u, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.a_full[c]);
+      }
+      s.mean_part[(buf * 4 + cg) * kTileM + row_e] = lo_of(mean2) + hi_of(mean2);
+
+      // ---- stage the next tile's A2 (this tile's distance GEMM has completed: d2_full) ----
+      const int next = tile + (int)gridDim.x;
+      if (next < p.num_tiles) {
+        stage_a2(buf ^ 1);
+        if (next + (int)gridDim.x < p.num_tiles) prefetch(next + gridDim.x);
+      }
+
+      // ---- |V|^2: the 64 columns of sub-block c are final once chunk c's MMAs have completed ----
+      {
+        unsigned long long ss2 = 0ull;
+        for (int sb = 0; sb < C; ++sb) {
+          float v[16];
+          mbar_wait(&s.vsub_full[sb], par);
+          tc_fence_after();
+          tmem_ld16(tmem_base + lane_base + (uint32_t)(sb * kChunk + cg * 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const unsigned long long vv = pack2(v[2 * e], v[2 * e + 1]);
+            ss2 = fma2(vv, vv, ss2);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s.v_empty);
+        s.var_part[(buf * 4 + cg) * kTileM + row_e] = lo_of(ss2) + hi_of(ss2);
+      }
+      bar_quarter_sync(6 + quarter);
+
+      // ---- moments + acquisition: rows 32q + 8cg + (lane >> 2), four lanes per row ----
+      {
+        const int sub = lane & 3;
+        const int r = quarter * 32 + cg * 8 + (lane >> 2);
+        float mp = s.mean_part[(buf * 4 + sub) * kTileM + r];
+        float vp = s.var_part[(buf * 4 + sub) * kTileM + r];
+        mp += __shfl_xor_sync(0xffffffffu, mp, 1);
+        vp += __shfl_xor_sync(0xffffffffu, vp, 1);
+        mp += __shfl_xor_sync(0xffffffffu, mp, 2);
+        vp += __shfl_xor_sync(0xffffffffu, vp, 2);
+        const int ctr = TASKS ? s.cand_task[buf * kTileM + r] : 0;
+        const float kss = (TASKS || p.scaled) ? s.tcov[ctr * p.n_tasks + ctr] : 1.0f;
+        const float var_t = fmaxf(kss - vp * inv_v_scale2, 1e-10f);
+        const float mu = fmaf(p.y_std, s.meanc[ctr] + mp, p.y_mean);
+        const float var = p.y_std * p.y_std * var_t;
+        const int64_t row = row0 + r;
+        const bool live = row < p.N;
+        if (sub == 0 && live) {
+          if (p.mu) p.mu[row] = mu;
+          if (p.var) p.var[row] = var;
+        }
+        if (p.has_acq) {
+          float score = 0.f;
+          if (is_mc) {
+            float c0, c1, s0 = 0.f, s1 = 0.f;
+            mc_coef(p.acq, mu, var, c0, c1);
+            if (fast_mc) {
+              const bool fast = mc_row_fast_part(s.mc_tab, c0, c1, sub, s0, s1);
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+              // rows outside the tabulated envelope: exact sum over all S samples, the whole warp per row
+              unsigned need = __ballot_sync(0xffffffffu, !fast && sub == 0);
+              while (need != 0u) {
+                const int b = __ffs(need) - 1;
+                need &= need - 1u;
+                const float e0 = __shfl_sync(0xffffffffu, c0, b), e1 = __shfl_sync(0xffffffffu, c1, b);
+                float a0, a1;
+                mc_row_exact_warp(s.z_s, p.S, e0, e1, lane, a0, a1);
+                if ((lane >> 2) == (b >> 2)) {
+                  s0 = a0;
+                  s1 = a1;
+                }
+              }
+            } else if (p.acq.kind != BB_ACQ_QUCB && p.acq.kind != BB_ACQ_QSR) {
+              const int per = p.S >> 2;  // S is a multiple of 16
+              mc_accumulate(p.acq.kind, c0, c1, reinterpret_cast<const float4*>(s.z_s + sub * per), per >> 2, s0, s1);
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            }
+            score = mc_finalize(p.acq, mu, var, s0, s1, p.S, s.zstat[0], s.zstat[1]);
+          } else if (sub == 0) {
+            score = analytic_value(p.acq, mu, var);
+          }
+          if (sub == 0 && live) {
+            if (p.score) p.score[row] = score;
+            const bool ok = (p.keep == nullptr || p.keep[row] != 0) && !(score != score);
+            if (ok) {
+              const long long key = pack_key(score, (uint32_t)(row + p.index_offset));
+              best = key > best ? key : best;
+            }
+          }
+        }
+      }
+    }
+    if (p.best_key != nullptr && p.has_acq) {
+      for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+      }
+      if (lane == 0) s.best_red[warp] = best;
+      bar_compute();
+      if (tid == 0) {
+        long long b = s.best_red[0];
+        for (int w = 1; w < kComputeWarps; ++w) b = s.best_red[w] > b ? s.best_red[w] : b;
+        if (b != kEmptyKey) atomicMax(p.best_key, b);
+      }
+    }
+  } else if (warp == kWarpProducer) {
+    // =====================================================================================================
+    // producer (TMA engine): resident images once, then the lo image of L^-1 piece by piece for every tile
+    // =====================================================================================================
+    if (elect_one()) {
+      uint32_t left = hi_bytes;
+      mbar_expect_tx(s.res_full, hi_bytes + 3u * bt_split);
+      for (uint32_t o = 0; left > 0;) {
+        const uint32_t n = left < 32768u ? left : 32768u;
+        bulk_g2s(s.lh + o, p.timg_l + o, n, s.res_full);
+        o += n;
+        left -= n;
+      }
+      left = 3u * bt_split;
+      for (uint32_t o = 0; left > 0;) {
+        const uint32_t n = left < 32768u ? left : 32768u;
+        bulk_g2s(s.bt + o, p.timg_b + o, n, s.res_full);
+        o += n;
+        left -= n;
+      }
+      uint32_t rs = 0, rph = 0;
+      const uint8_t* lo_img = p.timg_l + hi_bytes;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        uint32_t off = 0;
+        for (int c = 0; c < C; ++c) {
+          const int rows_c = p.n_pad - c * kChunk;
+          for (int r0 = 0; r0 < rows_c; r0 += 128) {
+            const uint32_t bytes = (uint32_t)(rows_c - r0 < 128 ? rows_c - r0 : 128) * 128u;
+            mbar_wait_relaxed(&s.r_empty[rs], rph ^ 1u);
+            mbar_expect_tx(&s.r_full[rs], bytes);
+            bulk_g2s(s.ring + (size_t)rs * kTsLoStage, lo_img + off + (uint32_t)r0 * 128u, bytes, &s.r_full[rs]);
+            if (++rs == (uint32_t)kTsLoStages) {
+              rs = 0;
+              rph ^= 1u;
+            }
+          }
+          off += (uint32_t)rows_c * 128u;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =====================================================================================================
+    // MMA issuer: the whole warp runs the loop (converged), one elected lane issues
+    // =====================================================================================================
+    const uint32_t idesc_d2 = make_idesc_f16(kTileM, p.n_pad);
+    const uint32_t a2_addr = smem_u32(s.a2), bt_addr = smem_u32(s.bt), lh_addr = smem_u32(s.lh);
+    const uint64_t a2_h = make_swk_desc<kTsK2>(a2_addr), a2_m = make_swk_desc<kTsK2>(a2_addr + kTsA2Split),
+                   a2_l = make_swk_desc<kTsK2>(a2_addr + 2 * kTsA2Split);
+    const uint64_t b_h = make_swk_desc<kTsK2>(bt_addr), b_m = make_swk_desc<kTsK2>(bt_addr + bt_split),
+                   b_l = make_swk_desc<kTsK2>(bt_addr + 2 * bt_split);
+    const uint32_t d2_addr = tmem_base + kTsD2Col0;
+    // distance GEMM of one tile: D2 = A2 * Bt^T, six split products (2^-33), one MMA spans all training columns
+    auto issue_distance = [&](uint32_t a2_parity) {
+      mbar_wait_relaxed(s.a2_full, a2_parity);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kTsK2 / 16; ++kk) {
+          const uint64_t ko = (uint64_t)(kk * 2);
+          umma_f16(d2_addr, a2_h + ko, b_h + ko, idesc_d2, kk > 0 ? 1u : 0u);
+          umma_f16(d2_addr, a2_h + ko, b_m + ko, idesc_d2, 1u);
+          umma_f16(d2_addr, a2_m + ko, b_h + ko, idesc_d2, 1u);
+          umma_f16(d2_addr, a2_h + ko, b_l + ko, idesc_d2, 1u);
+          umma_f16(d2_addr, a2_l + ko, b_h + ko, idesc_d2, 1u);
+          umma_f16(d2_addr, a2_m + ko, b_m + ko, idesc_d2, 1u);
+        }
+        umma_commit(s.d2_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait_relaxed(s.res_full, 0u);
+    uint32_t rs = 0, rph = 0;
+    int j = 0;
+    int tile = blockIdx.x;
+    if (tile < p.num_tiles) issue_distance(0u);
+    for (; tile < p.num_tiles; tile += gridDim.x, ++j) {
+      const uint32_t par = (uint32_t)(j & 1);
+      if (j > 0) mbar_wait_relaxed(s.v_empty, par ^ 1u);  // the previous tile's |V|^2 has been read
+      tc_fence_after();
+      uint32_t hi_off = 0;
+      for (int c = 0; c < C; ++c) {
+        const int rows_c = p.n_pad - c * kChunk;
+        mbar_wait_relaxed(&s.a_full[c], par);
+        tc_fence_after();
+        const uint32_t a_col = d2_addr + (uint32_t)(c * kChunk);
+        if (elect_one()) {
+          // resident hi image: K*hi x Lhi, K*lo x Lhi; K step kk only reaches columns >= 64c + 16kk
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t n_cols = (uint32_t)(rows_c - 16 * kk);
+            const uint64_t bd = make_sw128_desc(lh_addr + hi_off + (uint32_t)kk * 2048u) + (uint64_t)(kk * 2);
+            const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + 16 * kk);
+            const uint32_t id = make_idesc_f16(kTileM, (int)n_cols);
+            umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, id, (c > 0 || kk > 0) ? 1u : 0u);
+            umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk + 8), bd, id, 1u);
+          }
+        }
+        __syncwarp();
+        // streamed lo image: K*hi x Llo, pieces of <= 128 rows
+        for (int r0 = 0; r0 < rows_c; r0 += 128) {
+          const int rows_p = rows_c - r0 < 128 ? rows_c - r0 : 128;
+          mbar_wait_relaxed(&s.r_full[rs], rph);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(s.ring + (size_t)rs * kTsLoStage);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const int skip = (r0 == 0) ? 16 * kk : 0;  // rows of this piece the K step cannot reach
+              const uint32_t n_cols = (uint32_t)(rows_p - skip);
+              const uint64_t bd = make_sw128_desc(b_addr + (uint32_t)skip * 128u) + (uint64_t)(kk * 2);
+              const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + r0 + skip);
+              umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, make_idesc_f16(kTileM, (int)n_cols), 1u);
+            }
+            umma_commit(&s.r_empty[rs]);
+          }
+          __syncwarp();
+          if (++rs == (uint32_t)kTsLoStages) {
+            rs = 0;
+            rph ^= 1u;
+          }
+        }
+        if (elect_one()) umma_commit(&s.vsub_full[c]);  // sub-block c of V has received its last contribution
+        __syncwarp();
+        hi_off += (uint32_t)rows_c * 128u;
+      }
+      if (tile + (int)gridDim.x < p.num_tiles) issue_distance(par ^ 1u);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpProducer) tmem_dealloc(tmem_base, 512);
+}
+
+// Shape envelope of this kernel; everything else runs fused_tc.cu / fused.cu.
+bool fused_ts_supported(const FusedParams& p, int max_smem) {
+  if (p.timg_l == nullptr || p.timg_b == nullptr || p.ts_alpha == nullptr) return false;
+  if (p.n_pad > 256 || p.d > kTsColSq || p.family == BB_KERNEL_MATERN12) return false;
+  if (p.has_acq && (p.S > 512 || (p.S & 15) != 0)) return false;
+  if (p.n_tasks > kMaxTasks) return false;
+  return ts_carve(nullptr, p.n_pad, p.n_tasks, nullptr) + 1024 <= (size_t)max_smem;
+}
+
+template <int FAMILY, bool TASKS>
+static int launch_ts_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
+  static int configured_for = -1;  // cudaFuncSetAttribute once per device, not per launch
+  int dev = 0;
+  BB_CUDA(cudaGetDevice(&dev));
+  if (configured_for != dev) {
+    BB_CUDA(cudaFuncSetAttribute(k_fused_ts<FAMILY, TASKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured_for = dev;
+  }
+  k_fused_ts<FAMILY, TASKS><<<grid, kFusedThreads, smem, stream>>>(p);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int launch_fused_ts(FusedParams& p, int grid, cudaStream_t stream) {
+  const size_t smem = ts_carve(nullptr, p.n_pad, p.n_tasks, nullptr) + 1024;
+  const bool tasks = p.task_col >= 0;
+  switch (p.family) {
+    case BB_KERNEL_MATERN32:
+      return tasks ? launch_ts_one<BB_KERNEL_MATERN32, true>(p, grid, smem, stream)
+                   : launch_ts_one<BB_KERNEL_MATERN32, false>(p, grid, smem, stream);
+    case BB_KERNEL_MATERN52:
+      return tasks ? launch_ts_one<BB_KERNEL_MATERN52, true>(p, grid, smem, stream)
+                   : launch_ts_one<BB_KERNEL_MATERN52, false>(p, grid, smem, stream);
+    default:
+      return tasks ? launch_ts_one<BB_KERNEL_RBF, true>(p, grid, smem, stream)
+                   : launch_ts_one<BB_KERNEL_RBF, false>(p, grid, smem, stream);
+  }
+}
+
+}  // namespace bb

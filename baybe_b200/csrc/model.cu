@@ -31,7 +31,8 @@ const char* last_error() { return g_err; }
 struct BlobLayout {
   size_t cand_scale, cand_shift, train_m2, train_sq, alpha, train_task, task_covar, mean_const,
       rimg, linv, alpha64, xn64, linv32, kmat, resid, noise_row, tcov64, cnorm, pend_norm, pend_w64, bimg, rimg2, flags,
-      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, rimg2g, pend_img, pend_norm2, pend_task, kpend_ws, vacc, mc_table, total;
+      wimg, wimg_bits, wnorm_bits, wsrc, wide_ws, rimg4, rimg2g, pend_img, pend_norm2, pend_task, kpend_ws, vacc, mc_table, timg_l, timg_b, ts_alpha, total;
+  int ts;  // operand images of fused_ts.cu present (n_pad <= 256, d <= 30)
   int n_pad, d_pad, n_chunks, n_tiles;
   int wide, d_wide;
   int64_t wide_ws_rows;
@@ -100,6 +101,16 @@ static BlobLayout make_layout(int n, int d, int T) {
     L.kpend_ws = take(sizeof(float) * (size_t)L.wide_ws_rows * 64);
     L.vacc = take(sizeof(float) * (size_t)L.wide_ws_rows);
     L.mc_table = take(sizeof(float) * 1024);
+  }
+  // fused_ts.cu: hi/lo images of L^-1 in per-chunk tiles of (n_pad - 64c) rows, augmented training-row image
+  L.ts = (L.n_pad <= 256 && d <= 30) ? 1 : 0;
+  L.timg_l = L.timg_b = L.ts_alpha = 0;
+  if (L.ts) {
+    size_t tile_bytes = 0;
+    for (int r = L.n_pad; r > 0; r -= kChunk) tile_bytes += (size_t)r * 128;
+    L.timg_l = take(2 * tile_bytes);
+    L.timg_b = take((size_t)3 * L.n_pad * 64);
+    L.ts_alpha = take(sizeof(float) * L.n_pad);
   }
   L.total = off;
   return L;
@@ -458,6 +469,58 @@ __global__ void k_build_bimg(const float* __restrict__ train_m2, int n_pad, int 
   }
 }
 
+// Operand images of fused_ts.cu.
+// (a) L^-1: for K chunk c one tile of R_c = n_pad - 64c rows (output columns j = 64c + r) x 64 k (training
+//     points i = 64c + kk), K-major, SWIZZLE_128B; all hi tiles first (resident in shared memory), then all lo tiles
+//     (streamed).  B[r][kk] = scale * Linv[j][i], zero above the diagonal.  One block per (chunk, 64-row group).
+__global__ void k_build_timg_l(const double* __restrict__ Linv, int n, int n_pad, double scale,
+                               uint8_t* __restrict__ img, uint32_t hi_total) {
+  int c = 0, grp = blockIdx.x;
+  uint32_t off = 0;
+  while (grp >= (n_pad - c * kChunk) / kChunk) {
+    grp -= (n_pad - c * kChunk) / kChunk;
+    off += (uint32_t)(n_pad - c * kChunk) * 128u;
+    ++c;
+  }
+  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    const int r = grp * 64 + (e >> 6), kk = e & 63;
+    const int j = c * kChunk + r, i = c * kChunk + kk;
+    const double v = (j < n && i < n && i <= j) ? Linv[(size_t)j * n + i] * scale : 0.0;
+    const __half hi = __float2half_rn((float)v);
+    const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+    const uint32_t o = off + sw128_offset((uint32_t)r, (uint32_t)(kk >> 3)) + (uint32_t)(kk & 7) * 2u;
+    *reinterpret_cast<__half*>(img + o) = hi;
+    *reinterpret_cast<__half*>(img + hi_total + o) = lo;
+  }
+}
+// (b) training rows: three panels [hi | mid | lo] of [n_pad rows][32 k] fp16 (64-byte rows, SWIZZLE_64B):
+//     k < d: scale_b * (-2 b_ij); k = 30: q_one (pairs with |a|^2 * P in the candidate tile); k = 31: |b_i|^2 * q_sq
+//     (pairs with P1).  Rows i >= n are zero.
+__global__ void k_build_timg_b(const float* __restrict__ train_m2, const float* __restrict__ train_sq, int n, int n_pad,
+                               int d, int d_pad, float scale_b, float q_one, float q_sq, uint8_t* __restrict__ img) {
+  const uint32_t split = (uint32_t)n_pad * 64u;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_pad * 32; e += gridDim.x * blockDim.x) {
+    const int i = e >> 5, j = e & 31;
+    float v = 0.f;
+    if (i < n) {
+      if (j < d) v = train_m2[(size_t)i * d_pad + j] * scale_b;
+      else if (j == 30) v = q_one;
+      else if (j == 31) v = train_sq[i] * q_sq;
+    }
+    const __half h = __float2half_rn(v);
+    const float r1 = v - __half2float(h);
+    const __half m = __float2half_rn(r1);
+    const __half l = __float2half_rn(r1 - __half2float(m));
+    const uint32_t o = swk_offset<32>((uint32_t)i, (uint32_t)(j >> 3)) + (uint32_t)(j & 7) * 2u;
+    *reinterpret_cast<__half*>(img + o) = h;
+    *reinterpret_cast<__half*>(img + split + o) = m;
+    *reinterpret_cast<__half*>(img + 2 * split + o) = l;
+  }
+}
+__global__ void k_scale_vec(const float* __restrict__ src, int n, float f, float* __restrict__ dst) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) dst[e] = src[e] * f;
+}
+
 // K-chunked fp16 hi/mid/lo image of scale * src[n_pad][d_wide] for wide.cu: per (256-row half,
 // 32-column K stage) `panels` panels [hi | mid (| lo)], each [ncols rows][32 fp16], 64-byte rows,
 // SWIZZLE_64B, 8-row groups contiguous -- one contiguous bulk copy per stage.
@@ -803,6 +866,54 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
     BB_LAUNCH_CHECK();
   }
 
+  // ---- fused_ts.cu operand images and their power-of-two scales ----
+  // A2 = [sa * a | asq * P | P1], Bt = [sb * (-2b) | Q1 | bsq * Q] with sa*sb = P*Q1 = P1*Q = G, so that the
+  // distance GEMM accumulates D = G * (|a|^2 + |b|^2 - 2 a.b) = G * t.  All fp16 operands stay below 2^15.
+  float ts_sa = 0.f, ts_aug_sq = 0.f, ts_aug_one = 0.f, ts_g = 0.f, ts_kscale = 1.f;
+  if (L.ts) {
+    double asq_max = 0.0, bsq_max = 1e-30;
+    for (int j = 0; j < d; ++j) {
+      const double aj = fmax(fabs((double)desc->lower[j] * cscale[j] + cshift[j]),
+                             fabs((double)desc->upper[j] * cscale[j] + cshift[j]));
+      asq_max += aj * aj;
+    }
+    for (int i = 0; i < n; ++i) bsq_max = fmax(bsq_max, (double)tsq[i]);
+    if (!(asq_max > 1e-12)) asq_max = 1.0;
+    const int e_p = (int)floor(log2(30000.0 / asq_max));                 // P  = 2^e_p
+    const int e_q = (int)floor(log2(30000.0 / bsq_max));                 // Q  = 2^e_q
+    const int e_sb = (int)floor(log2(30000.0 / (double)b_abs_max));      // sb = 2^e_sb
+    const int e_sa_max = (int)floor(log2(16000.0 / (double)a_abs_max));  // sa <= 2^e_sa_max
+    int e_g = e_sb + e_sa_max;                                           // G = 2^e_g
+    if (e_g > 15 + e_p) e_g = 15 + e_p;                                  // Q1 = G / P  <= 2^15
+    if (e_g > 15 + e_q) e_g = 15 + e_q;                                  // P1 = G / Q  <= 2^15
+    if (e_g & 1) --e_g;                                                  // sqrt(G) exact
+    ts_sa = ldexpf(1.0f, e_g - e_sb);
+    ts_aug_sq = ldexpf(1.0f, e_p);
+    ts_aug_one = ldexpf(1.0f, e_g - e_q);
+    ts_g = ldexpf(1.0f, -e_g);
+    const float q_one = ldexpf(1.0f, e_g - e_p), q_sq = ldexpf(1.0f, e_q), ts_sb = ldexpf(1.0f, e_sb);
+    // K* scale: largest kernel value (prior scale x task covariance) times ts_kscale stays below 2^15
+    double kmax = 0.0;
+    for (int a = 0; a < T * T; ++a) kmax = fmax(kmax, fabs(aux[a]));
+    if (!(kmax > 0.0)) kmax = 1.0;
+    int e_k = (int)floor(log2(30000.0 / kmax));
+    if (e_k > 10) e_k = 10;
+    ts_kscale = ldexpf(1.0f, e_k);
+    uint32_t hi_total = 0;
+    int n_groups = 0;
+    for (int r = L.n_pad; r > 0; r -= kChunk) {
+      hi_total += (uint32_t)r * 128u;
+      n_groups += r / kChunk;
+    }
+    k_build_timg_l<<<n_groups, 256, 0, stream>>>(dLinv, n, L.n_pad, scale, B + L.timg_l, hi_total);
+    BB_LAUNCH_CHECK();
+    k_build_timg_b<<<32, 256, 0, stream>>>((const float*)(B + L.train_m2), (const float*)(B + L.train_sq), n, L.n_pad, d,
+                                           L.d_pad, ts_sb, q_one, q_sq, B + L.timg_b);
+    BB_LAUNCH_CHECK();
+    k_scale_vec<<<4, 256, 0, stream>>>((const float*)(B + L.alpha), L.n_pad, 1.0f / ts_kscale, (float*)(B + L.ts_alpha));
+    BB_LAUNCH_CHECK();
+  }
+
   float dist_scale_w = 1.0f, dist_scale_p = 1.0f, dist_scale_wp = 1.0f;
   if (L.wide) {
     // pending points lie inside the scaling bounds like candidates: bound their operand magnitudes there
@@ -884,6 +995,16 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
   out->dist_k = dist_k;
   out->d_rimg2 = B + L.rimg2;
   out->d_rimg2g = L.n_chunks > 4 ? B + L.rimg2g : nullptr;
+  if (L.ts) {
+    out->d_timg_l = B + L.timg_l;
+    out->d_timg_b = B + L.timg_b;
+    out->d_ts_alpha = (const float*)(B + L.ts_alpha);
+    out->ts_sa = ts_sa;
+    out->ts_aug_sq = ts_aug_sq;
+    out->ts_aug_one = ts_aug_one;
+    out->ts_g = ts_g;
+    out->ts_kscale = ts_kscale;
+  }
   out->wide = L.wide;
   out->d_wide = L.d_wide;
   if (L.wide) {

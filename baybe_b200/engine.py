@@ -312,6 +312,10 @@ class DeviceGP:
         return torch.ops.baybe_b200.acq_score_joint(mu, var, cross, pmu, pcov, zf,
                                                     _lib.ACQ_KIND[acq.kind], acq.params())
 
+    def argmax(self, scores: torch.Tensor, keep: torch.Tensor | None, index_offset: int = 0) -> torch.Tensor:
+        """Packed (score, lowest global index) key of a score vector (``bb_argmax``)."""
+        return torch.ops.baybe_b200.argmax(scores, keep, int(index_offset))
+
     def best_f(self, acq: AcqConfig) -> float:
         """max_i o(mu(x_i)) over the training inputs (baybe/acquisition/_builder.py:256-265)."""
         mu, _ = self.posterior(torch.from_numpy(self.train_x))

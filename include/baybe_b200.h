@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BB_ABI_VERSION 1
+#define BB_ABI_VERSION 2
 
 typedef enum bb_status {
   BB_OK = 0,
@@ -162,6 +162,17 @@ typedef struct bb_model {
   float dist_scale_wp;
   float* d_mc_table;         /* [1024] per-call qLogEI table of the K*-reading kernel (acq_math.cuh)             */
   float* d_wide_vacc;        /* [wide_ws_rows] |V|^2 partial between the two column-panel passes (n_pad > 512) */
+  /* fused_ts.cu (n_pad <= 256, d <= 30; NULL otherwise): operand images of the kernel that keeps the K* operand
+   * in tensor memory, and the power-of-two scales folded into them */
+  const void* d_timg_l;      /* L^-1: hi tiles (chunk c: n_pad - 64c rows x 64 k, SW128), then the lo tiles        */
+  const void* d_timg_b;      /* training rows [-2b | q | |b|^2 q'] as hi/mid/lo panels of 32 k (SW64)              */
+  const float* d_ts_alpha;   /* [n_pad] alpha / ts_kscale                                                          */
+  float ts_sa;               /* candidate rows are multiplied by ts_sa                                             */
+  float ts_aug_sq;           /* K column 30 of the candidate tile = |a|^2 * ts_aug_sq                              */
+  float ts_aug_one;          /* K column 31 of the candidate tile = ts_aug_one                                     */
+  float ts_g;                /* accumulator * ts_g = scaled squared distance                                       */
+  float ts_kscale;           /* K* is multiplied by ts_kscale before the fp16 hi/lo split                          */
+  int32_t pad3_;
 } bb_model;
 
 /* Acquisition context built by BotorchAcquisitionFunctionBuilder.build

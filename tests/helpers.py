@@ -57,3 +57,74 @@ def score_bounds(om: oracle.GPModel, acq: oracle.AcqSpec, X, z, base_atol: float
             c = oracle.reference_path.acq_from_moments(acq, mu + sm * dmu, v, z)
             dev = torch.maximum(dev, (c - ref).abs())
     return ref, base_atol + base_rtol * ref.abs() + safety * dev
+
+
+# --------------------------------------------------------------------------------------
+# Oracle-backed stand-in for the device engine (CPU tests of the host-side binding only)
+# --------------------------------------------------------------------------------------
+class OracleBackedGP:
+    """Same constructor and methods as ``baybe_b200.engine.DeviceGP``, computed by the float64 oracle on the
+    CPU.  It exists so that the HOST logic around the engine (the BayBE plugin, masks, index plumbing, greedy
+    bookkeeping) can be exercised without a GPU; the numbers of the CUDA path are checked by the ``-m gpu``
+    tests.  Never imported by the product."""
+
+    def __init__(self, train_x, train_y, bounds, family, lengthscale, noise, mean_const=0.0, outputscale=None,
+                 task_col=None, task_covar=None, device=None):
+        import torch
+
+        tx = np.asarray(train_x, dtype=np.float64)
+        ls = np.broadcast_to(np.asarray(lengthscale, dtype=np.float64), (tx.shape[1],))
+        active = [j for j in range(tx.shape[1]) if ls[j] > 0 and j != task_col]
+        spec = oracle.KernelSpec(family=family, lengthscale=ls[active], active_dims=active, outputscale=outputscale,
+                                 task_idx=task_col, task_covar=task_covar)
+        self.om = oracle.build_model(spec, tx, np.asarray(train_y, dtype=np.float64), np.asarray(bounds), noise=noise,
+                                     mean_const=mean_const)
+        self.train_x = tx
+        self.n, self.d = tx.shape
+        self.device = torch.device("cpu")
+
+    @staticmethod
+    def _spec(acq) -> "oracle.AcqSpec":
+        return oracle.AcqSpec(kind=acq.kind, best_f=acq.best_f, beta=acq.beta, obj_scale=acq.obj_scale,
+                              obj_shift=acq.obj_shift, maximize=acq.maximize)
+
+    def close(self):
+        pass
+
+    def prepare(self, x):
+        import torch
+
+        return torch.as_tensor(np.asarray(x, dtype=np.float64))
+
+    def posterior(self, x):
+        mu, var = oracle.posterior(self.om, np.asarray(x, dtype=np.float64))
+        return mu.float(), var.float()
+
+    def best_f(self, acq) -> float:
+        return oracle.best_f_from_training(self.om, self.train_x, self._spec(acq))
+
+    def argmax(self, scores, keep, index_offset=0):
+        import torch
+
+        from baybe_b200.engine import pack_best
+
+        s = scores.double().clone()
+        if keep is not None:
+            s[keep == 0] = float("nan")
+        best = -(1 << 63)
+        ok = ~torch.isnan(s)
+        if bool(ok.any()):
+            m = float(s[ok].max())
+            i = int(torch.nonzero(ok & (s == m))[0])
+            best = pack_best(float(np.float32(m)), i + int(index_offset))
+        return torch.tensor([best], dtype=torch.int64)
+
+    def score(self, acq, x, z, keep=None, index_offset=0, want_scores=True):
+        vals = oracle.acq_values(self.om, self._spec(acq), np.asarray(x, dtype=np.float64),
+                                 None if z is None else z.reshape(-1))
+        scores = vals.float()
+        return (scores if want_scores else None), self.argmax(scores, keep, index_offset)
+
+    def score_joint(self, acq, x, pending, z):
+        return oracle.acq_values_joint(self.om, self._spec(acq), np.asarray(x, dtype=np.float64),
+                                       np.asarray(pending, dtype=np.float64), z).float()
