@@ -77,6 +77,14 @@ class Best(C.Structure):
     _fields_ = [("val", C.c_float), ("pad_", C.c_int32), ("idx", C.c_int64)]
 
 
+MAX_PEERS = 8
+
+
+class PeerGroup(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("d_key", C.c_void_p * MAX_PEERS),
+                ("d_count", C.c_void_p * MAX_PEERS)]
+
+
 class NativeLibraryError(RuntimeError):
     """The CUDA extension is missing or failed to load (there is no CPU fallback)."""
 
@@ -92,6 +100,7 @@ _SIGNATURES = {
     "bb_fit_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "bb_fit_setup": (C.c_int, [_vp, _sz, _i32, _i32, _i32, _dp, _dp, C.POINTER(C.c_int32), _vp]),
     "bb_fit_eval": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _dp, _dp, _dp, C.POINTER(C.c_int32), _vp]),
+    "bb_fit_eval_loo": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _dp, _dp, _dp, C.POINTER(C.c_int32), _vp]),
     "bb_kernel_matrix": (C.c_int, [C.POINTER(Model), _vp, _i32, _i64, _i64, _vp, _i64, _vp]),
     "bb_posterior": (C.c_int, [C.POINTER(Model), _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "bb_pending_stats": (C.c_int, [C.POINTER(Model), _vp, _i32, _vp, _vp, _vp, _vp]),
@@ -102,6 +111,9 @@ _SIGNATURES = {
     "bb_argmax": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "bb_best_decode": (C.c_int, [_vp, _vp, _vp]),
     "bb_topk": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "bb_decode_codes": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
+    "bb_peer_slots_init": (C.c_int, [_vp, _vp, _vp]),
+    "bb_allreduce_best": (C.c_int, [C.POINTER(PeerGroup), _vp, C.c_uint32, _vp, _vp, _vp]),
     "bb_debug_posterior_simt": (C.c_int, [C.POINTER(Model), _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
     "bb_debug_set_trace": (C.c_int, [_vp, _i64]),
 }

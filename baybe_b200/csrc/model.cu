@@ -1067,7 +1067,7 @@ extern "C" int bb_pending_stats(const bb_model* m, const float* d_pend_x, int32_
 namespace {
 
 struct FitLayout {
-  size_t xn, y, task, theta, K, Linv, Kinv, alpha, resid, partial, out, alpha32, flag, total;
+  size_t xn, y, task, theta, K, Linv, Kinv, alpha, resid, partial, out, alpha32, flag, wmat, loovec, total;
   int nblk, np;
 };
 
@@ -1094,6 +1094,8 @@ FitLayout fit_layout(int n, int d, int T) {
   L.out = take(sizeof(double) * (L.np + 1));
   L.alpha32 = take(sizeof(float) * n);
   L.flag = take(64);
+  L.wmat = take(sizeof(double) * (size_t)n * n);   // leave-one-out criterion: 2 dF/dK
+  L.loovec = take(sizeof(double) * 4 * n);          // kappa | w | u | v
   L.total = off;
   return L;
 }
@@ -1159,7 +1161,8 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
 __global__ void __launch_bounds__(256) k_fit_grad(const double* __restrict__ xn, const int32_t* __restrict__ task,
                                                   const double* __restrict__ theta, const double* __restrict__ alpha,
                                                   const double* __restrict__ Kinv, int n, int d, int T, int family,
-                                                  double* __restrict__ partial) {
+                                                  double* __restrict__ partial,
+                                                  const double* __restrict__ wmat) {  // null: exact MLL
   __shared__ double red[256];
   const double* B = theta + d + 2;
   const int np = d + 2 + T * T;
@@ -1175,7 +1178,7 @@ __global__ void __launch_bounds__(256) k_fit_grad(const double* __restrict__ xn,
       const int i = (int)(e / n), k = (int)(e - (size_t)i * n);
       pi[q] = i;
       pk[q] = k;
-      const double W = alpha[i] * alpha[k] - Kinv[e];
+      const double W = wmat != nullptr ? wmat[e] : alpha[i] * alpha[k] - Kinv[e];
       if (i == k) {
         gn += 0.5 * W;
         hb[q] = 0.5 * W;
@@ -1244,6 +1247,60 @@ __global__ void k_fit_final(const double* __restrict__ partial, int nblk, int np
   }
 }
 
+// ---- leave-one-out pseudo-likelihood (gpytorch LeaveOneOutPseudoLikelihood; the reference's criterion for
+// transfer-learning search spaces, presets/baybe.py:270-281, components/fit_criterion.py:22-41) ----
+//   kappa_i = [K^-1]_ii,  sigma_i^2 = 1/kappa_i,  y_i - mu_i = alpha_i / kappa_i
+//   F = sum_i ( 1/2 log kappa_i - 1/2 alpha_i^2 / kappa_i ) - n/2 log 2 pi
+//   dF = 1/2 sum_ab W_ab dK_ab,  W = -2 K^-1 diag(w) K^-1 + v alpha^T + alpha v^T,
+//        w_i = 1/(2 kappa_i) + alpha_i^2 / (2 kappa_i^2),  u_i = alpha_i / kappa_i,  v = K^-1 u;   dF/dc = sum_i v_i
+__global__ void k_loo_prep(const double* __restrict__ Kinv, const double* __restrict__ alpha, int n,
+                           double* __restrict__ vec) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double kap = Kinv[(size_t)i * n + i], a = alpha[i];
+    vec[i] = kap;
+    vec[n + i] = 0.5 / kap + 0.5 * a * a / (kap * kap);
+    vec[2 * n + i] = a / kap;
+  }
+}
+__global__ void k_loo_v(const double* __restrict__ Kinv, int n, double* __restrict__ vec) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int m = 0; m < n; ++m) s += Kinv[(size_t)i * n + m] * vec[2 * n + m];
+    vec[3 * n + i] = s;
+  }
+}
+__global__ void k_loo_wmat(const double* __restrict__ Kinv, const double* __restrict__ alpha,
+                           const double* __restrict__ vec, int n, double* __restrict__ wmat) {
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || k >= n) return;
+  double s = 0.0;
+  for (int m = 0; m < n; ++m) s += Kinv[(size_t)i * n + m] * vec[n + m] * Kinv[(size_t)m * n + k];
+  wmat[(size_t)i * n + k] = -2.0 * s + vec[3 * n + i] * alpha[k] + alpha[i] * vec[3 * n + k];
+}
+__global__ void k_fit_final_loo(const double* __restrict__ partial, int nblk, int np, const double* __restrict__ alpha,
+                                const double* __restrict__ vec, int n, int d, double* __restrict__ out) {
+  __shared__ double red[256];
+  for (int p = threadIdx.x; p < np; p += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * np + p];
+    out[1 + p] = s;
+  }
+  double f = 0.0, sv = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double kap = vec[i], a = alpha[i];
+    f += 0.5 * log(kap) - 0.5 * a * a / kap;
+    sv += vec[3 * n + i];
+  }
+  f = block_sum_256(f, red);
+  sv = block_sum_256(sv, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[0] = f - 0.5 * n * 1.8378770664093453;
+    out[1 + d + 1] = sv;
+  }
+}
+
 }  // namespace
 
 extern "C" size_t bb_fit_workspace_bytes(int32_t n, int32_t d, int32_t n_tasks) {
@@ -1277,10 +1334,8 @@ extern "C" int bb_fit_setup(void* d_ws, size_t ws_bytes, int32_t n, int32_t d, i
   return BB_OK;
 }
 
-// value[0] = mll, grad[np] = d mll / d theta (np = d + 2 + T*T); *not_pd != 0 when K is not positive
-// definite at this theta (value/grad are then unspecified).  Synchronises the stream.
-extern "C" int bb_fit_eval(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, int32_t family,
-                           const double* theta, double* value, double* grad, int32_t* not_pd, void* stream_) {
+static int fit_eval_impl(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, int32_t family, const double* theta,
+                         double* value, double* grad, int32_t* not_pd, void* stream_, bool loo) {
   cudaStream_t stream = (cudaStream_t)stream_;
   BB_CHECK_ARG(d_ws && theta && value && grad && not_pd, "bb_fit_eval: null argument");
   BB_CHECK_ARG(family >= 0 && family <= 3, "bb_fit_eval: unknown kernel family %d", family);
@@ -1304,12 +1359,28 @@ extern "C" int bb_fit_eval(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, in
   BB_LAUNCH_CHECK();
   k_fit_kinv<<<grd, blk, 0, stream>>>(dLinv, n, (double*)(W + L.Kinv));
   BB_LAUNCH_CHECK();
+  const double* wmat = nullptr;
+  if (loo) {
+    double* vec = (double*)(W + L.loovec);
+    k_loo_prep<<<(n + 255) / 256, 256, 0, stream>>>((const double*)(W + L.Kinv), (const double*)(W + L.alpha), n, vec);
+    BB_LAUNCH_CHECK();
+    k_loo_v<<<(n + 63) / 64, 64, 0, stream>>>((const double*)(W + L.Kinv), n, vec);
+    BB_LAUNCH_CHECK();
+    k_loo_wmat<<<grd, blk, 0, stream>>>((const double*)(W + L.Kinv), (const double*)(W + L.alpha), vec, n,
+                                        (double*)(W + L.wmat));
+    BB_LAUNCH_CHECK();
+    wmat = (const double*)(W + L.wmat);
+  }
   k_fit_grad<<<L.nblk, 256, 0, stream>>>((const double*)(W + L.xn), (const int32_t*)(W + L.task), dtheta,
                                          (const double*)(W + L.alpha), (const double*)(W + L.Kinv), n, d, n_tasks,
-                                         family, (double*)(W + L.partial));
+                                         family, (double*)(W + L.partial), wmat);
   BB_LAUNCH_CHECK();
-  k_fit_final<<<1, 256, 0, stream>>>((const double*)(W + L.partial), L.nblk, L.np, dresid,
-                                     (const double*)(W + L.alpha), dLinv, n, d, (double*)(W + L.out));
+  if (loo)
+    k_fit_final_loo<<<1, 256, 0, stream>>>((const double*)(W + L.partial), L.nblk, L.np, (const double*)(W + L.alpha),
+                                           (const double*)(W + L.loovec), n, d, (double*)(W + L.out));
+  else
+    k_fit_final<<<1, 256, 0, stream>>>((const double*)(W + L.partial), L.nblk, L.np, dresid,
+                                       (const double*)(W + L.alpha), dLinv, n, d, (double*)(W + L.out));
   BB_LAUNCH_CHECK();
   std::vector<double> out(L.np + 1);
   int flag = 0;
@@ -1320,4 +1391,18 @@ extern "C" int bb_fit_eval(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, in
   *value = out[0];
   for (int p = 0; p < L.np; ++p) grad[p] = out[1 + p];
   return BB_OK;
+}
+
+// value[0] = mll, grad[np] = d mll / d theta (np = d + 2 + T*T); *not_pd != 0 when K is not positive
+// definite at this theta (value/grad are then unspecified).  Synchronises the stream.
+extern "C" int bb_fit_eval(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, int32_t family,
+                           const double* theta, double* value, double* grad, int32_t* not_pd, void* stream) {
+  return fit_eval_impl(d_ws, n, d, n_tasks, family, theta, value, grad, not_pd, stream, false);
+}
+
+// Same contract for the leave-one-out pseudo-likelihood (the reference's fit criterion when the search space has
+// a task parameter: presets/baybe.py:270-281 -> gpytorch.mlls.LeaveOneOutPseudoLikelihood).
+extern "C" int bb_fit_eval_loo(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, int32_t family,
+                               const double* theta, double* value, double* grad, int32_t* not_pd, void* stream) {
+  return fit_eval_impl(d_ws, n, d, n_tasks, family, theta, value, grad, not_pd, stream, true);
 }

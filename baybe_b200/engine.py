@@ -303,6 +303,77 @@ class DeviceGP:
                 t.record_stream(main)
         return score, key
 
+    def score_coded(self, acq: AcqConfig, codes: torch.Tensor, table, bits: int, z: torch.Tensor | None,
+                    keep: torch.Tensor | None = None, index_offset: int = 0, want_scores: bool = True):
+        """``score`` for a LEVEL-CODED candidate matrix (``baybe_b200.bits.encode_levels``): rows of 4- or 8-bit
+        level indices plus the per-column value table -- the compact, exact form of a discrete search space
+        (d/2 or d bytes per candidate instead of 4d).  `codes` may live in (pinned) host memory: row blocks are
+        copied on a side stream, expanded on the device by ``bb_decode_codes`` and scored, so the end-to-end pass
+        moves 8x / 4x fewer bytes over PCIe than the float32 matrix.  Scores are bit-identical to ``score`` on the
+        decoded float32 matrix."""
+        if bits not in (4, 8):
+            raise ValueError("bits must be 4 or 8")
+        if codes.dtype != torch.uint8 or codes.dim() != 2 or not codes.is_contiguous():
+            raise ValueError("codes must be a contiguous 2-D uint8 tensor")
+        row_bytes = (self.d + 1) // 2 if bits == 4 else self.d
+        if codes.shape[1] != row_bytes:
+            raise ValueError(f"expected {row_bytes} code bytes per row, got {codes.shape[1]}")
+        tab = torch.as_tensor(np.asarray(table, dtype=np.float32) if not torch.is_tensor(table) else table)
+        tab = tab.to(self.device, torch.float32).contiguous()
+        if tab.dim() != 2 or tab.shape[0] != self.d or tab.shape[1] > (1 << bits):
+            raise ValueError(f"value table must be ({self.d}, <= {1 << bits})")
+        zf = None
+        if acq.is_mc:
+            if z is None:
+                raise ValueError("Monte Carlo acquisition functions need base samples")
+            zf = z.reshape(-1).to(self.device, torch.float32)
+        lib = _lib.load()
+        N = codes.shape[0]
+        on_host = codes.device.type == "cpu"
+        nblk = self.STREAM_BLOCKS if (on_host and N >= self.STREAM_MIN_ROWS) else 1
+        rows = -(-N // nblk)
+        rows = max(-(-rows // 128) * 128, 128)
+        c_acq = acq.to_c()
+        lay = _lib.LAYOUT["row_f32"]
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream()
+            if not hasattr(self, "_copy_stream"):
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            copy = self._copy_stream
+            cbufs = [torch.empty((rows, row_bytes), dtype=torch.uint8, device=self.device) for _ in range(2)]
+            fbuf = [torch.empty((rows, self.d), dtype=torch.float32, device=self.device) for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            freed = [torch.cuda.Event() for _ in range(2)]
+            score = torch.empty(N if want_scores else 0, dtype=torch.float32, device=self.device)
+            key = torch.empty(1, dtype=torch.int64, device=self.device)
+            _lib.check(lib.bb_best_init(_ptr(key), _stream_ptr()), "bb_best_init")
+            copy.wait_stream(main)
+            S = 0 if zf is None else zf.numel()
+            for b, lo in enumerate(range(0, N, rows)):
+                hi = min(lo + rows, N)
+                slot = b & 1
+                if on_host:
+                    with torch.cuda.stream(copy):
+                        if b >= 2:
+                            copy.wait_event(freed[slot])
+                        cbufs[slot][: hi - lo].copy_(codes[lo:hi], non_blocking=True)
+                        ready[slot].record(copy)
+                    main.wait_event(ready[slot])
+                    src = cbufs[slot]
+                else:
+                    src = codes[lo:hi]
+                _lib.check(lib.bb_decode_codes(_ptr(src), bits, hi - lo, self.d, row_bytes, _ptr(tab), tab.shape[1],
+                                               _ptr(fbuf[slot]), self.d, _stream_ptr()), "bb_decode_codes")
+                kp = None if keep is None else keep[lo:hi]
+                _lib.check(lib.bb_score_fused(
+                    C.byref(self.model), C.byref(c_acq), _ptr(fbuf[slot]), lay, hi - lo, self.d, _ptr(kp), _ptr(zf), S,
+                    C.c_void_p(score.data_ptr() + 4 * lo) if want_scores else None, _ptr(key),
+                    int(index_offset) + lo, _stream_ptr()), "bb_score_fused")
+                freed[slot].record(main)
+            for t in cbufs + fbuf:
+                t.record_stream(main)
+        return score, key
+
     def score_joint(self, acq: AcqConfig, x, pending, z: torch.Tensor) -> torch.Tensor:
         """MC acquisition value of [x*; pending] for every row x* (sequential-greedy round)."""
         xd = self.prepare(x)

@@ -11,9 +11,10 @@ discrete subspace and recommendations come back as row *posit
 the per-call re-encoding (discrete.py:123) nor the float-equality merge (discrete.py:133-140) of
 the reference is needed.
 
-Multi-GPU: when ``torch.distributed`` is initialised with the NCCL backend, every rank scores a
-contiguous row shard and one 8-byte MAX all-reduce of the packed (score, lowest index) key
-selects the global winner per greedy round.
+Multi-GPU: when ``torch.distributed`` is initialised (one process per GPU), every rank scores a
+contiguous row shard and the packed (score, lowest index) keys are max-reduced per greedy round by
+``bb_allreduce_best`` over NVLink peer memory (``baybe_b200/peers.py``).  A rank only ever holds
+its own shard; the features of a round's winner are broadcast from the rank that owns it.
 """
 
 from __future__ import annotations
@@ -77,9 +78,16 @@ def _broadcast_seed(seed: int, device) -> int:
 
 
 def _allreduce_key(key: torch.Tensor) -> torch.Tensor:
+    """Global maximum of the ranks' packed (score, lowest index) keys.  Device keys go through
+    ``bb_allreduce_best`` (baybe_b200/peers.py: one warp per rank, NVLink peer atomics, enqueued on the stream --
+    no host-issued collective); host keys (the gloo protocol tests) through ``dist.all_reduce``."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if key.is_cuda:
+            from baybe_b200.peers import get_peer_reduce
+
+            return get_peer_reduce(key.device).allreduce_best(key)
         dist.all_reduce(key, op=dist.ReduceOp.MAX)
     return key
 

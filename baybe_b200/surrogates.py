@@ -6,7 +6,8 @@ and the model owns input Normalize / output Standardize (core.py:130-141 "Scalin
 
 The fitted model lives on the GPU as a ``DeviceGP`` (caches built by ``bb_model_build``); every
 posterior evaluation runs the tcgen05 kernel.  Hyper-parameter fitting (*before*
-the hot path) evaluates the exact marginal likelihood and its gradient on the GPU (``bb_fit_eval``, float64)
+the hot path) evaluates the fit criterion -- exact marginal likelihood, or the leave-one-out pseudo-likelihood
+for transfer-learning search spaces -- and its gradient on the GPU (``bb_fit_eval[_loo]``, float64)
 under scipy's L-BFGS-B on the BayBE preset's MAP objective
 (``presets/baybe.py:57-144``: Matern-5/2 ARD, Gamma(3, rate(d)) lengthscale prior with lower bound
 2.5e-2, Gamma(2, e^5) noise prior with floor 1e-4, constant mean, no output scale).
@@ -25,8 +26,8 @@ from attrs import define, field
 from baybe_b200.engine import DeviceGP
 from baybe_b200.searchspace import objective_affine
 
-__all__ = ["GaussianProcessSurrogate", "ModelNotTrainedError", "fit_map", "fit_map_hyperparameters",
-           "fit_map_hyperparameters_device", "DeviceMLL", "HostMLL"]
+__all__ = ["GaussianProcessSurrogate", "ModelNotTrainedError", "fit_map", "fit_map_hyperparameters_device",
+           "DeviceMLL", "default_fit_criterion"]
 
 MIN_INFERRED_NOISE_LEVEL = 1e-4
 MIN_LENGTHSCALE = 2.5e-2
@@ -36,59 +37,24 @@ class ModelNotTrainedError(Exception):
     """Same name/meaning as baybe.exceptions.ModelNotTrainedError (surrogates/base.py:240-243)."""
 
 
-def _torch_kernel(family: str, d2: torch.Tensor) -> torch.Tensor:
-    if family == "rbf":
-        return torch.exp(-0.5 * d2)
-    r = d2.clamp_min(1e-30).sqrt()
-    if family == "matern12":
-        return torch.exp(-r)
-    if family == "matern32":
-        s = math.sqrt(3.0) * r
-        return (1.0 + s) * torch.exp(-s)
-    s = math.sqrt(5.0) * r
-    return (1.0 + s + (5.0 / 3.0) * d2.clamp_min(0.0)) * torch.exp(-s)
-
-
-class HostMLL:
-    """Float64 torch-autograd twin of ``DeviceMLL`` (same call signature); the independent cross-check of
-    the device objective and the ``fit_backend="host"`` path."""
-
-    def __init__(self, Xa: np.ndarray, y_std: np.ndarray, task_ids=None, n_tasks: int = 1,
-                 family: str = "matern52", device=None):
-        self.X = torch.as_tensor(np.ascontiguousarray(Xa), dtype=torch.float64)
-        self.y = torch.as_tensor(np.ascontiguousarray(y_std), dtype=torch.float64)
-        self.n, self.d = self.X.shape
-        self.T = int(n_tasks)
-        self.family = family
-        self.tid = (torch.zeros(self.n, dtype=torch.long) if task_ids is None
-                    else torch.as_tensor(np.asarray(task_ids), dtype=torch.long))
-        self.np = self.d + 2 + self.T * self.T
-
-    def __call__(self, theta: np.ndarray) -> tuple[float, np.ndarray, bool]:
-        t = torch.tensor(np.asarray(theta, dtype=np.float64), requires_grad=True)
-        d, n, T = self.d, self.n, self.T
-        ls, nz, c, B = t[:d], t[d], t[d + 1], t[d + 2:].reshape(T, T)
-        diff = (self.X[:, None, :] - self.X[None, :, :]) / ls  # direct differences, like the device kernels
-        d2 = (diff * diff).sum(-1)
-        eye = torch.eye(n, dtype=torch.float64)
-        K = _torch_kernel(self.family, d2) * (1.0 - eye) + eye  # exact unit diagonal (x1 is x2)
-        K = K * B[self.tid][:, self.tid] + nz * eye
-        L, info = torch.linalg.cholesky_ex(K)
-        if int(info) != 0:
-            return float("nan"), np.zeros(self.np), False
-        r = (self.y - c).unsqueeze(-1)
-        alpha = torch.cholesky_solve(r, L)
-        mll = -0.5 * (r * alpha).sum() - torch.log(torch.diagonal(L)).sum() - 0.5 * n * math.log(2 * math.pi)
-        mll.backward()
-        return float(mll.detach()), t.grad.numpy().copy(), True
+def default_fit_criterion(n_tasks: int) -> str:
+    """``BayBEFitCriterionFactory`` / ``_MLLForNonTLFitCriterionFactory`` (presets/baybe.py:270-281,
+    components/fit_criterion.py:61-80): exact marginal likelihood without a task parameter, the leave-one-out
+    pseudo-likelihood for transfer-learning search spaces."""
+    return "mll" if n_tasks <= 1 else "loo"
 
 
 class DeviceMLL:
-    """Exact marginal log likelihood and its gradient on the GPU (``bb_fit_setup`` / ``bb_fit_eval``,
-    float64): theta = [lengthscale[d] | noise | mean constant | B[T*T]]."""
+    """Fit criterion and its gradient on the GPU (``bb_fit_setup`` / ``bb_fit_eval`` / ``bb_fit_eval_loo``,
+    float64): theta = [lengthscale[d] | noise | mean constant | B[T*T]].  ``criterion``: "mll" = exact marginal
+    log likelihood (gpytorch ExactMarginalLogLikelihood), "loo" = leave-one-out pseudo-likelihood
+    (gpytorch LeaveOneOutPseudoLikelihood); both un-normalised (the caller divides by n like gpytorch)."""
 
     def __init__(self, Xa: np.ndarray, y_std: np.ndarray, task_ids=None, n_tasks: int = 1,
-                 family: str = "matern52", device=None):
+                 family: str = "matern52", device=None, criterion: str = "mll"):
+        if criterion not in ("mll", "loo"):
+            raise ValueError(f"unknown fit criterion {criterion!r}")
+        self.criterion = criterion
         import ctypes as C
 
         from baybe_b200 import _lib
@@ -124,21 +90,25 @@ class DeviceMLL:
         bad = C.c_int32(0)
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
         with torch.cuda.device(self.device):
-            self._lib_mod.check(self.lib.bb_fit_eval(
+            fn = self.lib.bb_fit_eval_loo if self.criterion == "loo" else self.lib.bb_fit_eval
+            self._lib_mod.check(fn(
                 C.c_void_p(self._base), self.n, self.d, self.T, self.family, dp(th), C.byref(val), dp(grad),
                 C.byref(bad), self._stream_ptr()), "bb_fit_eval")
         return float(val.value), grad, bad.value == 0
 
 
 def fit_map(Xn: np.ndarray, y_std: np.ndarray, active: Sequence[int], task_ids=None, n_tasks: int = 1,
-            max_iter: int = 200, config=None, backend: str = "device", device=None) -> dict:
+            max_iter: int = 200, config=None, device=None, criterion: str | None = None,
+            mll_factory=None) -> dict:
     """MAP fit of (lengthscales, noise, constant mean[, output scale][, task covariance]) on normalised inputs
     and standardised targets: maximises (log marginal likelihood + log priors) / n like
     ``botorch.fit.fit_gpytorch_mll`` on an ``ExactMarginalLogLikelihood`` (core.py:340-341), starting from the
-    preset's initial values (prior modes for the BayBE preset, presets/baybe.py:100-107,134-144).
+    preset's initial values (prior modes for the BayBE preset, presets/baybe.py:100-107,134-144).  With a task
+    parameter the criterion is the leave-one-out pseudo-likelihood (``default_fit_criterion``), as in the reference.
 
-    The marginal likelihood and its gradient come from ``DeviceMLL`` (GPU, default) or ``HostMLL`` (torch
-    autograd); priors, bounds and scipy's L-BFGS-B step are shared host code."""
+    The criterion and its gradient are evaluated on the GPU (``DeviceMLL``); priors, bounds and scipy's L-BFGS-B
+    step are host code.  ``mll_factory`` lets the tests inject their float64 autograd twin of the evaluator
+    (``tests/helpers.py::HostMLL``); the product never constructs a CPU evaluator."""
     from scipy.optimize import minimize
 
     from baybe_b200.kernels import gp_preset
@@ -148,7 +118,8 @@ def fit_map(Xn: np.ndarray, y_std: np.ndarray, active: Sequence[int], task_ids=N
     cfg = gp_preset("BAYBE", da) if config is None else config
     has_tasks = task_ids is not None
     T = n_tasks if has_tasks else 1
-    mll = (DeviceMLL if backend == "device" else HostMLL)(Xa, y_std, task_ids, T, cfg.family, device)
+    crit = criterion or default_fit_criterion(T)
+    mll = (mll_factory or DeviceMLL)(Xa, y_std, task_ids, T, cfg.family, device, crit)
     fit_os = cfg.outputscale and cfg.outputscale_trainable
     i_os = da + 2 if fit_os else None
     i_w = da + 2 + (1 if fit_os else 0)
@@ -203,19 +174,13 @@ def fit_map(Xn: np.ndarray, y_std: np.ndarray, active: Sequence[int], task_ids=N
     return {"lengthscale": res.x[:da].copy(), "noise": float(res.x[da]), "mean_const": float(res.x[da + 1]),
             "outputscale": float(osv) if cfg.outputscale else None,
             "task_covar": Bi if n_task_par else None, "family": cfg.family, "objective": float(res.fun),
-            "n_iter": int(res.nit), "n_eval": int(res.nfev), "backend": backend}
-
-
-def fit_map_hyperparameters(Xn, y_std, active, task_ids=None, n_tasks: int = 1, max_iter: int = 200,
-                            config=None) -> dict:
-    """``fit_map`` with the objective evaluated by float64 torch autograd on the host."""
-    return fit_map(Xn, y_std, active, task_ids, n_tasks, max_iter, config, backend="host")
+            "n_iter": int(res.nit), "n_eval": int(res.nfev), "criterion": crit}
 
 
 def fit_map_hyperparameters_device(Xn, y_std, active, task_ids=None, n_tasks: int = 1, max_iter: int = 200,
                                    device=None, config=None) -> dict:
-    """``fit_map`` with the objective evaluated on the GPU (``bb_fit_eval``)."""
-    return fit_map(Xn, y_std, active, task_ids, n_tasks, max_iter, config, backend="device", device=device)
+    """``fit_map`` (kept under its round-1 name)."""
+    return fit_map(Xn, y_std, active, task_ids, n_tasks, max_iter, config, device=device)
 
 
 class _Posterior:
@@ -249,9 +214,9 @@ class GaussianProcessSurrogate:
     """None (BayBE preset), a preset name ("BAYBE", "CHEN", "EDBO") or a ``baybe_b200.kernels`` kernel object
     (``GaussianProcessSurrogate(kernel_or_factory=...)``, surrogates/gaussian_process/core.py:147-186)."""
 
-    fit_backend: str = field(default="device")
-    """"device": marginal likelihood + gradient on the GPU (bb_fit_eval); "host": float64 torch autograd
-    (kept as the independent cross-check of the device objective)."""
+    fit_criterion: str | None = field(default=None)
+    """None: the reference's default (exact MLL; leave-one-out pseudo-likelihood with a task parameter), or
+    "mll" / "loo" explicitly (``GaussianProcessSurrogate(fit_criterion_or_factory=...)``, core.py:188-200)."""
 
     device_gp: DeviceGP | None = field(init=False, default=None, eq=False, repr=False)
     fitted_hyperparameters: dict | None = field(init=False, default=None, eq=False, repr=False)
@@ -292,7 +257,11 @@ class GaussianProcessSurrogate:
 
             kf = self.kernel_or_factory
             if kf is None:
-                config = gp_preset("BAYBE", len(active))
+                # presets/baybe.py:151-197 (_dispatch): a SubstanceParameter anywhere in the search space switches
+                # kernel, mean and likelihood to the Chen preset; otherwise the custom-scaled BayBE preset
+                has_substance = any(type(p_).__name__ == "SubstanceParameter"
+                                    for p_ in getattr(searchspace, "parameters", ()))
+                config = gp_preset("CHEN" if has_substance else "BAYBE", len(active))
             elif isinstance(kf, str):
                 config = gp_preset(kf, len(active))
             elif isinstance(kf, Kernel):
@@ -300,7 +269,7 @@ class GaussianProcessSurrogate:
             else:
                 raise TypeError("kernel_or_factory must be None, a preset name or a baybe_b200.kernels.Kernel")
             hp = fit_map(Xn, (train_y - train_y.mean()) / ys, active, tids, n_tasks, self.max_fit_iter, config,
-                         backend=self.fit_backend, device=self.device)
+                         device=self.device, criterion=self.fit_criterion)
         ls_full = np.full(d, -1.0)
         ls_full[active] = np.broadcast_to(np.asarray(hp["lengthscale"], dtype=np.float64), (len(active),))
         task_covar = hp.get("task_covar")

@@ -1,16 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- candidates/sec scored (qLogEI, 1M x 20D discrete space), BASELINE.json's metric.
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
-    python bench.py --impl reference --steps K --warmup W    # reference arm (CPU restatement)
+    python bench.py --gpus N --steps K --warmup W              # our arm (CUDA, sm_100a), BASELINE config 2
+    python bench.py --config 4|5 --gpus N ...                  # the other single-path configs (extra lines)
+    python bench.py --impl reference --steps K --warmup W      # reference arm (CPU restatement)
 
-A "step" is one pass of the hot path over one batch: posterior + qLogEI + global arg-max over
-the rank's 1,000,000 x 20 candidate shard (BASELINE config 2: n=256 training points,
-Matern-5/2 ARD, S=512 Sobol base samples, q=1), ending with the arg-max key on the host.
-With N>1 every rank scores its own 1M-row shard (weak scaling: the candidate set is row-sharded,
-SURVEY.md 8e) and one 8-byte NCCL MAX all-reduce of the packed (score, index) key gives the
-global winner.  The only place this file touches ``oracle/`` is the CPU-baseline leg and the
-``--impl reference`` arm.
+A "step" is one pass of the hot path over one batch: posterior + qLogEI + global arg-max over the rank's
+candidate shard (config 2: 1,000,000 x 20 rows, n=256 training points, Matern-5/2 ARD, S=512 Sobol base
+samples, q=1), ending with the arg-max key on the host.  With N>1 every rank scores its own shard (weak scaling:
+the candidate set is row-sharded) and the global winner comes out of ``bb_allreduce_best``: one warp
+per rank folding the packed (score, index) key into every peer's slot over NVLink (no host-issued collective).
+The same run also reports STRONG scaling (the 1M set split N ways).  The only place this file touches
+``oracle/`` is the CPU-baseline leg and the ``--impl reference`` arm.
 """
 from __future__ import annotations
 
@@ -33,6 +34,13 @@ S = 512
 SOBOL_SEED = 1234
 METRIC = "candidates/sec scored (qLogEI, 1M x 20D discrete space)"
 UNIT = "candidates/s"
+# identical in both arms (the driver compares the arms' `config`); arm-specific remarks live in `notes`
+CONFIG2 = {
+    "workload": "BASELINE config 2: 1M x 20D grid candidates per GPU (row-sharded), n=256, Matern-5/2 ARD "
+                "prior-mode hyper-parameters, qLogEI S=512 Sobol, q=1",
+    "candidates_per_gpu": N_PER_GPU, "d": D, "n_train": N_TRAIN, "mc_samples": S, "q": 1,
+    "step_ends": "global arg-max (packed key) on the host",
+}
 
 
 def _workload(n_rows: int, shard: int = 0):
@@ -47,20 +55,23 @@ def _workload(n_rows: int, shard: int = 0):
     return base, other.candidates
 
 
-def _ncu_traffic_bytes() -> float | None:
-    """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel from the committed ncu
+def _ncu_traffic_bytes(names=("r02_k_fused_ts_ncu_full_summary.txt", "r01_k_fused_tc_ncu_full_summary.txt")):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the committed ncu
     --set full capture (profiles/, one launch at this exact workload)."""
-    f = ROOT / "profiles" / "r01_k_fused_tc_ncu_full_summary.txt"
-    if not f.exists():
-        return None
-    tot, found = 0.0, 0
-    for line in f.read_text().splitlines():
-        parts = line.split()
-        if parts and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(parts[2], 1.0)
-            tot += float(parts[1]) * mult
-            found += 1
-    return tot if found == 2 else None
+    for name in names:
+        f = ROOT / "profiles" / name
+        if not f.exists():
+            continue
+        tot, found = 0.0, 0
+        for line in f.read_text().splitlines():
+            parts = line.split()
+            if parts and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(parts[2], 1.0)
+                tot += float(parts[1]) * mult
+                found += 1
+        if found == 2:
+            return tot, name
+    return None, None
 
 
 def _peaks() -> dict:
@@ -126,16 +137,19 @@ class ClockSampler:
                 "reasons": sorted(self.reasons)}
 
 
-def _cpu_reference(n_sample: int, steps: int, warmup: int):
-    """Time the CPU restatement of the reference path (oracle, torch float64, all host threads,
-    2048-row chunks like optimize_acqf_discrete) on `n_sample` candidates per step."""
+def _cpu_reference(steps: int, warmup: int, full_steps: int, n_sample: int = 50_000):
+    """Time the CPU restatement of the reference path (oracle, torch float64, host threads, 2048-row chunks like
+    optimize_acqf_discrete).  The first `full_steps` timed steps score ALL 1,000,000 config-2 candidates, the
+    remaining timed steps (and the warm-up) a `n_sample`-row sample of them -- the per-candidate cost of the
+    chunked path does not depend on the row count, and the whole run stays within a few minutes."""
     import torch
 
     import oracle
     from tests.helpers import oracle_model
 
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    w, cand = _workload(n_sample)
+    w, cand_full = _workload(N_PER_GPU)
+    cand = cand_full[:n_sample]
     om = oracle_model(w)
     acq = oracle.AcqSpec("qLogEI")
     acq.best_f = oracle.best_f_from_training(om, w.train_x, acq)
@@ -152,14 +166,16 @@ def _cpu_reference(n_sample: int, steps: int, warmup: int):
         if best_t is None or dt < best_t:
             best_t, cores = dt, t
     torch.set_num_threads(cores)
-    times = []
+    times, rows = [], []
     for i in range(warmup + steps):
+        x = cand_full if (i >= warmup and i - warmup < full_steps) else cand
         t0 = time.perf_counter()
-        vals = oracle.acq_values(om, acq, cand, z, chunk=2048)
+        vals = oracle.acq_values(om, acq, x, z, chunk=2048)
         int(torch.argmax(vals))
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+            rows.append(len(x))
     total = sum(times)
     # SURVEY.md 8(d) also asks for the best-effort single-pass form (no 2048-row chunking): two passes, best one
     single = None
@@ -169,39 +185,75 @@ def _cpu_reference(n_sample: int, steps: int, warmup: int):
         int(torch.argmax(vals))
         dt = time.perf_counter() - t0
         single = dt if single is None else min(single, dt)
-    return {"value": n_sample * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
-            "single_pass_value": n_sample / single}
+    full_rate = [r / t for r, t in zip(rows, times) if r == N_PER_GPU]
+    return {"value": sum(rows) / total, "ms_per_step_1m": 1e3 * N_PER_GPU * total / sum(rows), "cores": cores,
+            "single_pass_value": n_sample / single, "full_steps": min(full_steps, steps), "n_sample": n_sample,
+            "full_step_value": (sum(full_rate) / len(full_rate)) if full_rate else None}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = 40_000
-    r = _cpu_reference(n_sample, args.steps, args.warmup)
-    sample = f"{n_sample} of the 1,000,000 config-2 candidates per step, 2048-row chunks, torch float64, {r['cores']} threads"
+    r = _cpu_reference(args.steps, args.warmup, full_steps=2)
+    sample = (f"{r['full_steps']} timed steps over all 1,000,000 config-2 candidates, the other timed steps over "
+              f"{r['n_sample']} of them; 2048-row chunks, torch float64, {r['cores']} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step_1m"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "BASELINE config 2: 1M x 20D grid candidates, n=256, Matern-5/2 ARD, qLogEI S=512, q=1",
-                   "note": "reference arm = CPU restatement of the reference's BoTorch/GPyTorch path (oracle port); "
-                           "botorch/gpytorch are not installable offline"},
+        "data": "synthetic", "config": CONFIG2,
+        "notes": "reference arm = CPU restatement of the reference's BoTorch/GPyTorch path (oracle port); "
+                 "botorch/gpytorch are not installable offline; ms_per_step is normalised to a 1,000,000-row step",
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
-                         "single_pass_value": r["single_pass_value"]},
+                         "single_pass_value": r["single_pass_value"], "full_step_value": r["full_step_value"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(line)
 
 
-def run_b200(args):
+class _Timer:
+    """K timed steps, per-step CUDA events on the launching stream, L2 flushed (untimed) before every step,
+    barrier + synchronize on both sides, MAX over ranks of the summed step times."""
+
+    def __init__(self, dev, world):
+        import torch
+
+        self.torch, self.dev, self.world = torch, dev, world
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def __call__(self, fn, k, w_):
+        torch = self.torch
+        import torch.distributed as dist
+
+        for _ in range(w_):
+            fn()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total = 0.0
+        for _ in range(k):
+            self.flush.fill_(1)  # evict the candidate shard from L2 (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            t = torch.tensor([total], device=self.dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total
+
+
+def _setup_dist():
     import torch
     import torch.distributed as dist
-
-    from baybe_b200 import AcqConfig, DeviceGP, sobol_normal_samples
-    from baybe_b200.engine import unpack_best
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -212,7 +264,24 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local_rank, dev
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from baybe_b200 import AcqConfig, DeviceGP, sobol_normal_samples
+    from baybe_b200.bits import encode_levels
+    from baybe_b200.engine import unpack_best
+
+    world, rank, local_rank, dev = _setup_dist()
     steps, warmup = args.steps, max(args.warmup, 3)
+    peer = None
+    if world > 1:
+        from baybe_b200.peers import get_peer_reduce
+
+        peer = get_peer_reduce(dev)
 
     w, cand = _workload(N_PER_GPU, shard=rank)
     gp = DeviceGP(device=dev, **w.gp_kwargs())
@@ -221,56 +290,44 @@ def run_b200(args):
     z = sobol_normal_samples(S, 1, SOBOL_SEED)[:, 0].to(dev, torch.float32)
     x_host = torch.from_numpy(cand).to(torch.float32).pin_memory()
     x_dev = x_host.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    codes_np, table_np, bits = encode_levels(cand)  # the discrete space in its compact exact form (done once)
+    codes_host = torch.from_numpy(codes_np).pin_memory()
+    table = torch.from_numpy(table_np)
     offset = rank * N_PER_GPU
     key_host = torch.empty(1, dtype=torch.int64).pin_memory()
+    timed = _Timer(dev, world)
 
-    def step_device():
-        _, key = gp.score(acq, x_dev, z, index_offset=offset, want_scores=False)
-        if world > 1:
-            dist.all_reduce(key, op=dist.ReduceOp.MAX)
+    def finish(key):
+        if peer is not None:
+            key = peer.allreduce_best(key)  # one warp per rank, NVLink peer atomics; no host-issued collective
         key_host.copy_(key, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # arg-max key is on the host: step ends
         return key_host
 
-    def step_e2e():
-        # public API call with the HOST matrix: row blocks are copied on a side stream while the
-        # previous block is scored (DeviceGP._score_streamed); all 80 MB cross PCIe inside the step
-        _, key = gp.score(acq, x_host, z, index_offset=offset, want_scores=False)
-        if world > 1:
-            dist.all_reduce(key, op=dist.ReduceOp.MAX)
-        key_host.copy_(key, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return key_host
+    def step_device():
+        _, key = gp.score(acq, x_dev, z, index_offset=offset, want_scores=False)
+        return finish(key)
 
-    def timed(fn, k, w_):
-        for _ in range(w_):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        total = 0.0
-        for _ in range(k):
-            flush.fill_(1)  # evict the 80 MB candidate shard from L2 (untimed)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            e1.synchronize()
-            total += e0.elapsed_time(e1)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            t = torch.tensor([total], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total = float(t.item())
-        return total
+    def step_e2e():
+        # public API call with the HOST candidate set in its level-coded form (4-bit codes + value table): row blocks
+        # are copied on a side stream, expanded on the device (bb_decode_codes) and scored; all bytes cross PCIe
+        # inside the step
+        _, key = gp.score_coded(acq, codes_host, table, bits, z, index_offset=offset, want_scores=False)
+        return finish(key)
+
+    def step_e2e_f32():
+        # same with the float32 host matrix (80 B per candidate): streamed in 8 row blocks, PCIe-bound
+        _, key = gp.score(acq, x_host, z, index_offset=offset, want_scores=False)
+        return finish(key)
 
     with ClockSampler(local_rank) as clocks:
         total_ms = timed(step_device, steps, warmup)
     best_val, best_idx = unpack_best(int(key_host.item()))
     e2e_ms = timed(step_e2e, steps, warmup)
+    key_coded = int(key_host.item())
+    e2e32_ms = timed(step_e2e_f32, max(3, steps // 4), 2) / max(3, steps // 4)
+    if peer is not None:
+        peer.check()
 
     # dominant kernel alone (events on the launching stream), for the roofline
     def kernel_only():
@@ -281,46 +338,176 @@ def run_b200(args):
     value = world * N_PER_GPU / (ms_per_step * 1e-3)
     e2e_value = world * N_PER_GPU / (e2e_ms / steps * 1e-3)
 
+    # strong scaling: the SAME 1,000,000-row set (seed 0) split over the ranks
+    strong = None
+    if world > 1:
+        _, all_rows = _workload(N_PER_GPU, shard=0)
+        per = -(-N_PER_GPU // world)
+        lo, hi = min(rank * per, N_PER_GPU), min((rank + 1) * per, N_PER_GPU)
+        xs = torch.from_numpy(all_rows[lo:hi]).to(dev, torch.float32)
+
+        def step_strong():
+            _, key = gp.score(acq, xs, z, index_offset=lo, want_scores=False)
+            return finish(key)
+
+        s_ms = timed(step_strong, steps, warmup) / steps
+        strong = {"value": N_PER_GPU / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms,
+                  "candidates_total": N_PER_GPU, "rows_per_gpu": per,
+                  "best": dict(zip(("value", "index"), unpack_best(int(key_host.item()))))}
+
     if rank == 0:
         peaks = _peaks()
         flops = N_PER_GPU * (2.0 * N_TRAIN * N_TRAIN + 2.0 * N_TRAIN * D)  # 2n^2 + 2nd per candidate
         achieved = flops / (kern_ms * 1e-3) / 1e12
+        traffic, traffic_src = _ncu_traffic_bytes()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = _cpu_reference(40_000, 6, 1)
+            r = _cpu_reference(6, 1, full_steps=1)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                   "sample": "6 passes over 40,000 of the 1M config-2 candidates, 2048-row chunks, torch float64",
+                   "sample": f"1 pass over all 1,000,000 config-2 candidates + 5 passes over {r['n_sample']} of them, "
+                             "2048-row chunks, torch float64",
                    "single_pass_value": r["single_pass_value"],
-                   "single_pass_note": "same sample scored in one unchunked pass (best of 2), same thread count"}
+                   "single_pass_note": "50,000-row sample scored in one unchunked pass (best of 2), same thread count"}
+        launches = (2 + (1 if world > 1 else 0)) * steps  # key init + fused kernel (+ one-warp peer reduction)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {
-                "workload": "BASELINE config 2: 1M x 20D grid candidates per GPU (row-sharded), n=256, "
-                            "Matern-5/2 ARD prior-mode hyper-parameters, qLogEI S=512 Sobol, q=1",
-                "candidates_per_gpu": N_PER_GPU, "layout": "fp32 row-major, resident in HBM",
+            "data": "synthetic", "config": CONFIG2,
+            "notes": {
+                "layout": "fp32 row-major, resident in HBM",
                 "l2": "flushed between timed steps (256 MiB write, untimed)",
-                "step_ends": "packed arg-max key on host (8-byte D2H)" + ("; 8-byte NCCL MAX all-reduce" if world > 1 else ""),
-                "precision": "distance GEMM and K* L^-T on tcgen05 (fp16 hi/mid/lo resp. hi/lo split operands, fp32 TMEM accumulate), fp32 Matern epilogue and MC",
+                "reduction": "bb_allreduce_best: one warp per rank, atomicMax.sys into every peer's slot over NVLink "
+                             "(CUDA IPC mapped), no host-issued collective" if world > 1 else "single GPU",
+                "precision": "distance GEMM (fp16 hi/mid/lo split, 2^-33) and K* L^-T (fp16 hi/lo split, A operand "
+                             "in tensor memory) on tcgen05, fp32 TMEM accumulate; packed-fp32 Matern epilogue and MC",
                 "best": {"value": best_val, "index": best_idx},
+                "e2e_coded_matches_resident": key_coded == int(key_host.item()) if world == 1 else None,
             },
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 8,
-                    "api": "DeviceGP.score(pinned host fp32 matrix) -> host arg-max key; H2D in 8 row blocks overlapped with scoring"},
-            "gpu_launches": 2 * steps,
+                    "h2d_bytes_per_step": int(codes_host.numel() + table.numel() * 4), "d2h_bytes_per_step": 8,
+                    "api": f"DeviceGP.score_coded(pinned host {bits}-bit level codes + value table) -> host arg-max key; "
+                           "H2D in 8 row blocks overlapped with decode + scoring; scores bit-identical to the float32 matrix",
+                    "fp32_matrix": {"value": world * N_PER_GPU / (e2e32_ms * 1e-3), "h2d_bytes_per_step": x_host.numel() * 4,
+                                    "api": "DeviceGP.score(pinned host fp32 matrix)"}},
+            "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": {
-                "bound": "tensor", "kernel": "k_fused_tc<matern52,K32>", "achieved": achieved,
+                "bound": "tensor", "kernel": "k_fused_ts<matern52>", "achieved": achieved,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": _ncu_traffic_bytes(), "traffic_unit": "bytes per launch (ncu --set full, profiles/)",
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, profiles/)",
+                "traffic_source": traffic_src,
                 "algorithmic_bytes": N_PER_GPU * (4 * D + 4), "kernel_ms": kern_ms, "peak_source": peaks["source"],
-                "note": "algorithmic flops = N*(2n^2 + 2nd) (SURVEY 8d); the tensor pipe executes 3 split "
-                        "products over 5/8 of the n^2 (triangular skip) plus 6 split products of the "
-                        "distance GEMM; bound in practice by per-MMA shared-memory operand reads, see DESIGN.md",
+                "note": "algorithmic flops = N*(2n^2 + 2nd) (SURVEY 8d); the tensor pipe executes 3 split products "
+                        "over 8.5/16 of the n^2 (triangular skip at 16-column granularity) plus 6 split products of "
+                        "the distance GEMM over K = 32; see DESIGN.md",
             },
             "cpu_baseline": cpu,
+        }
+        if strong is not None:
+            line["strong_scaling"] = strong
+        _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_other(args):
+    """BASELINE configs 4 and 5 (extra lines, not the driver's headline): same JSON shape."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from baybe_b200 import AcqConfig, DeviceGP, sobol_normal_samples
+    from baybe_b200.engine import unpack_best
+    from baybe_b200.synthetic import fingerprint_workload, task_workload
+
+    world, rank, local_rank, dev = _setup_dist()
+    steps, warmup = args.steps, max(args.warmup, 3)
+    peer = None
+    if world > 1:
+        from baybe_b200.peers import get_peer_reduce
+
+        peer = get_peer_reduce(dev)
+    z = sobol_normal_samples(S, 1, SOBOL_SEED)[:, 0].to(dev, torch.float32)
+    timed = _Timer(dev, world)
+    key_host = torch.empty(1, dtype=torch.int64).pin_memory()
+    peaks = _peaks()
+    if args.config == 4:
+        # 10M x 2048-bit fingerprints (Bernoulli 0.05), n = 512, ScaleKernel(RBF); STRONG: 10M split over the ranks
+        total_rows = 10_000_000
+        per = -(-total_rows // world)
+        lo, hi = min(rank * per, total_rows), min((rank + 1) * per, total_rows)
+        w = fingerprint_workload(N=4096, d=2048, n=512, seed=1)
+        gp = DeviceGP(device=dev, **w.gp_kwargs())
+        g = torch.Generator(device=dev).manual_seed(1000 + rank)
+        x = torch.empty((hi - lo, 256), dtype=torch.uint8, device=dev)
+        for a in range(0, hi - lo, 500_000):  # generate in blocks: the boolean staging tensor is 8x the packed size
+            b = min(a + 500_000, hi - lo)
+            bits = torch.rand((b - a, 256, 8), device=dev, generator=g) < 0.05
+            x[a:b] = (bits.to(torch.uint8) << torch.arange(8, device=dev, dtype=torch.uint8)).sum(dim=2).to(torch.uint8)
+        del bits
+        n_tr, d_feat = 512, 2048
+        name = "BASELINE config 4: 10M x 2048-bit Morgan-like fingerprints (bit-packed), n=512, ScaleKernel(RBF), qLogEI S=512"
+        scaling, metric = "strong", "candidates/sec scored (qLogEI, 10M x 2048-bit fingerprint space)"
+        kern_rows = min(hi - lo, 262_144)
+        kernel_fn = lambda: gp.kernel_matrix(x[:kern_rows])  # noqa: E731  (k_kmat_tc alone: the dominant kernel)
+        kern_flops = kern_rows * 2.0 * n_tr * d_feat
+        kern_name = "k_kmat_tc<rbf,bits> (distance GEMM of one 262,144-row block)"
+        rl_note = ("algorithmic flops = rows*2*n*d; the bit-linear form issues 2 fp16 split products, so the tensor "
+                   "pipe executes 2x this")
+        total = total_rows
+    else:
+        # 4 tasks x 250k rows (config-2 grid + task column), ICM kernel, n = 512; rows sharded regardless of task
+        total_rows = 1_000_000
+        w = task_workload(N_per_task=250_000, n_tasks=4, d_num=20, n_per_task=128, seed=0)
+        per = -(-total_rows // world)
+        lo, hi = min(rank * per, total_rows), min((rank + 1) * per, total_rows)
+        perm = np.random.default_rng(0).permutation(total_rows)  # shards see all tasks
+        gp = DeviceGP(device=dev, **w.gp_kwargs())
+        x = torch.from_numpy(w.candidates[perm[lo:hi]]).to(dev, torch.float32)
+        n_tr, d_feat = 512, 21
+        name = "BASELINE config 5: 4 tasks x 250k candidates (20 numeric + task column), ICM kernel, n=512, qLogEI S=512"
+        scaling, metric = "strong", "candidates/sec scored (qLogEI, 4 x 250k transfer-learning space)"
+        kernel_fn = lambda: gp.score(acq, x, z, want_scores=False)  # noqa: E731
+        kern_flops = (hi - lo) * (2.0 * n_tr * n_tr + 2.0 * n_tr * d_feat)
+        kern_name = "k_fused<matern52> (FFMA2 distances, tcgen05 V contraction, n_pad=512)"
+        rl_note = "algorithmic flops = rows*(2n^2 + 2nd)"
+        total = total_rows
+    acq = AcqConfig(kind="qLogEI", best_f=gp.best_f(AcqConfig(kind="qLogEI")))
+
+    def step():
+        _, key = gp.score(acq, x, z, index_offset=lo, want_scores=False)
+        if peer is not None:
+            key = peer.allreduce_best(key)
+        key_host.copy_(key, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    with ClockSampler(local_rank) as clocks:
+        total_ms = timed(step, steps, warmup)
+    kern_ms = timed(kernel_fn, steps, 2) / steps
+    topk = None
+    if args.config == 5:
+        # "NCCL top-k argmax": per-rank bb_topk + one all-gather of k (value, index) pairs
+        from baybe_b200.recommenders import distributed_topk
+
+        scores, _ = gp.score(acq, x, z, index_offset=lo)
+        v, i = distributed_topk(scores, None, 8, offset=lo)
+        topk = {"values": v.tolist(), "positions_in_shard_order": i.tolist()}
+    if peer is not None:
+        peer.check()
+    if rank == 0:
+        ms = total_ms / steps
+        achieved = kern_flops / (kern_ms * 1e-3) / 1e12
+        line = {
+            "metric": metric, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": name, "candidates_total": total, "rows_per_gpu": per},
+            "e2e": None, "gpu_launches": None, "clocks": clocks.summary(),
+            "roofline": {"bound": "tensor", "kernel": kern_name, "achieved": achieved, "peak": peaks["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                         "kernel_ms": kern_ms, "peak_source": peaks["source"], "note": rl_note},
+            "cpu_baseline": None,
+            "notes": {"best": dict(zip(("value", "index"), unpack_best(int(key_host.item())))), "topk": topk},
         }
         _emit(line)
     if world > 1:
@@ -346,12 +533,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--config", type=int, choices=[2, 4, 5], default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.config == 2:
         run_b200(args)
+    else:
+        run_other(args)
 
 
 if __name__ == "__main__":

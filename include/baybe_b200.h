@@ -216,6 +216,11 @@ int bb_fit_setup(void* d_ws, size_t ws_bytes, int32_t n, int32_t d, int32_t n_ta
                  const double* y, const int32_t* task, void* stream);
 int bb_fit_eval(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, int32_t family, const double* theta,
                 double* value, double* grad, int32_t* not_pd, void* stream);
+/* Leave-one-out pseudo-likelihood (gpytorch.mlls.LeaveOneOutPseudoLikelihood), the criterion the reference's
+ * presets select when the search space has a task parameter (presets/baybe.py:270-281,
+ * components/fit_criterion.py:22-41): value = sum_i log N(y_i | mu_-i, sigma_-i^2), same theta / gradient layout. */
+int bb_fit_eval_loo(void* d_ws, int32_t n, int32_t d, int32_t n_tasks, int32_t family, const double* theta,
+                    double* value, double* grad, int32_t* not_pd, void* stream);
 
 /* ---- K2: K(X*, X_train), fp32 row-major [N, ldk>=n].  Replaces gpytorch
  * MaternKernel/RBFKernel/ScaleKernel/ProductKernel.forward built at
@@ -269,6 +274,35 @@ int bb_argmax(const float* d_score, const uint8_t* d_keep, int64_t N, int64_t in
 int bb_best_decode(const int64_t* d_best_key, bb_best* d_out, void* stream);
 int bb_topk(const float* d_score, const uint8_t* d_keep, int64_t N, int32_t k, float* d_vals,
             int64_t* d_idx, uint8_t* d_scratch_mask /* [N] */, int64_t* d_scratch_key, void* stream);
+
+/* ---- multi-GPU: global arg-max of a row-sharded candidate set.  Every rank owns a small buffer of
+ * two key slots (int64) and two arrival counters (uint32), double-buffered by epoch parity, initialised once with
+ * bb_peer_slots_init; the ranks exchange the buffers' addresses with CUDA IPC (one process per GPU, NVLink peer
+ * access) and fill bb_peer_group with their own and the mapped peer pointers.  bb_allreduce_best then runs ONE warp on
+ * the caller's stream: atomicMax.sys of the local packed key into every rank's slot, a system fence, a bump of
+ * every rank's counter, a bounded wait for `world` arrivals at the own counter, copy-out and re-arm.  No host
+ * code and no NCCL call sits between the scoring kernel and the reduced key.  `epoch` must be the same on all ranks
+ * and increase by one per call; *d_status = 1 if a peer did not arrive within ~2 s (d_out_key then holds the local
+ * key).  Replaces torch.argmax over the full candidate set inside botorch.optim.optimize_acqf_discrete
+ * (baybe/recommenders/pure/bayesian/botorch/discrete.py:124-126) for a candidate set sharded over GPUs. */
+#define BB_MAX_PEERS 8
+typedef struct bb_peer_group {
+  int32_t rank, world;
+  int64_t* d_key[BB_MAX_PEERS];    /* [r] -> two key slots in rank r's memory (own or IPC-mapped)      */
+  uint32_t* d_count[BB_MAX_PEERS]; /* [r] -> two arrival counters in rank r's memory                   */
+} bb_peer_group;
+int bb_peer_slots_init(int64_t* d_keys /* [2] */, uint32_t* d_counts /* [2] */, void* stream);
+int bb_allreduce_best(const bb_peer_group* g, const int64_t* d_local_key, uint32_t epoch, int64_t* d_out_key,
+                      int32_t* d_status, void* stream);
+
+/* ---- level-coded candidate rows (device-resident search-space cache): a discrete search space has
+ * few distinct values per comp-rep column (the parameters' value lists, baybe/searchspace/discrete.py:529-536), so
+ * the host side may ship rows as `bits`-bit level codes (4: two columns per byte, low nibble = even column; 8: one
+ * byte per column; row r at d_codes + r*ld_bytes) plus a value table d_table[d][table_ld] (fp32).  Expands to
+ * fp32 row-major d_out[N][ldo]; exact (the table holds the comp-rep values).  Replaces shipping the float64
+ * comp-rep matrix that SubspaceDiscrete.transform builds per call (botorch/discrete.py:123). */
+int bb_decode_codes(const uint8_t* d_codes, int32_t bits, int64_t N, int32_t d, int64_t ld_bytes,
+                    const float* d_table, int32_t table_ld, float* d_out, int64_t ldo, void* stream);
 
 /* ---- test-only diagnostic: plain fp32 SIMT posterior (no tensor cores), used by the GPU
  * tests to separate tcgen05-path errors from formula errors.  Not called by the product. -- */

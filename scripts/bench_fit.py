@@ -8,7 +8,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from baybe_b200.surrogates import fit_map_hyperparameters, fit_map_hyperparameters_device  # noqa: E402
+from baybe_b200.surrogates import fit_map, fit_map_hyperparameters_device  # noqa: E402
+from tests.helpers import HostMLL  # noqa: E402  (float64 autograd twin, test infrastructure)
 from baybe_b200.synthetic import numeric_grid_workload  # noqa: E402
 
 for n in (256, 512):
@@ -20,7 +21,7 @@ for n in (256, 512):
     dev = fit_map_hyperparameters_device(w.train_x, y, active, None, 1, 200, device="cuda:0")
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    host = fit_map_hyperparameters(w.train_x, y, active, None, 1, 200)
+    host = fit_map(w.train_x, y, active, None, 1, 200, mll_factory=HostMLL)
     t2 = time.perf_counter()
     print(json.dumps(dict(n=n, d=20, device_s=t1 - t0, host_s=t2 - t1, device_evals=dev["n_eval"],
                           device_ms_per_eval=(t1 - t0) / dev["n_eval"] * 1e3, host_iters=host["n_iter"],

@@ -1,7 +1,10 @@
 """Glue between the synthetic workloads and the CPU oracle (test infrastructure only)."""
 from __future__ import annotations
 
+import math
+
 import numpy as np
+import torch
 
 import oracle
 from baybe_b200.synthetic import Workload
@@ -128,3 +131,64 @@ class OracleBackedGP:
     def score_joint(self, acq, x, pending, z):
         return oracle.acq_values_joint(self.om, self._spec(acq), np.asarray(x, dtype=np.float64),
                                        np.asarray(pending, dtype=np.float64), z).float()
+
+
+# --------------------------------------------------------------------------------------
+# Host twin of the device fit criterion (cross-check only)
+# --------------------------------------------------------------------------------------
+def _torch_kernel(family: str, d2: torch.Tensor) -> torch.Tensor:
+    if family == "rbf":
+        return torch.exp(-0.5 * d2)
+    r = d2.clamp_min(1e-30).sqrt()
+    if family == "matern12":
+        return torch.exp(-r)
+    if family == "matern32":
+        s = math.sqrt(3.0) * r
+        return (1.0 + s) * torch.exp(-s)
+    s = math.sqrt(5.0) * r
+    return (1.0 + s + (5.0 / 3.0) * d2.clamp_min(0.0)) * torch.exp(-s)
+
+
+class HostMLL:
+    """Float64 torch-autograd twin of ``baybe_b200.surrogates.DeviceMLL`` (same constructor and call signature):
+    the independent cross-check of the device fit criteria ("mll": exact marginal log likelihood, "loo":
+    leave-one-out pseudo-likelihood) and their gradients.  TEST INFRASTRUCTURE -- it used to live in the product
+    package as ``fit_backend="host"`` (VERDICT r1, weak #11)."""
+
+    def __init__(self, Xa: np.ndarray, y_std: np.ndarray, task_ids=None, n_tasks: int = 1,
+                 family: str = "matern52", device=None, criterion: str = "mll"):
+        self.criterion = criterion
+        self.X = torch.as_tensor(np.ascontiguousarray(Xa), dtype=torch.float64)
+        self.y = torch.as_tensor(np.ascontiguousarray(y_std), dtype=torch.float64)
+        self.n, self.d = self.X.shape
+        self.T = int(n_tasks)
+        self.family = family
+        self.tid = (torch.zeros(self.n, dtype=torch.long) if task_ids is None
+                    else torch.as_tensor(np.asarray(task_ids), dtype=torch.long))
+        self.np = self.d + 2 + self.T * self.T
+
+    def __call__(self, theta: np.ndarray) -> tuple[float, np.ndarray, bool]:
+        t = torch.tensor(np.asarray(theta, dtype=np.float64), requires_grad=True)
+        d, n, T = self.d, self.n, self.T
+        ls, nz, c, B = t[:d], t[d], t[d + 1], t[d + 2:].reshape(T, T)
+        diff = (self.X[:, None, :] - self.X[None, :, :]) / ls  # direct differences, like the device kernels
+        d2 = (diff * diff).sum(-1)
+        eye = torch.eye(n, dtype=torch.float64)
+        K = _torch_kernel(self.family, d2) * (1.0 - eye) + eye  # exact unit diagonal (x1 is x2)
+        K = K * B[self.tid][:, self.tid] + nz * eye
+        L, info = torch.linalg.cholesky_ex(K)
+        if int(info) != 0:
+            return float("nan"), np.zeros(self.np), False
+        r = (self.y - c).unsqueeze(-1)
+        alpha = torch.cholesky_solve(r, L)
+        if self.criterion == "loo":
+            # gpytorch LeaveOneOutPseudoLikelihood: sigma_i^2 = 1/[K^-1]_ii, mu_i = y_i - alpha_i sigma_i^2
+            kap = torch.cholesky_inverse(L).diagonal()
+            a = alpha.squeeze(-1)
+            mll = (0.5 * kap.log() - 0.5 * a * a / kap).sum() - 0.5 * n * math.log(2 * math.pi)
+        else:
+            mll = -0.5 * (r * alpha).sum() - torch.log(torch.diagonal(L)).sum() - 0.5 * n * math.log(2 * math.pi)
+        mll.backward()
+        return float(mll.detach()), t.grad.numpy().copy(), True
+
+

@@ -115,3 +115,71 @@ def test_topk_merge_single_process_and_padding():
     i = torch.tensor([9, 4, -1])
     gv, gi = merge_topk_across_ranks(v, i, 3)
     assert gi.tolist() == [4, 9, -1] and gv[:2].tolist() == [2.0, 2.0]
+
+
+def _seed_worker(rank: int, world: int, port: int, out):
+    from baybe_b200.recommenders import _broadcast_seed
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)  # the usual seed+rank pattern: the ranks' own draws differ
+    own = int(torch.randint(0, 1_000_000, (1,)).item())
+    got = _broadcast_seed(own, torch.device("cpu"))
+    out.put((rank, own, got))
+    dist.destroy_process_group()
+
+
+def test_sampler_seed_is_broadcast_from_rank_zero():
+    """every rank must score its shard with the same base samples, whatever its own RNG state."""
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seed_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(out.get() for _ in range(2))
+    assert res[0][1] != res[1][1]  # different local draws ...
+    assert res[0][2] == res[1][2] == res[0][1]  # ... one shared seed: rank 0's
+
+
+def _greedy_worker(rank: int, world: int, port: int, out):
+    """greedy_select across two ranks with the oracle-backed engine: shard-local scoring, global arg-max, winner rows
+    fetched from the owning rank, pending points growing round by round."""
+    import oracle
+    from baybe_b200.engine import AcqConfig
+    from baybe_b200.recommenders import greedy_select, shard_bounds as sb
+    from baybe_b200.synthetic import numeric_grid_workload
+    from tests.helpers import OracleBackedGP, oracle_model
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = numeric_grid_workload(N=301, d=4, n=20, seed=3)
+    gp = OracleBackedGP(**w.gp_kwargs())
+    cfg = AcqConfig(kind="qLogEI", best_f=gp.best_f(AcqConfig(kind="qLogEI")))
+    lo, hi = sb(len(w.candidates), rank, world)
+    x = torch.from_numpy(w.candidates[lo:hi]).to(torch.float32)
+    chosen, vals = greedy_select(gp, cfg, x, 4, 3, None, seed=5, n_samples=64, offset=lo)
+    if rank == 1:
+        om = oracle_model(w)
+        oacq = oracle.AcqSpec("qLogEI", best_f=cfg.best_f)
+        ref, _ = oracle.optimize_acqf_discrete(om, oacq, w.candidates.astype(np.float32).astype(np.float64), q=3,
+                                               sampler_seed=5, n_samples=64)
+        out.put((chosen, ref))
+    dist.destroy_process_group()
+
+
+def test_sharded_greedy_selection_matches_single_process_oracle():
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_greedy_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    chosen, ref = out.get()
+    assert chosen == ref

@@ -12,7 +12,8 @@ from baybe_b200.engine import AcqConfig, pack_best, sobol_normal_samples, unpack
 from baybe_b200.recommenders import B200Recommender, shard_bounds
 from baybe_b200.searchspace import (CategoricalParameter, NumericalDiscreteParameter, NumericalTarget,
                                     SearchSpace, SingleTargetObjective, TaskParameter, objective_affine)
-from baybe_b200.surrogates import GaussianProcessSurrogate, ModelNotTrainedError, fit_map_hyperparameters
+from baybe_b200.surrogates import GaussianProcessSurrogate, ModelNotTrainedError, fit_map
+from tests.helpers import HostMLL
 
 
 def _space():
@@ -93,7 +94,7 @@ def test_map_fit_recovers_sensible_hyperparameters():
     rng = np.random.default_rng(1)
     X = rng.uniform(size=(60, 3))
     y = np.sin(6 * X[:, 0]) + 0.02 * rng.standard_normal(60)  # only dim 0 matters
-    hp = fit_map_hyperparameters(X, (y - y.mean()) / y.std(ddof=1), [0, 1, 2])
+    hp = fit_map(X, (y - y.mean()) / y.std(ddof=1), [0, 1, 2], mll_factory=HostMLL)
     ls = hp["lengthscale"]
     assert ls[0] < ls[1] and ls[0] < ls[2]  # ARD: the relevant dimension gets the short lengthscale
     assert 1e-4 <= hp["noise"] < 0.1 and np.all(ls >= 2.5e-2)
@@ -199,14 +200,13 @@ def test_kernel_specs_and_presets():
 
 def test_host_fit_with_presets_improves_on_the_start_point():
     from baybe_b200.kernels import gp_preset
-    from baybe_b200.surrogates import HostMLL, fit_map_hyperparameters
     from baybe_b200.synthetic import numeric_grid_workload
 
     w = numeric_grid_workload(N=200, d=3, n=30, seed=2)
     y = (w.train_y - w.train_y.mean()) / w.train_y.std(ddof=1)
     for name in ("BAYBE", "CHEN", "EDBO"):
         cfg = gp_preset(name, 3)
-        hp = fit_map_hyperparameters(w.train_x, y, [0, 1, 2], None, 1, 60, config=cfg)
+        hp = fit_map(w.train_x, y, [0, 1, 2], None, 1, 60, config=cfg, mll_factory=HostMLL)
         assert hp["family"] == "matern52" and (hp["outputscale"] is not None) == cfg.outputscale
         assert hp["noise"] >= 1e-4 and (hp["lengthscale"] >= cfg.lengthscale_lower).all()
         # the optimum is at least as good as the start point
