@@ -457,6 +457,11 @@ extern "C" int bb_kernel_matrix(const bb_model* m, const void* d_x, int32_t layo
   BB_CHECK_ARG(d_k != nullptr || N == 0, "bb_kernel_matrix: output pointer is null");
   BB_CHECK_ARG(ldk >= m->n, "bb_kernel_matrix: ldk=%lld smaller than n=%d", (long long)ldk, m->n);
   if (N == 0) return BB_OK;
+  {  // tensor-core distances + TMA tensor-map stores (fused_ts.cu: k_kmat_ts) where the shape allows
+    bool handled = false;
+    rc = try_kmat_ts(m, d_x, layout, N, ldx, d_k, ldk, stream, &handled);
+    if (rc != BB_OK || handled) return rc;
+  }
   p.kout = d_k;
   p.ldk = ldk;
   int sms, max_smem;

@@ -14,6 +14,8 @@
 // (/root/reference/baybe/recommenders/pure/bayesian/botorch/discrete.py:124-126) =
 // acqf(X[chunk].unsqueeze(-2)) -> SingleTaskGP.posterior (gaussian_process/core.py:268-269)
 // -> qLogExpectedImprovement.forward (class chosen at acquisition/base.py:162-181).
+#include <stdlib.h>
+
 #include "assemble.cuh"
 #include "fused_common.cuh"
 
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
     // =====================================================================================
     // producer: stream the fp16 image of L^-1 (B operand) through the TMA engine
     // =====================================================================================
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: straight UBLKCP, no ELECT/BRA.U.ANY wrapper (see fused_common.cuh)
       uint32_t st = 0, ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         size_t off = 0;
@@ -473,8 +475,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
   } else {
     // =====================================================================================
     // MMA issuer: D[128 x n_pad] (TMEM, fp32) = K*[128 x n_pad] (smem, fp16 hi+lo) * Linv^T
+    // The whole warp runs the loop converged and one lane issues under elect.sync: issued under `if (lane == 0)`
+    // every tcgen05.mma costs ~106 cycles of ELECT/R2UR/BRA.U.ANY wrapper (scripts/ubench/mma_rate.cu).
     // =====================================================================================
-    if (lane == 0) {
+    {
       uint32_t slot = 0, pha = 0, st = 0, phb = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -500,26 +504,31 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(const FusedParams p)
             const uint64_t b_lo = make_sw128_desc(b_addr + (uint32_t)gsz * 8192u);
             const uint32_t d_addr = d_base + (uint32_t)((sb - p.sb_lo) * kChunk);
             sb += gsz;
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ko = (uint64_t)(kk * 2);  // 16 fp16 = 32 bytes = 2 x 16-byte units
-              umma_f16(d_addr, a_hi + ko, b_hi + ko, idesc, (c > 0 || kk > 0) ? 1u : 0u);
-              umma_f16(d_addr, a_hi + ko, b_lo + ko, idesc, 1u);
-              umma_f16(d_addr, a_lo + ko, b_hi + ko, idesc, 1u);
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ko = (uint64_t)(kk * 2);  // 16 fp16 = 32 bytes = 2 x 16-byte units
+                umma_f16(d_addr, a_hi + ko, b_hi + ko, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+                umma_f16(d_addr, a_hi + ko, b_lo + ko, idesc, 1u);
+                umma_f16(d_addr, a_lo + ko, b_hi + ko, idesc, 1u);
+              }
+              umma_commit(&s.b_empty[st]);
             }
-            umma_commit(&s.b_empty[st]);
+            __syncwarp();
             if (++st == (uint32_t)p.stages_b) {
               st = 0;
               phb ^= 1u;
             }
           }
-          umma_commit(&s.a_empty[slot]);
+          if (elect_one()) umma_commit(&s.a_empty[slot]);
+          __syncwarp();
           if (++slot == (uint32_t)p.slots_a) {
             slot = 0;
             pha ^= 1u;
           }
         }
-        umma_commit(&s.d_full[buf]);
+        if (elect_one()) umma_commit(&s.d_full[buf]);
+        __syncwarp();
       }
     }
   }
@@ -746,7 +755,12 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (m->wide) return launch_wide_blocks(m, p, sms, max_smem, wc, stream);
-  if (g_trace_buf == nullptr && fused_ts_supported(p, max_smem)) {  // headline kernel (fused_ts.cu); tracing is a fused_tc feature
+  // diagnostic knob (tests / profiling only): BB_FORCE_KERNEL=tc keeps shapes the TS kernel covers on fused_tc.cu
+  static const bool ts_off = [] {
+    const char* e = getenv("BB_FORCE_KERNEL");
+    return e != nullptr && e[0] == 't' && e[1] == 'c';
+  }();
+  if (!ts_off && g_trace_buf == nullptr && fused_ts_supported(p, max_smem)) {  // headline kernel (fused_ts.cu); tracing is a fused_tc feature
     const int grid_ts = p.num_tiles < sms ? p.num_tiles : sms;
     return launch_fused_ts(p, grid_ts, stream);
   }

@@ -136,6 +136,10 @@ __device__ __forceinline__ void split3_quad(const float (&x)[4], uint2& hi, uint
 int launch_fused_tc(FusedParams& p, int grid, cudaStream_t stream);
 int launch_fused_ts(FusedParams& p, int grid, cudaStream_t stream);
 bool fused_ts_supported(const FusedParams& p, int max_smem);
+bool kmat_ts_supported(const FusedParams& p, const float* d_k, int64_t ldk, int max_smem);
+int launch_kmat_ts(FusedParams& p, float* d_k, int64_t ldk, int n_cols, int grid, cudaStream_t stream);
+int try_kmat_ts(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx, float* d_k, int64_t ldk,
+                cudaStream_t stream, bool* handled);
 // elect.sync: true in exactly one lane of a converged warp.  tcgen05.mma / cp.async.bulk / tcgen05.commit issued
 // under this predicate compile to straight uniform-datapath code; the same instructions under `if (lane == 0)` are
 // wrapped by ptxas in an ELECT / R2UR / BRA.U.ANY loop that costs ~106 cycles per MMA (scripts/ubench/mma_rate.cu).

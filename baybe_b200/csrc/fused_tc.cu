@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
     // =====================================================================================
     // producer (TMA engine): streams the L^-1 tiles (same sequence for every candidate tile)
     // =====================================================================================
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: straight UBLKCP (fused_common.cuh)
       uint32_t rs = 0, rph = 0;
       int pit = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++pit) {
@@ -547,9 +547,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
     }
   } else {
     // =====================================================================================
-    // MMA issuer
+    // MMA issuer: the whole warp runs the loop converged, one lane issues under elect.sync (issued under
+    // `if (lane == 0)` every tcgen05.mma is wrapped in an ELECT/R2UR/BRA.U.ANY loop, ~106 cycles per instruction)
     // =====================================================================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_f16(kTileM, kChunk), idesc128 = make_idesc_f16(kTileM, 2 * kChunk);
       const uint32_t idesc_d2 = make_idesc_f16(kTileM, p.n_pad);  // one MMA spans all training columns
       uint32_t slot = 0, pha = 0, rs = 0, rph = 0;
@@ -561,68 +562,76 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_tc(const FusedParams
       // distance GEMM of tile number j: D2 = A2 * Bt^T, six split products, N = n_pad per MMA
       auto issue_distance = [&](int j) {
         const uint32_t par = (uint32_t)(j & 1);
-        trace_ev(p, j, 250);
+        if (lane == 0) trace_ev(p, j, 250);
         mbar_wait_relaxed(s.a2_full, par);
-        trace_ev(p, j, 251);
+        if (lane == 0) trace_ev(p, j, 251);
         mbar_wait_relaxed(s.d2_empty, par ^ 1u);  // D2 drained by the previous tile's chunk loop
-        trace_ev(p, j, 252);
+        if (lane == 0) trace_ev(p, j, 252);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + kD2Col0;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t ko = (uint64_t)(kk * 2);
-          umma_f16(d_addr, a2_h + ko, b_h + ko, idesc_d2, kk > 0 ? 1u : 0u);
-          umma_f16(d_addr, a2_h + ko, b_m + ko, idesc_d2, 1u);
-          umma_f16(d_addr, a2_m + ko, b_h + ko, idesc_d2, 1u);
-          umma_f16(d_addr, a2_h + ko, b_l + ko, idesc_d2, 1u);
-          umma_f16(d_addr, a2_l + ko, b_h + ko, idesc_d2, 1u);
-          umma_f16(d_addr, a2_m + ko, b_m + ko, idesc_d2, 1u);
+        if (elect_one()) {
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t ko = (uint64_t)(kk * 2);
+            umma_f16(d_addr, a2_h + ko, b_h + ko, idesc_d2, kk > 0 ? 1u : 0u);
+            umma_f16(d_addr, a2_h + ko, b_m + ko, idesc_d2, 1u);
+            umma_f16(d_addr, a2_m + ko, b_h + ko, idesc_d2, 1u);
+            umma_f16(d_addr, a2_h + ko, b_l + ko, idesc_d2, 1u);
+            umma_f16(d_addr, a2_l + ko, b_h + ko, idesc_d2, 1u);
+            umma_f16(d_addr, a2_m + ko, b_m + ko, idesc_d2, 1u);
+          }
+          umma_commit(s.d2_full);
+          umma_commit(s.a2_empty);
         }
-        umma_commit(s.d2_full);
-        umma_commit(s.a2_empty);
-        trace_ev(p, j, 253);
+        __syncwarp();
+        if (lane == 0) trace_ev(p, j, 253);
       };
       int j = 0;
       int tile = blockIdx.x;
       if (tile < p.num_tiles) issue_distance(0);
       for (; tile < p.num_tiles; tile += gridDim.x, ++j) {
         mbar_wait_relaxed(s.d_empty, (uint32_t)((j & 1) ^ 1));  // previous epilogue drained V
-        trace_ev(p, j, 200);
+        if (lane == 0) trace_ev(p, j, 200);
         tc_fence_after();
         for (int c = 0; c < C; ++c) {
           mbar_wait_relaxed(&s.a_full[slot], pha);
-          trace_ev(p, j, 210 + c);
+          if (lane == 0) trace_ev(p, j, 210 + c);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(s.ring_a + (size_t)slot * kSlotABytes);
           const uint64_t a_hi = make_sw128_desc(a_addr), a_lo = make_sw128_desc(a_addr + 16384);
-          // Every SS-form tcgen05.mma re-reads its 128x16 A slice from shared memory (~130 cycles,
-          // four times the math of a 64-column MMA), so adjacent column sub-blocks are issued as one
-          // 128-column MMA wherever the lower-triangular structure allows a pair.
+          // adjacent column sub-blocks are issued as one 128-column MMA wherever the lower-triangular structure
+          // allows a pair
           for (int sb = c; sb < C;) {
             const int g = ((sb & 1) == 0 && sb + 1 < C) ? 2 : 1;
             mbar_wait_relaxed(&s.r_full[rs], rph);
-            trace_ev(p, j, 220 + c * 4 + sb);
+            if (lane == 0) trace_ev(p, j, 220 + c * 4 + sb);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(s.ring_r + (size_t)rs * kRStageBytes);
             const uint64_t b_hi = make_sw128_desc(b_addr), b_lo = make_sw128_desc(b_addr + (uint32_t)g * 8192u);
             const uint32_t d_addr = tmem_base + (uint32_t)(sb * kChunk);
             const uint32_t id = (g == 2) ? idesc128 : idesc;
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ko = (uint64_t)(kk * 2);
-              umma_f16(d_addr, a_hi + ko, b_hi + ko, id, (c > 0 || kk > 0) ? 1u : 0u);
-              umma_f16(d_addr, a_hi + ko, b_lo + ko, id, 1u);
-              umma_f16(d_addr, a_lo + ko, b_hi + ko, id, 1u);
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ko = (uint64_t)(kk * 2);
+                umma_f16(d_addr, a_hi + ko, b_hi + ko, id, (c > 0 || kk > 0) ? 1u : 0u);
+                umma_f16(d_addr, a_hi + ko, b_lo + ko, id, 1u);
+                umma_f16(d_addr, a_lo + ko, b_hi + ko, id, 1u);
+              }
+              umma_commit(&s.r_empty[rs]);
             }
-            umma_commit(&s.r_empty[rs]);
+            __syncwarp();
             if (++rs == (uint32_t)p.stages_b) {
               rs = 0;
               rph ^= 1u;
             }
             sb += g;
           }
-          umma_commit(&s.a_empty[slot]);
-          umma_commit(&s.dsub_full[c]);  // sub-block c of V has received its last contribution
-          trace_ev(p, j, 240 + c);
+          if (elect_one()) {
+            umma_commit(&s.a_empty[slot]);
+            umma_commit(&s.dsub_full[c]);  // sub-block c of V has received its last contribution
+          }
+          __syncwarp();
+          if (lane == 0) trace_ev(p, j, 240 + c);
           if (++slot == (uint32_t)kTcSlotsA) {
             slot = 0;
             pha ^= 1u;

@@ -22,6 +22,10 @@
 //
 // Tensor memory: columns [0, n_pad) V accumulator; [256, 256 + n_pad) D2, overwritten in place by the A operand.
 // Reference path replaced: see fused.cu.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "assemble.cuh"
 #include "fused_common.cuh"
 
@@ -647,6 +651,395 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
   tc_fence_before();
   __syncthreads();
   if (warp == kWarpProducer) tmem_dealloc(tmem_base, 512);
+}
+
+// ============================================================================================================
+// k_kmat_ts -- stand-alone K(X*, X) (bb_kernel_matrix), the HBM-side kernel of the north star.
+// Same front half as k_fused_ts (augmented tcgen05 distance GEMM, packed-f32x2 kernel epilogue); the kernel values
+// go to a 128B-swizzled staging tile in shared memory and leave the SM through the TMA engine: one
+// cp.async.bulk.tensor.2d store (UTMASTG) per 128 x 32 box, addressed through a tensor map that also clips the
+// ragged edges (rows >= N, columns >= n).  D2 is double-buffered in tensor memory (2 x 256 columns) so the distance
+// GEMM of tile t+1 runs under the epilogue of tile t.  Algorithmic bytes: 4d read + 4n written per candidate.
+// ============================================================================================================
+constexpr uint32_t kKmBox = 128u * 128u;   // one TMA box: 128 rows x 32 fp32 = 16 KB
+constexpr uint32_t kKmStage = 2u * kKmBox; // one 64-column chunk of a tile
+
+struct KmSmem {
+  uint8_t *bt, *a2, *out;
+  float *tcov, *cscale_s, *cshift_s, *an_part;
+  int32_t *ttask, *cand_task;
+  uint64_t *d2_full, *d2_empty, *a2_full, *res_full;
+  uint32_t* tmem_ptr;
+};
+
+__host__ __device__ inline size_t km_carve(uint8_t* base, int n_pad, KmSmem* s) {
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t align) {
+    off = (off + align - 1) / align * align;
+    size_t o = off;
+    off += bytes;
+    return o;
+  };
+  const size_t o_bt = take((size_t)3 * n_pad * kTsK2 * 2, 1024);
+  const size_t o_a2 = take((size_t)3 * kTsA2Split, 1024);
+  const size_t o_out = take((size_t)2 * kKmStage, 1024);
+  const size_t o_tt = take((size_t)n_pad * 4, 16);
+  const size_t o_tc = take((size_t)kMaxTasks * kMaxTasks * 4, 16);
+  const size_t o_cs = take(32 * 4, 16), o_sh = take(32 * 4, 16);
+  const size_t o_an = take(4 * kTileM * 4, 16), o_ct = take(2 * kTileM * 4, 16);
+  const size_t o_bar = take(16 * 8, 16), o_misc = take(32, 16);
+  if (s) {
+    s->bt = base + o_bt;
+    s->a2 = base + o_a2;
+    s->out = base + o_out;
+    s->ttask = reinterpret_cast<int32_t*>(base + o_tt);
+    s->tcov = reinterpret_cast<float*>(base + o_tc);
+    s->cscale_s = reinterpret_cast<float*>(base + o_cs);
+    s->cshift_s = reinterpret_cast<float*>(base + o_sh);
+    s->an_part = reinterpret_cast<float*>(base + o_an);
+    s->cand_task = reinterpret_cast<int32_t*>(base + o_ct);
+    uint64_t* b = reinterpret_cast<uint64_t*>(base + o_bar);
+    s->d2_full = b;        // [2]
+    s->d2_empty = b + 2;   // [2]
+    s->a2_full = b + 4;
+    s->res_full = b + 5;
+    s->tmem_ptr = reinterpret_cast<uint32_t*>(base + o_misc);
+  }
+  return off;
+}
+
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int FAMILY, bool TASKS>
+__global__ void __launch_bounds__(kFusedThreads, 1) k_kmat_ts(const FusedParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  KmSmem s;
+  km_carve(smem_raw, p.n_pad, &s);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = p.n_chunks;
+  const uint32_t bt_split = (uint32_t)p.n_pad * kTsK2 * 2u;
+  if (tid == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  if (warp == kWarpMma && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.d2_full[i], 1);
+      mbar_init(&s.d2_empty[i], kComputeWarps);
+    }
+    mbar_init(s.a2_full, kComputeWarps);
+    mbar_init(s.res_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kWarpProducer) {
+    tmem_alloc(s.tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  for (int e = tid; e < (int)(3 * kTsA2Split / 16); e += kFusedThreads)
+    reinterpret_cast<uint4*>(s.a2)[e] = make_uint4(0u, 0u, 0u, 0u);
+  for (int e = tid; e < 32; e += kFusedThreads) {
+    s.cscale_s[e] = e < p.d_pad ? __ldg(p.cand_scale + e) : 0.f;
+    s.cshift_s[e] = e < p.d_pad ? __ldg(p.cand_shift + e) : 0.f;
+  }
+  for (int e = tid; e < p.n_pad; e += kFusedThreads) s.ttask[e] = TASKS ? __ldg(p.train_task + e) : 0;
+  for (int e = tid; e < p.n_tasks * p.n_tasks; e += kFusedThreads) s.tcov[e] = __ldg(p.task_covar + e);
+  for (int e = tid; e < 2 * kTileM; e += kFusedThreads) s.cand_task[e] = 0;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_ptr;
+
+  if (warp < kComputeWarps) {
+    const int row_e = tid & 127, cg = tid >> 7, quarter = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int dq = p.d_pad >> 2;
+    TsConsts cst;
+    {
+      const float g = p.ts_g, ks = (!TASKS && p.scaled) ? s.tcov[0] : 1.0f, sg = sqrtf(g);
+      cst.k0 = pack2(ks, ks);
+      cst.c1 = pack2(ks * sg, ks * sg);
+      cst.c2 = pack2(ks * g * (1.0f / 3.0f), ks * g * (1.0f / 3.0f));
+      const float c3 = (FAMILY == BB_KERNEL_RBF) ? -g : -kLog2e * sg;
+      cst.c3 = pack2(c3, c3);
+    }
+    TsStageRegs regs;
+    auto prefetch = [&](int tile) {
+      const int64_t row = (int64_t)tile * kTileM + row_e;
+      regs.v[0] = (cg < dq) ? ts_load_quad(p, row, cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+      regs.v[1] = (cg + 4 < dq) ? ts_load_quad(p, row, cg + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto stage_a2 = [&](int buf) {  // as in k_fused_ts
+      float an = 0.f;
+      float a7[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int jq = cg + 4 * u;
+        if (jq < dq) {
+          const int j0 = jq * 4;
+          const float4 q = regs.v[u];
+          if (TASKS && p.task_col >= j0 && p.task_col < j0 + 4) {
+            const float tv = (p.task_col == j0) ? q.x : (p.task_col == j0 + 1) ? q.y : (p.task_col == j0 + 2) ? q.z : q.w;
+            s.cand_task[buf * kTileM + row_e] = min(max(__float2int_rn(tv), 0), p.n_tasks - 1);
+          }
+          float a[4];
+          a[0] = fmaf(q.x, s.cscale_s[j0], s.cshift_s[j0]);
+          a[1] = fmaf(q.y, s.cscale_s[j0 + 1], s.cshift_s[j0 + 1]);
+          a[2] = fmaf(q.z, s.cscale_s[j0 + 2], s.cshift_s[j0 + 2]);
+          a[3] = fmaf(q.w, s.cscale_s[j0 + 3], s.cshift_s[j0 + 3]);
+          an = fmaf(a[0], a[0], fmaf(a[1], a[1], fmaf(a[2], a[2], fmaf(a[3], a[3], an))));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a[e] *= p.ts_sa;
+          if (jq == 7) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a7[e] = a[e];
+          } else {
+            uint2 hi, mid, lo;
+            split3_quad(a, hi, mid, lo);
+            const uint32_t off = swk_offset<kTsK2>((uint32_t)row_e, (uint32_t)(jq >> 1)) + (uint32_t)(jq & 1) * 8u;
+            *reinterpret_cast<uint2*>(s.a2 + off) = hi;
+            *reinterpret_cast<uint2*>(s.a2 + kTsA2Split + off) = mid;
+            *reinterpret_cast<uint2*>(s.a2 + 2 * kTsA2Split + off) = lo;
+          }
+        }
+      }
+      s.an_part[cg * kTileM + row_e] = an;
+      if (cg != 3) {
+        bar_quarter_arrive(2 + quarter);
+      } else {
+        bar_quarter_sync(2 + quarter);
+        const float asq = (s.an_part[row_e] + s.an_part[kTileM + row_e]) +
+                          (s.an_part[2 * kTileM + row_e] + s.an_part[3 * kTileM + row_e]);
+        a7[kTsColSq - 28] = asq * p.ts_aug_sq;
+        a7[kTsColOne - 28] = p.ts_aug_one;
+        uint2 hi, mid, lo;
+        split3_quad(a7, hi, mid, lo);
+        const uint32_t off = swk_offset<kTsK2>((uint32_t)row_e, 3u) + 8u;
+        *reinterpret_cast<uint2*>(s.a2 + off) = hi;
+        *reinterpret_cast<uint2*>(s.a2 + kTsA2Split + off) = mid;
+        *reinterpret_cast<uint2*>(s.a2 + 2 * kTsA2Split + off) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s.a2_full);
+    };
+
+    int it = 0, chunk_no = 0;
+    int tile = blockIdx.x;
+    if (tile < p.num_tiles) {
+      prefetch(tile);
+      stage_a2(0);
+      if (tile + (int)gridDim.x < p.num_tiles) prefetch(tile + gridDim.x);
+    }
+    for (; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int slot = it & 1;
+      mbar_wait(&s.d2_full[slot], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      // this tile's distance GEMM has consumed A2: stage the next tile so that ITS GEMM runs under this epilogue
+      const int next = tile + (int)gridDim.x;
+      if (next < p.num_tiles) {
+        stage_a2((it + 1) & 1);
+        if (next + (int)gridDim.x < p.num_tiles) prefetch(next + gridDim.x);
+      }
+      const int ct = TASKS ? s.cand_task[(it & 1) * kTileM + row_e] : 0;
+      const float* tcrow = s.tcov + ct * p.n_tasks;
+      for (int c = 0; c < C; ++c, ++chunk_no) {
+        float v[16];
+        tmem_ld16(tmem_base + lane_base + (uint32_t)(slot * 256 + c * kChunk + cg * 16), v);
+        tmem_ld_wait();
+        if (c == C - 1) {  // all of D2 is in registers: the distance GEMM of tile t+2 may overwrite this slot
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.d2_empty[slot]);
+        }
+        const int i0 = c * kChunk + cg * 16;
+        uint8_t* box = s.out + (size_t)(chunk_no & 1) * kKmStage + (size_t)(cg >> 1) * kKmBox + (size_t)row_e * 128u;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          unsigned long long k01 = ts_kernel_pair<FAMILY>(v[4 * q4], v[4 * q4 + 1], cst);
+          unsigned long long k23 = ts_kernel_pair<FAMILY>(v[4 * q4 + 2], v[4 * q4 + 3], cst);
+          if constexpr (TASKS) {
+            k01 = mul2(k01, pack2(tcrow[s.ttask[i0 + 4 * q4]], tcrow[s.ttask[i0 + 4 * q4 + 1]]));
+            k23 = mul2(k23, pack2(tcrow[s.ttask[i0 + 4 * q4 + 2]], tcrow[s.ttask[i0 + 4 * q4 + 3]]));
+          }
+          const uint32_t chunk16 = (uint32_t)(((cg & 1) * 4 + q4) ^ (row_e & 7));  // SWIZZLE_128B
+          *reinterpret_cast<float4*>(box + chunk16 * 16u) = make_float4(lo_of(k01), hi_of(k01), lo_of(k23), hi_of(k23));
+        }
+        fence_proxy_async();            // generic-proxy writes -> visible to the TMA engine
+        if (tid == 0) tma_wait_read0(); // the store that last read the OTHER buffer (one chunk ago) has drained it
+        bar_compute();
+        if (tid == 0) {
+          const uint8_t* src = s.out + (size_t)(chunk_no & 1) * kKmStage;
+          const int y = tile * kTileM;  // row coordinate; int32 limits N to 2^31 rows
+          tma_store_2d(&tmap, src, c * kChunk, y);
+          tma_store_2d(&tmap, src + kKmBox, c * kChunk + 32, y);
+          tma_commit_group();
+        }
+      }
+    }
+    if (tid == 0) tma_wait_all();  // global writes complete before the CTA exits
+  } else if (warp == kWarpProducer) {
+    if (elect_one()) {
+      uint32_t left = 3u * bt_split;
+      mbar_expect_tx(s.res_full, left);
+      for (uint32_t o = 0; left > 0;) {
+        const uint32_t n = left < 32768u ? left : 32768u;
+        bulk_g2s(s.bt + o, p.timg_b + o, n, s.res_full);
+        o += n;
+        left -= n;
+      }
+    }
+    __syncwarp();
+  } else {
+    const uint32_t idesc_d2 = make_idesc_f16(kTileM, p.n_pad);
+    const uint32_t a2_addr = smem_u32(s.a2), bt_addr = smem_u32(s.bt);
+    const uint64_t a2_h = make_swk_desc<kTsK2>(a2_addr), a2_m = make_swk_desc<kTsK2>(a2_addr + kTsA2Split),
+                   a2_l = make_swk_desc<kTsK2>(a2_addr + 2 * kTsA2Split);
+    const uint64_t b_h = make_swk_desc<kTsK2>(bt_addr), b_m = make_swk_desc<kTsK2>(bt_addr + bt_split),
+                   b_l = make_swk_desc<kTsK2>(bt_addr + 2 * bt_split);
+    mbar_wait_relaxed(s.res_full, 0u);
+    int j = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+      const int slot = j & 1;
+      mbar_wait_relaxed(s.a2_full, (uint32_t)(j & 1));
+      if (j >= 2) mbar_wait_relaxed(&s.d2_empty[slot], (uint32_t)(((j >> 1) - 1) & 1));
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + (uint32_t)(slot * 256);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kTsK2 / 16; ++kk) {
+          const uint64_t ko = (uint64_t)(kk * 2);
+          umma_f16(d_addr, a2_h + ko, b_h + ko, idesc_d2, kk > 0 ? 1u : 0u);
+          umma_f16(d_addr, a2_h + ko, b_m + ko, idesc_d2, 1u);
+          umma_f16(d_addr, a2_m + ko, b_h + ko, idesc_d2, 1u);
+          umma_f16(d_addr, a2_h + ko, b_l + ko, idesc_d2, 1u);
+          umma_f16(d_addr, a2_l + ko, b_h + ko, idesc_d2, 1u);
+          umma_f16(d_addr, a2_m + ko, b_m + ko, idesc_d2, 1u);
+        }
+        umma_commit(&s.d2_full[slot]);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpProducer) tmem_dealloc(tmem_base, 512);
+}
+
+bool kmat_ts_supported(const FusedParams& p, const float* d_k, int64_t ldk, int max_smem) {
+  if (p.timg_b == nullptr || p.n_pad > 256 || p.d > kTsColSq || p.family == BB_KERNEL_MATERN12) return false;
+  if (p.n_tasks > kMaxTasks || p.N >= (1ll << 31)) return false;
+  if ((reinterpret_cast<uintptr_t>(d_k) & 15u) != 0 || (ldk & 3) != 0) return false;  // TMA: 16-byte aligned base / row pitch
+  return km_carve(nullptr, p.n_pad, nullptr) + 1024 <= (size_t)max_smem;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int FAMILY, bool TASKS>
+static int launch_km_one(FusedParams& p, const CUtensorMap& tm, int grid, size_t smem, cudaStream_t stream) {
+  static int configured_for = -1;
+  int dev = 0;
+  BB_CUDA(cudaGetDevice(&dev));
+  if (configured_for != dev) {
+    BB_CUDA(cudaFuncSetAttribute(k_kmat_ts<FAMILY, TASKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured_for = dev;
+  }
+  k_kmat_ts<FAMILY, TASKS><<<grid, kFusedThreads, smem, stream>>>(p, tm);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+// K(X*, X) -> d_k [N, ldk] (columns >= n untouched); returns BB_ERR_UNSUPPORTED if the driver lacks tensor maps.
+int launch_kmat_ts(FusedParams& p, float* d_k, int64_t ldk, int n_cols, int grid, cudaStream_t stream) {
+  static EncodeTiledFn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    BB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    BB_CHECK_SUPPORTED(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)n_cols, (cuuint64_t)p.N};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ldk * 4};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_k, gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return BB_ERR_CUDA;
+  }
+  const size_t smem = km_carve(nullptr, p.n_pad, nullptr) + 1024;
+  const bool tasks = p.task_col >= 0;
+  switch (p.family) {
+    case BB_KERNEL_MATERN32:
+      return tasks ? launch_km_one<BB_KERNEL_MATERN32, true>(p, tm, grid, smem, stream)
+                   : launch_km_one<BB_KERNEL_MATERN32, false>(p, tm, grid, smem, stream);
+    case BB_KERNEL_MATERN52:
+      return tasks ? launch_km_one<BB_KERNEL_MATERN52, true>(p, tm, grid, smem, stream)
+                   : launch_km_one<BB_KERNEL_MATERN52, false>(p, tm, grid, smem, stream);
+    default:
+      return tasks ? launch_km_one<BB_KERNEL_RBF, true>(p, tm, grid, smem, stream)
+                   : launch_km_one<BB_KERNEL_RBF, false>(p, tm, grid, smem, stream);
+  }
+}
+
+// bb_kernel_matrix front door: *handled = false when the shape / alignment is outside this kernel's envelope.
+int try_kmat_ts(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx, float* d_k, int64_t ldk,
+                cudaStream_t stream, bool* handled) {
+  *handled = false;
+  if (m->d_timg_b == nullptr || layout == BB_BITS_U8) return BB_OK;
+  static const bool off = [] {
+    const char* e = getenv("BB_FORCE_KERNEL");
+    return e != nullptr && e[0] == 't' && e[1] == 'c';
+  }();
+  if (off) return BB_OK;
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = d_x;
+  p.layout = layout;
+  p.N = N;
+  p.ldx = ldx;
+  p.num_tiles = (int)((N + kTileM - 1) / kTileM);
+  p.cand_scale = m->d_cand_scale;
+  p.cand_shift = m->d_cand_shift;
+  p.task_covar = m->d_task_covar;
+  p.train_task = m->d_train_task;
+  p.family = m->family;
+  p.n_pad = m->n_pad;
+  p.d = m->d;
+  p.d_pad = m->d_pad;
+  p.n_chunks = m->n_chunks;
+  p.task_col = m->task_col;
+  p.n_tasks = m->n_tasks;
+  p.scaled = (m->task_col >= 0 || m->prior_scale != 1.0f) ? 1 : 0;
+  p.timg_b = reinterpret_cast<const uint8_t*>(m->d_timg_b);
+  p.ts_sa = m->ts_sa;
+  p.ts_aug_sq = m->ts_aug_sq;
+  p.ts_aug_one = m->ts_aug_one;
+  p.ts_g = m->ts_g;
+  p.ts_kscale = 1.0f;
+  static int sms = 0, max_smem = 0, cached_dev = -1;  // device attributes once per device, not per call
+  int dev = 0;
+  BB_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cached_dev = dev;
+  }
+  if (!kmat_ts_supported(p, d_k, ldk, max_smem)) return BB_OK;
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  const int rc = launch_kmat_ts(p, d_k, ldk, m->n, grid, stream);
+  if (rc == BB_OK) *handled = true;
+  return rc == BB_ERR_UNSUPPORTED ? BB_OK : rc;
 }
 
 // Shape envelope of this kernel; everything else runs fused_tc.cu / fused.cu.

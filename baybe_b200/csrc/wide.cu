@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_kmat_tc(const WideParams p
     // =====================================================================================
     // producer: one bulk copy (TMA engine) per K stage of the B image
     // =====================================================================================
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: straight UBLKCP (fused_common.cuh)
       uint32_t st = 0, ph = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int half = item % p.n_halves;
@@ -348,8 +348,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_kmat_tc(const WideParams p
   } else {
     // =====================================================================================
     // MMA issuer: D[m] (128 x ncols, fp32, TMEM) += A_panel[m] (128 x 32) * B_panel^T
+    // converged warp, one lane issues under elect.sync (no ELECT/R2UR/BRA.U.ANY wrapper per MMA, fused_common.cuh)
     // =====================================================================================
-    if (lane == 0) {
+    {
       uint32_t st = 0, ph = 0;
       int it = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
@@ -365,36 +366,40 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_kmat_tc(const WideParams p
           const uint32_t a_base = smem_u32(s.ring + (size_t)st * kStage), b_base = a_base + kStageA;
           const uint64_t b_h = make_swk_desc<kWK>(b_base), b_m = make_swk_desc<kWK>(b_base + bsplit),
                          b_l = make_swk_desc<kWK>(b_base + (PB > 2 ? 2 : 0) * bsplit);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const uint64_t ko = (uint64_t)(kk * 2);  // 16 fp16 = 32 bytes
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t ko = (uint64_t)(kk * 2);  // 16 fp16 = 32 bytes
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              const uint32_t d_addr = tmem_base + (uint32_t)(m * kWHalfN);
-              const uint32_t a_m0 = a_base + (uint32_t)m * (128u * kWK * 2);
-              const uint32_t acc = (kc > 0 || kk > 0) ? 1u : 0u;
-              const uint64_t a_h = make_swk_desc<kWK>(a_m0);
-              if constexpr (BITS) {
-                umma_f16(d_addr, a_h + ko, b_h + ko, idesc, acc);
-                umma_f16(d_addr, a_h + ko, b_m + ko, idesc, 1u);
-              } else {
-                const uint64_t a_md = make_swk_desc<kWK>(a_m0 + kWPanelA), a_l = make_swk_desc<kWK>(a_m0 + 2 * kWPanelA);
-                umma_f16(d_addr, a_h + ko, b_h + ko, idesc, acc);
-                umma_f16(d_addr, a_h + ko, b_m + ko, idesc, 1u);
-                umma_f16(d_addr, a_md + ko, b_h + ko, idesc, 1u);
-                umma_f16(d_addr, a_h + ko, b_l + ko, idesc, 1u);
-                umma_f16(d_addr, a_l + ko, b_h + ko, idesc, 1u);
-                umma_f16(d_addr, a_md + ko, b_m + ko, idesc, 1u);
+              for (int m = 0; m < 2; ++m) {
+                const uint32_t d_addr = tmem_base + (uint32_t)(m * kWHalfN);
+                const uint32_t a_m0 = a_base + (uint32_t)m * (128u * kWK * 2);
+                const uint32_t acc = (kc > 0 || kk > 0) ? 1u : 0u;
+                const uint64_t a_h = make_swk_desc<kWK>(a_m0);
+                if constexpr (BITS) {
+                  umma_f16(d_addr, a_h + ko, b_h + ko, idesc, acc);
+                  umma_f16(d_addr, a_h + ko, b_m + ko, idesc, 1u);
+                } else {
+                  const uint64_t a_md = make_swk_desc<kWK>(a_m0 + kWPanelA), a_l = make_swk_desc<kWK>(a_m0 + 2 * kWPanelA);
+                  umma_f16(d_addr, a_h + ko, b_h + ko, idesc, acc);
+                  umma_f16(d_addr, a_h + ko, b_m + ko, idesc, 1u);
+                  umma_f16(d_addr, a_md + ko, b_h + ko, idesc, 1u);
+                  umma_f16(d_addr, a_h + ko, b_l + ko, idesc, 1u);
+                  umma_f16(d_addr, a_l + ko, b_h + ko, idesc, 1u);
+                  umma_f16(d_addr, a_md + ko, b_m + ko, idesc, 1u);
+                }
               }
             }
+            umma_commit(&s.empty[st]);
           }
-          umma_commit(&s.empty[st]);
+          __syncwarp();
           if (++st == (uint32_t)p.stages) {
             st = 0;
             ph ^= 1u;
           }
         }
-        umma_commit(s.acc_full);
+        if (elect_one()) umma_commit(s.acc_full);
+        __syncwarp();
       }
     }
   }

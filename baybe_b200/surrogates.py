@@ -197,6 +197,23 @@ class _Posterior:
         return self.mean + self.variance.sqrt() * z.to(self.mean.dtype)
 
 
+class _JointPosterior:
+    """Joint posterior of one q-batch: ``mean`` (1, q, 1), ``variance`` (1, q, 1), ``covariance`` (q, q) -- the
+    attributes BayBE reads from ``GPyTorchPosterior`` (``mean``, ``variance``, ``mvn.covariance_matrix``)."""
+
+    def __init__(self, mean: torch.Tensor, cov: torch.Tensor):
+        q = mean.numel()
+        self.mean = mean.reshape(1, q, 1)
+        self.covariance = cov.reshape(q, q)
+        self.variance = torch.diagonal(self.covariance).reshape(1, q, 1)
+
+    @property
+    def mvn(self):
+        return torch.distributions.MultivariateNormal(
+            self.mean.reshape(-1).double().cpu(),
+            covariance_matrix=self.covariance.double().cpu() + 1e-9 * torch.eye(self.covariance.shape[0], dtype=torch.float64))
+
+
 @define
 class GaussianProcessSurrogate:
     """GP surrogate whose posterior runs on the B200 engine."""
@@ -296,13 +313,21 @@ class GaussianProcessSurrogate:
         if self.device_gp is None or self._searchspace is None:
             raise ModelNotTrainedError("The surrogate must be trained before a posterior can be computed.")
 
-    def posterior(self, candidates: pd.DataFrame, *, joint: bool = False) -> _Posterior:
+    def posterior(self, candidates: pd.DataFrame, *, joint: bool = False):
         """Posterior at candidates given in experimental representation (surrogates/base.py:213-247).
-        Only the marginal (``joint=False``, t-batch) form is on the fast path."""
+        ``joint=False``: marginal posteriors of all rows (t-batch; the scoring path).  ``joint=True``: ONE q-batch
+        posterior with the full (q, q) covariance, computed in float64 on the device (``bb_pending_stats``, the
+        routine that conditions sequential-greedy rounds on their pending points) for q <= 31."""
         self._require_fit()
-        if joint:
-            raise NotImplementedError("joint q-batch posteriors are outside the B200 fast path")
         comp = self._searchspace.transform(candidates, allow_extra=True)
+        if joint:
+            from baybe_b200._lib import MAX_PENDING
+
+            if len(comp) > MAX_PENDING:
+                raise NotImplementedError(f"joint posteriors are implemented for q <= {MAX_PENDING} points "
+                                          f"(got {len(comp)}); use joint=False for marginals of a large set")
+            _, _, mean, cov = self.device_gp.pending_stats(comp.to_numpy(dtype=np.float64, copy=True))
+            return _JointPosterior(mean, cov)
         return self._posterior_comp(torch.from_numpy(comp.to_numpy(dtype=np.float64, copy=True)))
 
     def _posterior_comp(self, candidates_comp: torch.Tensor) -> _Posterior:

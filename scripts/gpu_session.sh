@@ -1,0 +1,46 @@
+#!/bin/bash
+# One GPU lease, several independent stages, each bounded by `timeout` so that a hanging kernel costs one stage and
+# not the call.  Everything lands in gpurun_out/.
+# usage: scripts/gpu_session.sh [stage ...]   (default: all)
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+STAGES=${@:-"ubench light tests bench ncu sanitizer"}
+OUT=gpurun_out
+for st in $STAGES; do
+  echo "=== stage $st $(date +%T) ==="
+  case $st in
+    ubench)
+      timeout 100 scripts/ubench/mma_rate 1 > $OUT/mma_rate_cg1.txt 2>&1; echo "rc=$?" >> $OUT/mma_rate_cg1.txt
+      timeout 100 scripts/ubench/mma_rate 2 > $OUT/mma_rate_cg2.txt 2>&1; echo "rc=$?" >> $OUT/mma_rate_cg2.txt
+      grep -E "elect=1|rc=" $OUT/mma_rate_cg1.txt | grep -E "bg=0|rc=" ;;
+    light)
+      timeout 200 python scripts/ts_first_light.py > $OUT/ts_first_light.txt 2>&1; echo "light rc=$?"
+      tail -45 $OUT/ts_first_light.txt ;;
+    tests)
+      if grep -q FIRST_LIGHT_DONE $OUT/ts_first_light.txt 2>/dev/null; then FK=""; else FK="tc"; echo "TS kernel not healthy: tests run with BB_FORCE_KERNEL=tc"; fi
+      BB_FORCE_KERNEL=$FK timeout 1200 python -m pytest tests -m gpu -q --timeout 300 --timeout-method thread -p no:cacheprovider > $OUT/pytest_gpu.txt 2>&1; echo "tests rc=$?"
+      tail -60 $OUT/pytest_gpu.txt ;;
+    bench)
+      timeout 600 python bench.py --steps 10 --warmup 3 > $OUT/bench_n1.json 2> $OUT/bench_n1.err; echo "bench rc=$?"
+      cat $OUT/bench_n1.json | cut -c1-3000; tail -5 $OUT/bench_n1.err ;;
+    benchtc)
+      BB_FORCE_KERNEL=tc timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_n1_tc.json 2> $OUT/bench_n1_tc.err; echo "bench rc=$?"
+      cat $OUT/bench_n1_tc.json | cut -c1-1500 ;;
+    ncu)
+      timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1; echo "ncu list rc=$?"
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_fused_ts -s 3 -c 1 -f -o $OUT/prof_fused_ts_r02 python scripts/profile_target.py fused > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+      tail -3 $OUT/ncu_full.log ;;
+    sanitizer)
+      timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python scripts/ts_first_light.py n64_d4 cfg1 task4 > $OUT/r02_sanitizer_memcheck.txt 2>&1; echo "memcheck rc=$?"
+      tail -8 $OUT/r02_sanitizer_memcheck.txt
+      timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python scripts/ts_first_light.py n64_d4 cfg1 > $OUT/r02_sanitizer_racecheck.txt 2>&1; echo "racecheck rc=$?"
+      tail -8 $OUT/r02_sanitizer_racecheck.txt ;;
+    bench2)
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > $OUT/bench_n2.json 2> $OUT/bench_n2.err; echo "bench2 rc=$?"
+      cat $OUT/bench_n2.json | cut -c1-3000; tail -15 $OUT/bench_n2.err ;;
+    tests2)
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 scripts/multi_gpu_check.py > $OUT/multi_gpu_check.txt 2>&1; echo "tests2 rc=$?"
+      tail -30 $OUT/multi_gpu_check.txt ;;
+  esac
+done
+echo "=== done $(date +%T) ==="

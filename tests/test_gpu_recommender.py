@@ -90,6 +90,67 @@ def test_posterior_stats_and_acquisition_values(cuda_device):
     torch.manual_seed(5)
     acqv = rec.acquisition_values(cands, ss, obj, meas)
     assert isinstance(acqv, pd.Series) and acqv.index.equals(cands.index) and np.isfinite(acqv).all()
+    # per-row values against the oracle with the same sampler seed (a14: acquisition/base.py:112-159)
+    torch.manual_seed(5)
+    seed = int(torch.randint(0, 1_000_000, (1,)))
+    oacq = oracle.AcqSpec("qLogEI")
+    oacq.best_f = oracle.best_f_from_training(om, ss.transform(meas).to_numpy(), oacq)
+    z = oracle.sobol_normal_samples(512, 1, seed)[:, 0]
+    from tests.helpers import score_bounds
+
+    ref, bound = score_bounds(om, oacq, ss.transform(cands).to_numpy(), z)
+    err = np.abs(acqv.to_numpy() - ref.numpy())
+    assert (err <= bound.numpy()).all(), float(err.max())
+
+
+def test_joint_posterior_of_a_small_batch(cuda_device):
+    """Surrogate.posterior(candidates, joint=True) (surrogates/base.py:213-247): mean and FULL covariance of one
+    q-batch against the oracle's joint posterior."""
+    ss = _space()
+    meas = _measure(ss, 15, seed=6)
+    obj = SingleTargetObjective(NumericalTarget("Yield"))
+    sur = GaussianProcessSurrogate(hyperparameters=HP)
+    sur.fit(ss, obj, meas)
+    batch = ss.discrete.exp_rep.iloc[[3, 50, 51, 120, 191]]
+    post = sur.posterior(batch, joint=True)
+    om = _oracle_model(ss, meas, HP)
+    m_ref, cov_ref = oracle.posterior_joint(om, ss.transform(batch).to_numpy())
+    assert post.mean.shape == (1, 5, 1) and post.covariance.shape == (5, 5)
+    assert np.allclose(post.mean.reshape(-1).double().cpu().numpy(), m_ref.numpy(), rtol=1e-5, atol=1e-3)
+    scale = float(cov_ref.diagonal().max())
+    assert np.abs(post.covariance.double().cpu().numpy() - cov_ref.numpy()).max() <= 2e-4 * scale
+    assert np.allclose(post.variance.reshape(-1).double().cpu().numpy(), cov_ref.diagonal().numpy(), rtol=1e-3, atol=2e-4 * scale)
+    _ = post.mvn  # a valid multivariate normal
+    with pytest.raises(NotImplementedError):
+        sur.posterior(ss.discrete.exp_rep.iloc[:40], joint=True)
+
+
+def test_filtered_candidate_set_becomes_a_position_mask(cuda_device):
+    """a1/a2: ``Campaign.recommend`` hands the recommender a FilteredSubspaceDiscrete whose get_candidates() returns
+    ``exp_rep.loc[mask]`` (campaign.py:549-572, _filtered.py:41-43).  The engine must only pick rows of that subset,
+    and pick the best of THEM."""
+    ss = _space()
+    meas = _measure(ss, 15, seed=3)
+    obj = SingleTargetObjective(NumericalTarget("Yield"))
+    rec = B200Recommender(surrogate_model=GaussianProcessSurrogate(hyperparameters=HP))
+    torch.manual_seed(11)
+    full = rec.recommend(1, ss, obj, meas)
+    torch.manual_seed(11)
+    vals = rec.acquisition_values(ss.discrete.exp_rep, ss, obj, meas)
+    assert full.index[0] == vals.idxmax()
+    # drop the 40 best rows and every third row: the recommendation must be the best remaining one
+    drop = set(vals.sort_values(ascending=False).index[:40]) | set(ss.discrete.exp_rep.index[::3])
+    mask = ~ss.discrete.exp_rep.index.isin(list(drop))
+    candidates_exp = ss.discrete.exp_rep.loc[mask]
+    surrogate = rec.get_surrogate(ss, obj, meas)
+    cfg = rec._get_acquisition_function(obj).to_engine(surrogate, ss, obj, meas, None)
+    rec._context = (cfg, ss, None)
+    torch.manual_seed(11)
+    idxs = rec._recommend_discrete(ss.discrete, candidates_exp, 3)
+    assert set(idxs) <= set(candidates_exp.index) and len(set(idxs)) == 3
+    assert idxs[0] == vals.loc[candidates_exp.index].idxmax()
+    with pytest.raises(ValueError):
+        rec._recommend_discrete(ss.discrete, candidates_exp.rename(index={candidates_exp.index[0]: 10**9}), 1)
 
 
 def test_fit_is_cached_and_refit_on_new_data(cuda_device):
