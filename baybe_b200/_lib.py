@@ -14,6 +14,7 @@ ABI_VERSION = 2
 # enums (mirror include/baybe_b200.h)
 KERNEL_FAMILY = {"matern12": 0, "matern32": 1, "matern52": 2, "rbf": 3}
 LAYOUT = {"row_f32": 0, "col_f32": 1, "row_f64": 2, "col_f64": 3, "bits_u8": 4}
+HOST_FORMAT = {"rows_f32": 0, "rows_f64": 1, "codes4": 2, "codes8": 3}
 ACQ_KIND = {
     "qLogEI": 0, "qEI": 1, "qUCB": 2, "qSR": 3, "qPI": 4,
     "UCB": 5, "EI": 6, "LogEI": 7, "PI": 8, "PM": 9, "PSTD": 10,
@@ -111,6 +112,8 @@ _SIGNATURES = {
     "bb_argmax": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "bb_best_decode": (C.c_int, [_vp, _vp, _vp]),
     "bb_topk": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "bb_score_fused_host": (C.c_int, [C.POINTER(Model), C.POINTER(AcqSpec), _vp, _i32, _i64, _i64, _vp, _i32,
+                                      C.POINTER(_vp), C.POINTER(_vp), _i64, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     "bb_decode_codes": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
     "bb_peer_slots_init": (C.c_int, [_vp, _vp, _vp]),
     "bb_allreduce_best": (C.c_int, [C.POINTER(PeerGroup), _vp, C.c_uint32, _vp, _vp, _vp]),

@@ -760,7 +760,7 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
     const char* e = getenv("BB_FORCE_KERNEL");
     return e != nullptr && e[0] == 't' && e[1] == 'c';
   }();
-  if (!ts_off && g_trace_buf == nullptr && fused_ts_supported(p, max_smem)) {  // headline kernel (fused_ts.cu); tracing is a fused_tc feature
+  if (!ts_off && fused_ts_supported(p, max_smem)) {  // headline kernel (fused_ts.cu)
     const int grid_ts = p.num_tiles < sms ? p.num_tiles : sms;
     return launch_fused_ts(p, grid_ts, stream);
   }

@@ -98,10 +98,10 @@ __host__ __device__ inline size_t ts_carve(uint8_t* base, int n_pad, int n_tasks
     s->vsub_full = b + 4;   // [4]
     s->r_full = b + 8;      // [kTsLoStages]
     s->r_empty = b + 12;    // [kTsLoStages]
-    s->d2_full = b + 16;
-    s->a2_full = b + 17;
-    s->v_empty = b + 18;
-    s->res_full = b + 19;
+    s->d2_full = b + 16;    // [2]: one per 128-column D2 slab
+    s->a2_full = b + 18;
+    s->v_empty = b + 19;
+    s->res_full = b + 20;
     s->best_red = reinterpret_cast<long long*>(base + o_best);
     s->tmem_ptr = reinterpret_cast<uint32_t*>(base + o_misc);
     s->zstat = reinterpret_cast<float*>(base + o_misc + 8);
@@ -149,6 +149,23 @@ __device__ __forceinline__ float h_hi_f32(uint32_t h2) {
 }
 __device__ __forceinline__ void bar_quarter_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_quarter_arrive(int id) { asm volatile("bar.arrive %0, 128;" ::"r"(id) : "memory"); }
+
+// Test-only pipeline trace without atomics (the atomicAdd of trace_ev costs ~700 cycles per event and distorts what
+// it measures): the compute thread 0 and the MMA lane 0 of CTA 0 each append (code, clock) pairs to their own half
+// of the buffer with plain stores; slot 0 of the buffer is set to the capacity at the end (unused pairs stay zero).
+template <bool TRACE>
+__device__ __forceinline__ void ts_trace(const FusedParams& p, int half, int& n, int it, int ev) {
+  if constexpr (!TRACE) return;
+  if (p.trace != nullptr && blockIdx.x == 0 && it >= 6 && it < 9) {
+    const int cap2 = p.trace_cap >> 1;
+    if (n < cap2) {
+      const int i = half * cap2 + n;
+      p.trace[1 + 2 * i] = (long long)it * 1000 + ev;
+      p.trace[2 + 2 * i] = clock64();
+      ++n;
+    }
+  }
+}
 
 struct TsStageRegs {
   float4 v[2];
@@ -212,7 +229,7 @@ __device__ __forceinline__ unsigned long long ts_kernel_pair(float d0, float d1,
   }
 }
 
-template <int FAMILY, bool TASKS>
+template <int FAMILY, bool TASKS, bool TRACE>
 __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TsSmem s;
@@ -233,7 +250,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
       mbar_init(&s.r_full[i], 1);
       mbar_init(&s.r_empty[i], 1);
     }
-    mbar_init(s.d2_full, 1);
+    mbar_init(&s.d2_full[0], 1);
+    mbar_init(&s.d2_full[1], 1);
     mbar_init(s.a2_full, kComputeWarps);
     mbar_init(s.v_empty, kComputeWarps);
     mbar_init(s.res_full, 1);
@@ -364,55 +382,82 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
     };
 
     const bool is_mc = p.has_acq && p.acq.kind <= BB_ACQ_QPI;
+    // One K* chunk: D2 (TMEM) -> kernel values -> fp16 hi/lo written over the same TMEM columns; returns the
+    // chunk's contribution to sum_i k_i alpha_i in `mean2`.
+    int trace_it = 0, trace_n = 0;  // test-only event trace: tile counter the next events are filed under
+    auto convert_chunk = [&](int c, int buf, unsigned long long& mean2) {
+      float v[16];
+      const uint32_t col = kTsD2Col0 + (uint32_t)(c * kChunk + cg * 16);
+      tmem_ld16(tmem_base + lane_base + col, v);
+      tmem_ld_wait();
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 100 + c);
+      const int i0 = c * kChunk + cg * 16;
+      const float* tcrow = s.tcov + (TASKS ? s.cand_task[buf * kTileM + row_e] : 0) * p.n_tasks;
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        unsigned long long k2 = ts_kernel_pair<FAMILY>(v[2 * e], v[2 * e + 1], cst);
+        if constexpr (TASKS) k2 = mul2(k2, pack2(tcrow[s.ttask[i0 + 2 * e]], tcrow[s.ttask[i0 + 2 * e + 1]]));
+        const float2 al = *reinterpret_cast<const float2*>(s.alpha_s + i0 + 2 * e);
+        mean2 = fma2(k2, pack2(al.x, al.y), mean2);
+        const uint32_t h = pack_h2(lo_of(k2), hi_of(k2));
+        const unsigned long long r2 = fma2(pack2(h_lo_f32(h), h_hi_f32(h)), pack2(-1.0f, -1.0f), k2);  // exact
+        hi[e] = h;
+        lo[e] = pack_h2(lo_of(r2), hi_of(r2));
+      }
+      tmem_st8(tmem_base + lane_base + col, hi);
+      tmem_st8(tmem_base + lane_base + col + 8u, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.a_full[c]);
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 110 + c);
+    };
+    // Schedule (software-pipelined over tiles; D2 lives in two 128-column slabs = chunks {0,1} and {2,3}):
+    //   iteration t:  [slab 1 of tile t ready]  stage A2(t+1), convert chunks 2,3 of tile t
+    //                 [slab 0 of tile t+1 ready] convert chunks 0,1 of tile t+1      <- runs under V(t) on the tensor pipe
+    //                 epilogue + acquisition of tile t
+    // so the tensor pipe sees V(t,c0) V(t,c1) DIST(t+1,slab0) V(t,c2) V(t,c3) DIST(t+1,slab1) back to back.
+    const int C0 = C < 2 ? C : 2;  // chunks in slab 0
     int it = 0;
     int tile = blockIdx.x;
+    unsigned long long mean_cur = 0ull;  // mean partial of the tile whose upper chunks are converted next
     if (tile < p.num_tiles) {
       prefetch(tile);
       stage_a2(0);
       if (tile + (int)gridDim.x < p.num_tiles) prefetch(tile + gridDim.x);
+      mbar_wait(&s.d2_full[0], 0u);
+      tc_fence_after();
+      for (int c = 0; c < C0; ++c) convert_chunk(c, 0, mean_cur);
     }
     for (; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t par = (uint32_t)(it & 1);
       const int64_t row0 = (int64_t)tile * kTileM;
-      // ---- K* chunk by chunk: D2 (TMEM) -> kernel values -> fp16 hi/lo, written over the same TMEM columns ----
-      mbar_wait(s.d2_full, par);
-      tc_fence_after();
-      const int ct = TASKS ? s.cand_task[buf * kTileM + row_e] : 0;
-      const float* tcrow = s.tcov + ct * p.n_tasks;
-      unsigned long long mean2 = 0ull;
-      for (int c = 0; c < C; ++c) {
-        float v[16];
-        const uint32_t col = kTsD2Col0 + (uint32_t)(c * kChunk + cg * 16);
-        tmem_ld16(tmem_base + lane_base + col, v);
-        tmem_ld_wait();
-        const int i0 = c * kChunk + cg * 16;
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          unsigned long long k2 = ts_kernel_pair<FAMILY>(v[2 * e], v[2 * e + 1], cst);
-          if constexpr (TASKS) k2 = mul2(k2, pack2(tcrow[s.ttask[i0 + 2 * e]], tcrow[s.ttask[i0 + 2 * e + 1]]));
-          const float2 al = *reinterpret_cast<const float2*>(s.alpha_s + i0 + 2 * e);
-          mean2 = fma2(k2, pack2(al.x, al.y), mean2);
-          const uint32_t h = pack_h2(lo_of(k2), hi_of(k2));
-          const unsigned long long r2 = fma2(pack2(h_lo_f32(h), h_hi_f32(h)), pack2(-1.0f, -1.0f), k2);  // exact
-          hi[e] = h;
-          lo[e] = pack_h2(lo_of(r2), hi_of(r2));
-        }
-        tmem_st8(tmem_base + lane_base + col, hi);
-        tmem_st8(tmem_base + lane_base + col + 8u, lo);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.a_full[c]);
-      }
-      s.mean_part[(buf * 4 + cg) * kTileM + row_e] = lo_of(mean2) + hi_of(mean2);
-
-      // ---- stage the next tile's A2 (this tile's distance GEMM has completed: d2_full) ----
       const int next = tile + (int)gridDim.x;
+      // ---- upper chunks of this tile; the A2 tile is free once this tile's distance GEMMs are complete ----
+      trace_it = it;
+      if (C > 2) {
+        mbar_wait(&s.d2_full[1], par);
+        tc_fence_after();
+      }
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 161);
       if (next < p.num_tiles) {
         stage_a2(buf ^ 1);
         if (next + (int)gridDim.x < p.num_tiles) prefetch(next + gridDim.x);
+      }
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 120);
+      for (int c = 2; c < C; ++c) convert_chunk(c, buf, mean_cur);
+      s.mean_part[(buf * 4 + cg) * kTileM + row_e] = lo_of(mean_cur) + hi_of(mean_cur);
+      mean_cur = 0ull;
+      // ---- lower chunks of the NEXT tile: their distance GEMM was issued behind V(t, c1) ----
+      if (next < p.num_tiles) {
+        mbar_wait(&s.d2_full[0], par ^ 1u);
+        tc_fence_after();
+        if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 160);
+        trace_it = it + 1;
+        for (int c = 0; c < C0; ++c) convert_chunk(c, buf ^ 1, mean_cur);
+        trace_it = it;
       }
 
       // ---- |V|^2: the 64 columns of sub-block c are final once chunk c's MMAs have completed ----
@@ -422,6 +467,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
           float v[16];
           mbar_wait(&s.vsub_full[sb], par);
           tc_fence_after();
+          if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 130 + sb);
           tmem_ld16(tmem_base + lane_base + (uint32_t)(sb * kChunk + cg * 16), v);
           tmem_ld_wait();
 #pragma unroll
@@ -433,6 +479,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s.v_empty);
+        if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 140);
         s.var_part[(buf * 4 + cg) * kTileM + row_e] = lo_of(ss2) + hi_of(ss2);
       }
       bar_quarter_sync(6 + quarter);
@@ -504,6 +551,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
           }
         }
       }
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 150);
     }
     if (p.best_key != nullptr && p.has_acq) {
       for (int o = 16; o > 0; o >>= 1) {
@@ -518,6 +566,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
         if (b != kEmptyKey) atomicMax(p.best_key, b);
       }
     }
+    if (TRACE && tid == 0 && p.trace != nullptr && blockIdx.x == 0) p.trace[0] = p.trace_cap;
   } else if (warp == kWarpProducer) {
     // =====================================================================================================
     // producer (TMA engine): resident images once, then the lo image of L^-1 piece by piece for every tile
@@ -561,90 +610,119 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
     __syncwarp();
   } else {
     // =====================================================================================================
-    // MMA issuer: the whole warp runs the loop (converged), one elected lane issues
+    // MMA issuer: the whole warp runs the loop (converged), one elected lane issues.  Order on the tensor pipe:
+    //   DIST(0,s0) DIST(0,s1) | V(t,c0) V(t,c1) DIST(t+1,s0) V(t,c2) V(t,c3) DIST(t+1,s1) | ...
+    // (a slab of D2 is overwritten by the next tile's distance GEMM right behind the V MMAs that read the A
+    // operand stored in it -- the pipe executes in issue order).
     // =====================================================================================================
-    const uint32_t idesc_d2 = make_idesc_f16(kTileM, p.n_pad);
     const uint32_t a2_addr = smem_u32(s.a2), bt_addr = smem_u32(s.bt), lh_addr = smem_u32(s.lh);
     const uint64_t a2_h = make_swk_desc<kTsK2>(a2_addr), a2_m = make_swk_desc<kTsK2>(a2_addr + kTsA2Split),
                    a2_l = make_swk_desc<kTsK2>(a2_addr + 2 * kTsA2Split);
-    const uint64_t b_h = make_swk_desc<kTsK2>(bt_addr), b_m = make_swk_desc<kTsK2>(bt_addr + bt_split),
-                   b_l = make_swk_desc<kTsK2>(bt_addr + 2 * bt_split);
     const uint32_t d2_addr = tmem_base + kTsD2Col0;
-    // distance GEMM of one tile: D2 = A2 * Bt^T, six split products (2^-33), one MMA spans all training columns
-    auto issue_distance = [&](uint32_t a2_parity) {
-      mbar_wait_relaxed(s.a2_full, a2_parity);
-      tc_fence_after();
+    const int C0 = C < 2 ? C : 2;
+    int mma_it = 0, mma_n = 0;
+    // distance GEMM of one slab (training columns [128 slab, ...)): six split products (2^-33)
+    auto issue_distance = [&](int slab) {
+      const int ncols = (p.n_pad - 128 * slab) < 128 ? (p.n_pad - 128 * slab) : 128;
+      const uint32_t idesc = make_idesc_f16(kTileM, ncols);
+      const uint32_t boff = (uint32_t)slab * 128u * (kTsK2 * 2u);  // 128 rows of 64 bytes
+      const uint64_t b_h = make_swk_desc<kTsK2>(bt_addr + boff), b_m = make_swk_desc<kTsK2>(bt_addr + bt_split + boff),
+                     b_l = make_swk_desc<kTsK2>(bt_addr + 2 * bt_split + boff);
+      const uint32_t d_addr = d2_addr + (uint32_t)(128 * slab);
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < kTsK2 / 16; ++kk) {
           const uint64_t ko = (uint64_t)(kk * 2);
-          umma_f16(d2_addr, a2_h + ko, b_h + ko, idesc_d2, kk > 0 ? 1u : 0u);
-          umma_f16(d2_addr, a2_h + ko, b_m + ko, idesc_d2, 1u);
-          umma_f16(d2_addr, a2_m + ko, b_h + ko, idesc_d2, 1u);
-          umma_f16(d2_addr, a2_h + ko, b_l + ko, idesc_d2, 1u);
-          umma_f16(d2_addr, a2_l + ko, b_h + ko, idesc_d2, 1u);
-          umma_f16(d2_addr, a2_m + ko, b_m + ko, idesc_d2, 1u);
+          umma_f16(d_addr, a2_h + ko, b_h + ko, idesc, kk > 0 ? 1u : 0u);
+          umma_f16(d_addr, a2_h + ko, b_m + ko, idesc, 1u);
+          umma_f16(d_addr, a2_m + ko, b_h + ko, idesc, 1u);
+          umma_f16(d_addr, a2_h + ko, b_l + ko, idesc, 1u);
+          umma_f16(d_addr, a2_l + ko, b_h + ko, idesc, 1u);
+          umma_f16(d_addr, a2_m + ko, b_m + ko, idesc, 1u);
         }
-        umma_commit(s.d2_full);
+        umma_commit(&s.d2_full[slab]);
       }
       __syncwarp();
+      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 250 + slab);
     };
     mbar_wait_relaxed(s.res_full, 0u);
     uint32_t rs = 0, rph = 0;
-    int j = 0;
-    int tile = blockIdx.x;
-    if (tile < p.num_tiles) issue_distance(0u);
-    for (; tile < p.num_tiles; tile += gridDim.x, ++j) {
-      const uint32_t par = (uint32_t)(j & 1);
-      if (j > 0) mbar_wait_relaxed(s.v_empty, par ^ 1u);  // the previous tile's |V|^2 has been read
+    // V MMAs of K chunk c: resident hi image (K*hi x Lhi, K*lo x Lhi), then the streamed lo pieces (K*hi x Llo)
+    auto issue_v_chunk = [&](int c, uint32_t par, uint32_t hi_off) {
+      const int rows_c = p.n_pad - c * kChunk;
+      mbar_wait_relaxed(&s.a_full[c], par);
       tc_fence_after();
-      uint32_t hi_off = 0;
-      for (int c = 0; c < C; ++c) {
-        const int rows_c = p.n_pad - c * kChunk;
-        mbar_wait_relaxed(&s.a_full[c], par);
+      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 210 + c);
+      const uint32_t a_col = d2_addr + (uint32_t)(c * kChunk);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {  // K step kk only reaches columns >= 64c + 16kk
+          const uint32_t n_cols = (uint32_t)(rows_c - 16 * kk);
+          const uint64_t bd = make_sw128_desc(lh_addr + hi_off + (uint32_t)kk * 2048u) + (uint64_t)(kk * 2);
+          const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + 16 * kk);
+          const uint32_t id = make_idesc_f16(kTileM, (int)n_cols);
+          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, id, (c > 0 || kk > 0) ? 1u : 0u);
+          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk + 8), bd, id, 1u);
+        }
+      }
+      __syncwarp();
+      for (int r0 = 0; r0 < rows_c; r0 += 128) {
+        const int rows_p = rows_c - r0 < 128 ? rows_c - r0 : 128;
+        mbar_wait_relaxed(&s.r_full[rs], rph);
         tc_fence_after();
-        const uint32_t a_col = d2_addr + (uint32_t)(c * kChunk);
+        const uint32_t b_addr = smem_u32(s.ring + (size_t)rs * kTsLoStage);
         if (elect_one()) {
-          // resident hi image: K*hi x Lhi, K*lo x Lhi; K step kk only reaches columns >= 64c + 16kk
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint32_t n_cols = (uint32_t)(rows_c - 16 * kk);
-            const uint64_t bd = make_sw128_desc(lh_addr + hi_off + (uint32_t)kk * 2048u) + (uint64_t)(kk * 2);
-            const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + 16 * kk);
-            const uint32_t id = make_idesc_f16(kTileM, (int)n_cols);
-            umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, id, (c > 0 || kk > 0) ? 1u : 0u);
-            umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk + 8), bd, id, 1u);
+            const int skip = (r0 == 0) ? 16 * kk : 0;  // rows of this piece the K step cannot reach
+            const uint32_t n_cols = (uint32_t)(rows_p - skip);
+            const uint64_t bd = make_sw128_desc(b_addr + (uint32_t)skip * 128u) + (uint64_t)(kk * 2);
+            const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + r0 + skip);
+            umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, make_idesc_f16(kTileM, (int)n_cols), 1u);
           }
+          umma_commit(&s.r_empty[rs]);
         }
         __syncwarp();
-        // streamed lo image: K*hi x Llo, pieces of <= 128 rows
-        for (int r0 = 0; r0 < rows_c; r0 += 128) {
-          const int rows_p = rows_c - r0 < 128 ? rows_c - r0 : 128;
-          mbar_wait_relaxed(&s.r_full[rs], rph);
-          tc_fence_after();
-          const uint32_t b_addr = smem_u32(s.ring + (size_t)rs * kTsLoStage);
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const int skip = (r0 == 0) ? 16 * kk : 0;  // rows of this piece the K step cannot reach
-              const uint32_t n_cols = (uint32_t)(rows_p - skip);
-              const uint64_t bd = make_sw128_desc(b_addr + (uint32_t)skip * 128u) + (uint64_t)(kk * 2);
-              const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + r0 + skip);
-              umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, make_idesc_f16(kTileM, (int)n_cols), 1u);
-            }
-            umma_commit(&s.r_empty[rs]);
-          }
-          __syncwarp();
-          if (++rs == (uint32_t)kTsLoStages) {
-            rs = 0;
-            rph ^= 1u;
-          }
+        if (++rs == (uint32_t)kTsLoStages) {
+          rs = 0;
+          rph ^= 1u;
         }
-        if (elect_one()) umma_commit(&s.vsub_full[c]);  // sub-block c of V has received its last contribution
-        __syncwarp();
-        hi_off += (uint32_t)rows_c * 128u;
       }
-      if (tile + (int)gridDim.x < p.num_tiles) issue_distance(par ^ 1u);
+      if (elect_one()) umma_commit(&s.vsub_full[c]);  // sub-block c of V has received its last contribution
+      __syncwarp();
+      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 220 + c);
+    };
+    int j = 0;
+    int tile = blockIdx.x;
+    if (tile < p.num_tiles) {
+      mbar_wait_relaxed(s.a2_full, 0u);
+      tc_fence_after();
+      issue_distance(0);
+      if (C > 2) issue_distance(1);
+    }
+    for (; tile < p.num_tiles; tile += gridDim.x, ++j) {
+      const uint32_t par = (uint32_t)(j & 1);
+      const bool has_next = tile + (int)gridDim.x < p.num_tiles;
+      mma_it = j;
+      if (j > 0) mbar_wait_relaxed(s.v_empty, par ^ 1u);  // the previous tile's |V|^2 has been read
+      tc_fence_after();
+      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, j, 200);
+      uint32_t hi_off = 0;
+      for (int c = 0; c < C0; ++c) {
+        issue_v_chunk(c, par, hi_off);
+        hi_off += (uint32_t)(p.n_pad - c * kChunk) * 128u;
+      }
+      if (has_next) {
+        mbar_wait_relaxed(s.a2_full, par ^ 1u);  // the next tile's candidate rows are staged
+        tc_fence_after();
+        if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, j, 260);
+        issue_distance(0);
+      }
+      for (int c = 2; c < C; ++c) {
+        issue_v_chunk(c, par, hi_off);
+        hi_off += (uint32_t)(p.n_pad - c * kChunk) * 128u;
+      }
+      if (has_next && C > 2) issue_distance(1);
     }
   }
 
@@ -1051,18 +1129,25 @@ bool fused_ts_supported(const FusedParams& p, int max_smem) {
   return ts_carve(nullptr, p.n_pad, p.n_tasks, nullptr) + 1024 <= (size_t)max_smem;
 }
 
-template <int FAMILY, bool TASKS>
-static int launch_ts_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
+template <int FAMILY, bool TASKS, bool TRACE>
+static int launch_ts_one2(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
   static int configured_for = -1;  // cudaFuncSetAttribute once per device, not per launch
   int dev = 0;
   BB_CUDA(cudaGetDevice(&dev));
   if (configured_for != dev) {
-    BB_CUDA(cudaFuncSetAttribute(k_fused_ts<FAMILY, TASKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BB_CUDA(cudaFuncSetAttribute(k_fused_ts<FAMILY, TASKS, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured_for = dev;
   }
-  k_fused_ts<FAMILY, TASKS><<<grid, kFusedThreads, smem, stream>>>(p);
+  k_fused_ts<FAMILY, TASKS, TRACE><<<grid, kFusedThreads, smem, stream>>>(p);
   BB_LAUNCH_CHECK();
   return BB_OK;
+}
+template <int FAMILY, bool TASKS>
+static int launch_ts_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
+  // the instrumented variant only exists for the headline family without tasks (test-only pipeline timeline)
+  if constexpr (FAMILY == BB_KERNEL_MATERN52 && !TASKS)
+    if (p.trace != nullptr) return launch_ts_one2<FAMILY, TASKS, true>(p, grid, smem, stream);
+  return launch_ts_one2<FAMILY, TASKS, false>(p, grid, smem, stream);
 }
 
 int launch_fused_ts(FusedParams& p, int grid, cudaStream_t stream) {

@@ -261,47 +261,44 @@ class DeviceGP:
     STREAM_MIN_ROWS = 262_144
     STREAM_BLOCKS = 8
 
-    def _score_streamed(self, acq: AcqConfig, x: torch.Tensor, zf, keep, index_offset: int, want_scores: bool):
-        if x.shape[1] != self.d:
-            raise ValueError(f"expected a (N, {self.d}) candidate matrix, got {tuple(x.shape)}")
+    def _host_pass(self, acq: AcqConfig, h: torch.Tensor, fmt: str, ld: int, row_bytes: int, table, zf, keep,
+                   index_offset: int, want_scores: bool):
+        """One ``bb_score_fused_host`` call: H2D of row blocks on the side stream overlapped with decode + scoring."""
         lib = _lib.load()
-        N = x.shape[0]
-        nblk = self.STREAM_BLOCKS
-        rows = -(-N // nblk)
-        rows = -(-rows // 128) * 128  # whole tiles per block
-        c_acq = acq.to_c()
-        lay = _lib.LAYOUT["row_f64" if x.dtype == torch.float64 else "row_f32"]
+        N = h.shape[0]
+        rows = -(-N // self.STREAM_BLOCKS)
+        rows = max(-(-rows // 128) * 128, 128)
+        coded = fmt.startswith("codes")
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()
             if not hasattr(self, "_copy_stream"):
                 self._copy_stream = torch.cuda.Stream(device=self.device)
-            copy = self._copy_stream
-            bufs = [torch.empty((rows, self.d), dtype=x.dtype, device=self.device) for _ in range(2)]
-            ready = [torch.cuda.Event() for _ in range(2)]
-            freed = [torch.cuda.Event() for _ in range(2)]
+            key_ = (rows * row_bytes, rows if coded else 0)
+            if getattr(self, "_stage_key", None) != key_:  # staging buffers are reused across calls
+                self._stage = [torch.empty(rows * row_bytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
+                self._rowbuf = ([torch.empty((rows, self.d), dtype=torch.float32, device=self.device) for _ in range(2)]
+                                if coded else [None, None])
+                self._stage_key = key_
             score = torch.empty(N if want_scores else 0, dtype=torch.float32, device=self.device)
             key = torch.empty(1, dtype=torch.int64, device=self.device)
-            _lib.check(lib.bb_best_init(_ptr(key), _stream_ptr()), "bb_best_init")
-            copy.wait_stream(main)
+            c_acq = acq.to_c()
+            stage = (C.c_void_p * 2)(self._stage[0].data_ptr(), self._stage[1].data_ptr())
+            rowb = (C.c_void_p * 2)(*(0 if t is None else t.data_ptr() for t in self._rowbuf))
             S = 0 if zf is None else zf.numel()
-            for b, lo in enumerate(range(0, N, rows)):
-                hi = min(lo + rows, N)
-                slot = b & 1
-                with torch.cuda.stream(copy):
-                    if b >= 2:
-                        copy.wait_event(freed[slot])
-                    bufs[slot][: hi - lo].copy_(x[lo:hi], non_blocking=True)
-                    ready[slot].record(copy)
-                main.wait_event(ready[slot])
-                kp = None if keep is None else keep[lo:hi]
-                _lib.check(lib.bb_score_fused(
-                    C.byref(self.model), C.byref(c_acq), _ptr(bufs[slot]), lay, hi - lo, self.d, _ptr(kp), _ptr(zf), S,
-                    C.c_void_p(score.data_ptr() + 4 * lo) if want_scores else None, _ptr(key),
-                    int(index_offset) + lo, _stream_ptr()), "bb_score_fused")
-                freed[slot].record(main)
-            for t in bufs:
-                t.record_stream(main)
+            _lib.check(lib.bb_score_fused_host(
+                C.byref(self.model), C.byref(c_acq), C.c_void_p(h.data_ptr()), _lib.HOST_FORMAT[fmt], N, ld,
+                _ptr(table), 0 if table is None else table.shape[1], stage, rowb, rows, _ptr(keep), _ptr(zf), S,
+                _ptr(score) if want_scores else None, _ptr(key), int(index_offset), _stream_ptr(),
+                C.c_void_p(self._copy_stream.cuda_stream)), "bb_score_fused_host")
+            self._copy_stream.wait_stream(main)  # later work on the side stream stays ordered behind this pass
         return score, key
+
+    def _score_streamed(self, acq: AcqConfig, x: torch.Tensor, zf, keep, index_offset: int, want_scores: bool):
+        if x.shape[1] != self.d:
+            raise ValueError(f"expected a (N, {self.d}) candidate matrix, got {tuple(x.shape)}")
+        f64 = x.dtype == torch.float64
+        return self._host_pass(acq, x, "rows_f64" if f64 else "rows_f32", self.d, self.d * (8 if f64 else 4), None, zf,
+                               keep, index_offset, want_scores)
 
     def score_coded(self, acq: AcqConfig, codes: torch.Tensor, table, bits: int, z: torch.Tensor | None,
                     keep: torch.Tensor | None = None, index_offset: int = 0, want_scores: bool = True):
@@ -327,52 +324,17 @@ class DeviceGP:
             if z is None:
                 raise ValueError("Monte Carlo acquisition functions need base samples")
             zf = z.reshape(-1).to(self.device, torch.float32)
+        if codes.device.type == "cpu":
+            return self._host_pass(acq, codes, "codes4" if bits == 4 else "codes8", row_bytes, row_bytes, tab, zf, keep,
+                                   index_offset, want_scores)
         lib = _lib.load()
         N = codes.shape[0]
-        on_host = codes.device.type == "cpu"
-        nblk = self.STREAM_BLOCKS if (on_host and N >= self.STREAM_MIN_ROWS) else 1
-        rows = -(-N // nblk)
-        rows = max(-(-rows // 128) * 128, 128)
-        c_acq = acq.to_c()
-        lay = _lib.LAYOUT["row_f32"]
-        with torch.cuda.device(self.device):
-            main = torch.cuda.current_stream()
-            if not hasattr(self, "_copy_stream"):
-                self._copy_stream = torch.cuda.Stream(device=self.device)
-            copy = self._copy_stream
-            cbufs = [torch.empty((rows, row_bytes), dtype=torch.uint8, device=self.device) for _ in range(2)]
-            fbuf = [torch.empty((rows, self.d), dtype=torch.float32, device=self.device) for _ in range(2)]
-            ready = [torch.cuda.Event() for _ in range(2)]
-            freed = [torch.cuda.Event() for _ in range(2)]
-            score = torch.empty(N if want_scores else 0, dtype=torch.float32, device=self.device)
-            key = torch.empty(1, dtype=torch.int64, device=self.device)
-            _lib.check(lib.bb_best_init(_ptr(key), _stream_ptr()), "bb_best_init")
-            copy.wait_stream(main)
-            S = 0 if zf is None else zf.numel()
-            for b, lo in enumerate(range(0, N, rows)):
-                hi = min(lo + rows, N)
-                slot = b & 1
-                if on_host:
-                    with torch.cuda.stream(copy):
-                        if b >= 2:
-                            copy.wait_event(freed[slot])
-                        cbufs[slot][: hi - lo].copy_(codes[lo:hi], non_blocking=True)
-                        ready[slot].record(copy)
-                    main.wait_event(ready[slot])
-                    src = cbufs[slot]
-                else:
-                    src = codes[lo:hi]
-                _lib.check(lib.bb_decode_codes(_ptr(src), bits, hi - lo, self.d, row_bytes, _ptr(tab), tab.shape[1],
-                                               _ptr(fbuf[slot]), self.d, _stream_ptr()), "bb_decode_codes")
-                kp = None if keep is None else keep[lo:hi]
-                _lib.check(lib.bb_score_fused(
-                    C.byref(self.model), C.byref(c_acq), _ptr(fbuf[slot]), lay, hi - lo, self.d, _ptr(kp), _ptr(zf), S,
-                    C.c_void_p(score.data_ptr() + 4 * lo) if want_scores else None, _ptr(key),
-                    int(index_offset) + lo, _stream_ptr()), "bb_score_fused")
-                freed[slot].record(main)
-            for t in cbufs + fbuf:
-                t.record_stream(main)
-        return score, key
+        with torch.cuda.device(self.device):  # device-resident codes: expand once, score
+            rows = torch.empty((N, self.d), dtype=torch.float32, device=self.device)
+            _lib.check(lib.bb_decode_codes(_ptr(codes), bits, N, self.d, row_bytes, _ptr(tab), tab.shape[1], _ptr(rows),
+                                           self.d, _stream_ptr()), "bb_decode_codes")
+        return torch.ops.baybe_b200.score_fused(rows, keep, zf, self.handle, _lib.ACQ_KIND[acq.kind], acq.params(),
+                                                int(index_offset), bool(want_scores))
 
     def score_joint(self, acq: AcqConfig, x, pending, z: torch.Tensor) -> torch.Tensor:
         """MC acquisition value of [x*; pending] for every row x* (sequential-greedy round)."""

@@ -304,6 +304,23 @@ int bb_allreduce_best(const bb_peer_group* g, const int64_t* d_local_key, uint32
 int bb_decode_codes(const uint8_t* d_codes, int32_t bits, int64_t N, int32_t d, int64_t ld_bytes,
                     const float* d_table, int32_t table_ld, float* d_out, int64_t ldo, void* stream);
 
+/* ---- end-to-end pass over a HOST-resident candidate set: blocks of block_rows rows (a multiple of 128) are copied
+ * on `copy_stream` into two caller-owned staging buffers (d_stage[2], each block_rows * row bytes) while the previous
+ * block is expanded (level codes -> d_rows[2], each block_rows * d floats) and scored by the fused kernel on `stream`.
+ * h_x should be pinned; row r starts at h_x + r * row bytes (ld in ELEMENTS for the float formats, in BYTES for the
+ * code formats).  Events are created and destroyed inside the call; nothing else is allocated.  Same results as
+ * bb_score_fused on the device-resident matrix. */
+typedef enum bb_host_format {
+  BB_HOST_ROWS_F32 = 0, /* float32 rows                                  */
+  BB_HOST_ROWS_F64 = 1, /* float64 rows (what the reference holds)       */
+  BB_HOST_CODES4 = 2,   /* 4-bit level codes + value table (bb_decode_codes) */
+  BB_HOST_CODES8 = 3    /* 8-bit level codes + value table               */
+} bb_host_format;
+int bb_score_fused_host(const bb_model* m, const bb_acq_spec* a, const void* h_x, int32_t host_format, int64_t N,
+                        int64_t ld, const float* d_table, int32_t table_ld, void* const* d_stage,
+                        float* const* d_rows, int64_t block_rows, const uint8_t* d_keep, const float* d_z, int32_t S,
+                        float* d_score, int64_t* d_best_key, int64_t index_offset, void* stream, void* copy_stream);
+
 /* ---- test-only diagnostic: plain fp32 SIMT posterior (no tensor cores), used by the GPU
  * tests to separate tcgen05-path errors from formula errors.  Not called by the product. -- */
 int bb_debug_posterior_simt(const bb_model* m, const void* d_x, int32_t layout, int64_t N,

@@ -17,7 +17,9 @@ for st in $STAGES; do
       timeout 200 python scripts/ts_first_light.py > $OUT/ts_first_light.txt 2>&1; echo "light rc=$?"
       tail -45 $OUT/ts_first_light.txt ;;
     tests)
-      if grep -q FIRST_LIGHT_DONE $OUT/ts_first_light.txt 2>/dev/null; then FK=""; else FK="tc"; echo "TS kernel not healthy: tests run with BB_FORCE_KERNEL=tc"; fi
+      FK=""  # only when the first-light stage ran IN THIS SESSION and failed, fall back to the fused_tc kernels
+      if [ -f $OUT/ts_first_light.txt ] && ! grep -q FIRST_LIGHT_DONE $OUT/ts_first_light.txt; then FK="tc"; echo "TS kernel not healthy: tests run with BB_FORCE_KERNEL=tc"; fi
+      [ -n "$BB_FORCE_KERNEL" ] && FK="$BB_FORCE_KERNEL"
       BB_FORCE_KERNEL=$FK timeout 1200 python -m pytest tests -m gpu -q --timeout 300 --timeout-method thread -p no:cacheprovider > $OUT/pytest_gpu.txt 2>&1; echo "tests rc=$?"
       tail -60 $OUT/pytest_gpu.txt ;;
     bench)
@@ -35,6 +37,16 @@ for st in $STAGES; do
       tail -8 $OUT/r02_sanitizer_memcheck.txt
       timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python scripts/ts_first_light.py n64_d4 cfg1 > $OUT/r02_sanitizer_racecheck.txt 2>&1; echo "racecheck rc=$?"
       tail -8 $OUT/r02_sanitizer_racecheck.txt ;;
+    trace)
+      timeout 200 python scripts/trace_timeline.py score ts > $OUT/r02_pipeline_trace_fused_ts.txt 2>&1; echo "trace rc=$?"
+      head -130 $OUT/r02_pipeline_trace_fused_ts.txt ;;
+    kmat)
+      timeout 300 python scripts/time_kmat.py > $OUT/time_kmat.txt 2>&1; echo "kmat rc=$?"; cat $OUT/time_kmat.txt | tail -8
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_kmat_ts -s 1 -c 1 -f -o $OUT/prof_kmat_ts_r02 python scripts/profile_target.py kmat > $OUT/ncu_kmat.log 2>&1; echo "ncu kmat rc=$?"
+      tail -2 $OUT/ncu_kmat.log ;;
+    bench45)
+      timeout 600 python bench.py --config 5 --steps 10 --warmup 3 > $OUT/bench_cfg5_n1.json 2> $OUT/bench_cfg5_n1.err; echo "cfg5 rc=$?"; cat $OUT/bench_cfg5_n1.json | cut -c1-1800; tail -3 $OUT/bench_cfg5_n1.err
+      timeout 900 python bench.py --config 4 --steps 5 --warmup 3 > $OUT/bench_cfg4_n1.json 2> $OUT/bench_cfg4_n1.err; echo "cfg4 rc=$?"; cat $OUT/bench_cfg4_n1.json | cut -c1-1800; tail -3 $OUT/bench_cfg4_n1.err ;;
     bench2)
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > $OUT/bench_n2.json 2> $OUT/bench_n2.err; echo "bench2 rc=$?"
       cat $OUT/bench_n2.json | cut -c1-3000; tail -15 $OUT/bench_n2.err ;;

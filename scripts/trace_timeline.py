@@ -24,8 +24,17 @@ run(); torch.cuda.synchronize()
 lib.bb_debug_set_trace(None, 0)
 h = buf.cpu()
 n = min(int(h[0]), cap)
-ev = sorted(((int(h[2 + 2 * i]), int(h[1 + 2 * i])) for i in range(n)))
+ev = sorted(((int(h[2 + 2 * i]), int(h[1 + 2 * i])) for i in range(n) if int(h[2 + 2 * i]) != 0))
 t0 = ev[0][0]
+if len(sys.argv) > 2 and sys.argv[2] == "ts":  # event ids of fused_ts.cu
+    names = {100: "C chunk in regs", 110: "C chunk arrived", 120: "C stage_a2 done", 130: "C vsub ok", 140: "C v_empty arrive",
+             150: "C acquisition done", 160: "C d2 slab0(next) ok", 161: "C d2 slab1 ok", 200: "M v_empty ok",
+             210: "M a_full ok", 220: "M V chunk issued", 250: "M DIST issued slab", 260: "M a2_full ok"}
+    for clk, code in ev:
+        it, e = divmod(code, 1000)
+        base = max(k for k in names if k <= e)
+        print(f"{clk - t0:8d}  tile {it}  {names[base]:22s} {e - base}")
+    sys.exit(0)
 names = {100: "C chunk start", 110: "C D2 in regs", 120: "C k+split done", 130: "C mc slice done", 140: "C a_empty ok",
          150: "C a_full arrive", 160: "C finish_prev done", 161: "C stage_a2 done", 170: "C dsub ok", 180: "C epilogue bar",
          200: "M d_empty ok", 210: "M a_full ok", 220: "M r_full ok", 240: "M chunk issued", 250: "M dist begin",

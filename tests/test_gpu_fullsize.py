@@ -103,6 +103,34 @@ def test_streamed_host_matrix_equals_resident_scoring(cuda_device):
     assert torch.equal(s_res, s64) and int(k_res.item()) == int(k64.item())
 
 
+def test_level_coded_candidates_score_bit_identically(cuda_device):
+    """The compact exact form of a discrete space (4- or 8-bit level codes + value table, bb_decode_codes) through
+    bb_score_fused_host (pinned host codes, H2D overlapped with decode + scoring) and from device-resident codes."""
+    from baybe_b200.bits import decode_levels, encode_levels
+
+    for levels, bits_expected in ((11, 4), (40, 8)):
+        w = numeric_grid_workload(N=300_017, d=20, n=256, seed=4, levels=levels)  # ragged last block
+        gp = DeviceGP(device=cuda_device, **w.gp_kwargs())
+        z = sobol_normal_samples(512, 1, seed=5)
+        acq = AcqConfig(kind="qLogEI", best_f=gp.best_f(AcqConfig(kind="qLogEI")))
+        codes, table, bits = encode_levels(w.candidates)
+        assert bits == bits_expected and codes.shape == (len(w.candidates), 10 if bits == 4 else 20)
+        assert np.array_equal(decode_levels(codes, table, bits, 20), w.candidates.astype(np.float32))
+        x32 = torch.from_numpy(w.candidates).to(cuda_device, torch.float32)
+        keep = torch.ones(len(x32), dtype=torch.uint8, device=cuda_device)
+        keep[::5] = 0
+        s_res, k_res = gp.score(acq, x32, z[:, 0], keep=keep, index_offset=77)
+        ch = torch.from_numpy(codes).pin_memory()
+        s_host, k_host = gp.score_coded(acq, ch, table, bits, z[:, 0], keep=keep, index_offset=77)
+        assert torch.equal(s_res, s_host) and int(k_res.item()) == int(k_host.item())
+        s_dev, k_dev = gp.score_coded(acq, ch.to(cuda_device), table, bits, z[:, 0], keep=keep, index_offset=77)
+        assert torch.equal(s_res, s_dev) and int(k_res.item()) == int(k_dev.item())
+        _, k2 = gp.score_coded(acq, ch, table, bits, z[:, 0], keep=keep, index_offset=77, want_scores=False)  # buffers reused
+        assert int(k2.item()) == int(k_res.item())
+    with pytest.raises(ValueError):
+        gp.score_coded(acq, ch[:, :5].contiguous(), table, bits, z[:, 0])
+
+
 def test_config5_four_tasks_one_million_candidates(cuda_device):
     w = task_workload(N_per_task=250_000, n_tasks=4, d_num=20, n_per_task=64, seed=0)
     _check_fullsize(w, cuda_device, n_shards=4)
