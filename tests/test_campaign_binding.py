@@ -28,9 +28,11 @@ def bb():
     when there is no GPU."""
     import torch
 
+    # appended, not prepended: the reference tree has its own top-level ``tests`` package, which must not shadow
+    # this repo's for processes spawned later in the session (tests/test_distributed_cpu.py)
     for p in (str(ROOT / "tests" / "shims"), str(REF)):
         if p not in sys.path:
-            sys.path.insert(0, p)
+            sys.path.append(p)
     import baybe  # noqa: F401
     from baybe_b200 import baybe_plugin, surrogates
     from tests.helpers import OracleBackedGP
