@@ -289,6 +289,21 @@ __device__ __forceinline__ void mc_row_exact_warp(const float* __restrict__ z_s,
   }
 }
 
+// Per-sample kinds without a table (qEI, qPI, qLogEI outside the table's S range) by a whole warp: lane l takes the
+// float4 sample groups l, l + 32, ...; fixed reduction order; result in every lane.  S is a multiple of 16.
+__device__ __forceinline__ void mc_row_groups_warp(int kind, const float* __restrict__ z_s, int S, float c0,
+                                                   float c1, int lane, float& a0, float& a1) {
+  a0 = 0.f;
+  a1 = 0.f;
+  const float4* z4 = reinterpret_cast<const float4*>(z_s);
+  const int G = S >> 2;
+  for (int g = lane; g < G; g += 32) mc_accumulate(kind, c0, c1, z4 + g, 1, a0, a1);
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+}
+
 __device__ __forceinline__ float mc_finalize(const bb_acq_spec& a, float mu, float var, float s0,
                                              float s1, int S, float z_mean, float zdev_mean) {
   const float sd = sqrtf(var);

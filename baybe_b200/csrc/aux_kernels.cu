@@ -401,13 +401,7 @@ static int fill_params(AuxParams& p, const bb_model* m, const void* d_x, int32_t
     BB_LAUNCH_CHECK();                                                                          \
   } while (0)
 
-static int device_limits(int& sms, int& max_smem) {
-  int dev = 0;
-  BB_CUDA(cudaGetDevice(&dev));
-  BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  return BB_OK;
-}
+static int device_limits(int& sms, int& max_smem) { return device_limits(&sms, &max_smem); }  // cached (common.cuh)
 
 int launch_cross(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
                  const float* d_pend_x, const float* d_pend_beta, int32_t P, float* d_cross,

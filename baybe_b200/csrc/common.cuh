@@ -44,6 +44,44 @@ void set_error(const char* fmt, ...);
 
 #define BB_LAUNCH_CHECK() BB_CUDA(cudaGetLastError())
 
+// SM count and opt-in shared-memory limit of the current device, queried once per device (not per launch).
+static inline int device_limits(int* sms, int* max_smem) {
+  constexpr int kMaxDev = 64;
+  static int c_sms[kMaxDev], c_smem[kMaxDev];
+  static bool c_ok[kMaxDev];
+  int dev = 0;
+  BB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev || !c_ok[dev]) {
+    int a = 0, b = 0;
+    BB_CUDA(cudaDeviceGetAttribute(&b, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    BB_CUDA(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev));
+    if (dev < 0 || dev >= kMaxDev) {
+      *sms = a;
+      *max_smem = b;
+      return BB_OK;
+    }
+    c_sms[dev] = a;
+    c_smem[dev] = b;
+    c_ok[dev] = true;
+  }
+  *sms = c_sms[dev];
+  *max_smem = c_smem[dev];
+  return BB_OK;
+}
+
+// Opt a kernel into the full dynamic shared-memory carve-out once per device (function-local static per
+// instantiation site), instead of one cudaFuncSetAttribute per launch.
+#define BB_SMEM_OPTIN_ONCE(kernel)                                                                         \
+  do {                                                                                                     \
+    static unsigned long long done_mask_ = 0ull;                                                           \
+    int dev_ = 0;                                                                                          \
+    BB_CUDA(cudaGetDevice(&dev_));                                                                         \
+    if (dev_ < 0 || dev_ >= 64 || !((done_mask_ >> dev_) & 1ull)) {                                        \
+      BB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));      \
+      if (dev_ >= 0 && dev_ < 64) done_mask_ |= 1ull << dev_;                                              \
+    }                                                                                                      \
+  } while (0)
+
 constexpr int kTileM = 128;     // candidates per tile = UMMA_M
 constexpr int kChunk = 64;      // training points per K chunk = one 128-byte swizzle row of fp16
 constexpr int kSMs = 148;

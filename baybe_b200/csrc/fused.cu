@@ -552,8 +552,7 @@ __global__ void __launch_bounds__(kFusedThreads) k_mc_table(const float* __restr
 
 template <int FAMILY, int LAG, bool PRE = false, int GMAX = 1>
 static int launch_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
-  BB_CUDA(cudaFuncSetAttribute(k_fused<FAMILY, LAG, PRE, GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
+  BB_SMEM_OPTIN_ONCE((k_fused<FAMILY, LAG, PRE, GMAX>));
   k_fused<FAMILY, LAG, PRE, GMAX><<<grid, kFusedThreads, smem, stream>>>(p);
   BB_LAUNCH_CHECK();
   return BB_OK;
@@ -659,13 +658,14 @@ static int launch_wide_blocks(const bb_model* m, const FusedParams& full, int sm
   return BB_OK;
 }
 
-static long long* g_trace_buf = nullptr;
-static int g_trace_cap = 0;
+static thread_local long long* g_trace_buf = nullptr;  // test-only; per host thread, so concurrent callers never see it
+static thread_local int g_trace_cap = 0;
 
 int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
                  const bb_acq_spec* acq, const float* d_z, int32_t S, const uint8_t* d_keep,
                  float* d_mu, float* d_var, float* d_score, int64_t* d_best_key,
-                 int64_t index_offset, cudaStream_t stream, const WideCross* wc = nullptr) {
+                 int64_t index_offset, cudaStream_t stream, const WideCross* wc = nullptr,
+                 const StreamGate* gate = nullptr) {
   BB_CHECK_ARG(m && m->abi_version == BB_ABI_VERSION, "model struct missing or ABI mismatch");
   BB_CHECK_ARG(d_x != nullptr || N == 0, "candidate pointer is null");
   BB_CHECK_ARG(layout >= 0 && layout <= BB_BITS_U8, "unknown candidate layout %d", layout);
@@ -673,7 +673,8 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   BB_CHECK_SUPPORTED(layout != BB_BITS_U8 || m->wide,
                      "bit-packed candidates need a wide-feature model (n_pad*d_pad*4 > 56 KB)");
   const bool col_major = (layout == BB_COL_MAJOR_F32 || layout == BB_COL_MAJOR_F64);
-  BB_CHECK_ARG(layout == BB_BITS_U8 ? ldx >= (m->d + 7) / 8 : (col_major ? ldx >= N : ldx >= m->d),
+  BB_CHECK_ARG((gate != nullptr && gate->layout >= kLayoutCodes4) ||  // code rows: ld in bytes, checked by the caller
+                   (layout == BB_BITS_U8 ? ldx >= (m->d + 7) / 8 : (col_major ? ldx >= N : ldx >= m->d)),
                "leading dimension %lld too small", (long long)ldx);
   BB_CHECK_ARG(N + index_offset < 0xffffffffLL, "candidate index exceeds the 32-bit key range");
   BB_CHECK_SUPPORTED(m->n_tasks <= kMaxTasks, "at most %d tasks supported", kMaxTasks);
@@ -744,26 +745,36 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   p.ts_aug_one = m->ts_aug_one;
   p.ts_g = m->ts_g;
   p.ts_kscale = m->ts_kscale;
+  if (gate != nullptr) {  // overlapped host pass: rows are published while the kernel runs (fused_ts.cu only)
+    p.ready_rows = gate->ready_rows;
+    p.gate_status = gate->status;
+    p.code_table = gate->code_table;
+    p.code_table_ld = gate->code_table_ld;
+    p.layout = gate->layout;
+  }
   BB_CHECK_SUPPORTED(p.n_pad <= 512 || m->wide, "n_pad=%d exceeds the 512 TMEM columns", p.n_pad);
   const int lag = (2 * p.n_pad <= 512) ? 1 : 0;  // two accumulators fit: defer the epilogue
   uint32_t cols = 32;
   while ((int)cols < (lag ? 2 : 1) * p.n_pad) cols <<= 1;
   p.tmem_cols = cols;
 
-  int dev = 0, max_smem = 0, sms = 0;
-  BB_CUDA(cudaGetDevice(&dev));
-  BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int max_smem = 0, sms = 0;
+  {
+    const int rc_lim = device_limits(&sms, &max_smem);
+    if (rc_lim != BB_OK) return rc_lim;
+  }
+  BB_CHECK_SUPPORTED(gate == nullptr || !m->wide, "the overlapped host pass does not cover wide-feature models");
   if (m->wide) return launch_wide_blocks(m, p, sms, max_smem, wc, stream);
   // diagnostic knob (tests / profiling only): BB_FORCE_KERNEL=tc keeps shapes the TS kernel covers on fused_tc.cu
   static const bool ts_off = [] {
     const char* e = getenv("BB_FORCE_KERNEL");
     return e != nullptr && e[0] == 't' && e[1] == 'c';
   }();
-  if (!ts_off && fused_ts_supported(p, max_smem)) {  // headline kernel (fused_ts.cu)
+  if (!ts_off && !m->wide && fused_ts_supported(p, max_smem)) {  // headline kernel (fused_ts.cu)
     const int grid_ts = p.num_tiles < sms ? p.num_tiles : sms;
     return launch_fused_ts(p, grid_ts, stream);
   }
+  BB_CHECK_SUPPORTED(gate == nullptr, "the overlapped host pass needs the headline kernel's shape envelope");
   if (fused_tc_supported(p, max_smem)) {
     const int grid_tc = p.num_tiles < sms ? p.num_tiles : sms;
     return launch_fused_tc(p, grid_tc, stream);
@@ -802,6 +813,32 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
     case BB_KERNEL_MATERN52: return launch_family<BB_KERNEL_MATERN52>(p, lag, grid, smem, stream);
     default: return launch_family<BB_KERNEL_RBF>(p, lag, grid, smem, stream);
   }
+}
+
+// Shape test of the single-launch gated pass: the same envelope as the headline kernel.
+bool fused_gate_supported(const bb_model* m, const bb_acq_spec* acq, int32_t S) {
+  if (m == nullptr || m->wide) return false;
+  static const bool ts_off = [] {
+    const char* e = getenv("BB_FORCE_KERNEL");
+    return e != nullptr && e[0] == 't' && e[1] == 'c';
+  }();
+  if (ts_off) return false;
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.layout = BB_ROW_MAJOR_F32;
+  p.timg_l = reinterpret_cast<const uint8_t*>(m->d_timg_l);
+  p.timg_b = reinterpret_cast<const uint8_t*>(m->d_timg_b);
+  p.ts_alpha = m->d_ts_alpha;
+  p.n_pad = m->n_pad;
+  p.d = m->d;
+  p.family = m->family;
+  p.n_tasks = m->n_tasks;
+  p.has_acq = acq ? 1 : 0;
+  if (acq) p.acq = *acq;
+  p.S = S;
+  int sms = 0, max_smem = 0;
+  if (device_limits(&sms, &max_smem) != BB_OK) return false;
+  return fused_ts_supported(p, max_smem);
 }
 
 }  // namespace bb

@@ -73,6 +73,23 @@ struct FusedParams {
   float ts_aug_one;        // A2 column 31 = ts_aug_one
   float ts_g;              // D2 * ts_g = scaled squared distance t (family constant folded in)
   float ts_kscale;         // power of two folded into K* before the fp16 hi/lo split
+  // single-launch end-to-end pass (bb_score_fused_overlapped): rows arrive from the host WHILE the kernel runs
+  const unsigned* ready_rows;  // rows [0, *ready_rows) of x have landed (published by the copy stream); null: all
+  int32_t* gate_status;        // set to 1 if a tile's rows were not published within the time-out
+  const float* code_table;     // level-coded layouts: value table [d][code_table_ld]
+  int code_table_ld;
+};
+
+// candidate layouts beyond bb_layout, internal to the overlapped host pass: level codes expanded in the staging step
+constexpr int kLayoutCodes4 = 16, kLayoutCodes8 = 17;
+
+// optional request threaded through launch_fused by the overlapped host pass (null: none)
+struct StreamGate {
+  const unsigned* ready_rows;
+  int32_t* status;
+  const float* code_table;
+  int code_table_ld;
+  int layout;  // kLayoutCodes4 / kLayoutCodes8 / BB_ROW_MAJOR_F32
 };
 
 // test-only: (event id, SM clock) pairs of CTA 0 for a few tiles, to reconstruct the pipeline timeline
@@ -163,6 +180,8 @@ struct WideCross {
   int32_t P;
   float* cross;
 };
+// true when the single-launch gated pass can run this model (headline kernel envelope)
+bool fused_gate_supported(const bb_model* m, const bb_acq_spec* acq, int32_t S);
 int launch_kmat_wide(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx,
                      float* d_out, int64_t ldk, int64_t out_rows, int out_cols, cudaStream_t stream);
 

@@ -662,7 +662,7 @@ bool fused_tc_supported(FusedParams& p, int max_smem) {
 
 template <int FAMILY, int K2>
 static int launch_tc_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
-  BB_CUDA(cudaFuncSetAttribute(k_fused_tc<FAMILY, K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BB_SMEM_OPTIN_ONCE((k_fused_tc<FAMILY, K2>));
   k_fused_tc<FAMILY, K2><<<grid, kFusedThreads, smem, stream>>>(p);
   BB_LAUNCH_CHECK();
   return BB_OK;

@@ -37,12 +37,18 @@ constexpr uint32_t kTsLoStage = 16384;       // one streamed piece of the lo ima
 constexpr int kTsLoStages = 3;
 constexpr uint32_t kTsD2Col0 = 256;
 constexpr uint32_t kTsA2Split = 128u * kTsK2 * 2u;  // one fp16 panel of the candidate tile: 8 KB
+// Warp roles of k_fused_ts: 16 conversion warps (stage candidate rows, D2 -> K* operand), 4 epilogue warps (one per
+// TMEM lane quarter: |V|^2, moments, acquisition, arg-max), the bulk-copy producer and the MMA issuer.
+constexpr int kTsEpiWarp0 = kComputeWarps, kTsEpiWarps = 4;
+constexpr int kTsWarpProducer = kTsEpiWarp0 + kTsEpiWarps, kTsWarpMma = kTsWarpProducer + 1;
+constexpr int kTsThreads = (kTsWarpMma + 1) * 32;  // 704
+constexpr int kTsTaskSlots = 4;                    // candidate task ids of the tiles in flight
 
 struct TsSmem {
   uint8_t *lh, *ring, *bt, *a2;
   float *alpha_s, *z_s, *mc_tab, *tcov, *meanc, *cscale_s, *cshift_s, *an_part, *mean_part, *var_part;
   int32_t *ttask, *cand_task;
-  uint64_t *a_full, *vsub_full, *r_full, *r_empty, *d2_full, *a2_full, *v_empty, *res_full;
+  uint64_t *a_full, *vsub_full, *r_full, *r_empty, *d2_full, *a2_full, *v_empty, *res_full, *mean_full;
   long long* best_red;
   uint32_t* tmem_ptr;
   float* zstat;
@@ -71,8 +77,8 @@ __host__ __device__ inline size_t ts_carve(uint8_t* base, int n_pad, int n_tasks
   const size_t o_tc = take((size_t)kMaxTasks * kMaxTasks * 4, 16), o_mcn = take(kMaxTasks * 4, 16);
   const size_t o_cs = take(32 * 4, 16), o_sh = take(32 * 4, 16);
   const size_t o_an = take(4 * kTileM * 4, 16);
-  const size_t o_mp = take(2 * 4 * kTileM * 4, 16), o_vp = take(2 * 4 * kTileM * 4, 16);
-  const size_t o_ct = take(2 * kTileM * 4, 16);
+  const size_t o_mp = take(2 * 4 * kTileM * 4, 16), o_vp = take(16, 16);
+  const size_t o_ct = take(kTsTaskSlots * kTileM * 4, 16);
   const size_t o_bar = take(32 * 8, 16);
   const size_t o_best = take(16 * 8, 16), o_misc = take(32, 16);
   (void)n_tasks;
@@ -102,6 +108,7 @@ __host__ __device__ inline size_t ts_carve(uint8_t* base, int n_pad, int n_tasks
     s->a2_full = b + 18;
     s->v_empty = b + 19;
     s->res_full = b + 20;
+    s->mean_full = b + 21;  // [2]
     s->best_red = reinterpret_cast<long long*>(base + o_best);
     s->tmem_ptr = reinterpret_cast<uint32_t*>(base + o_misc);
     s->zstat = reinterpret_cast<float*>(base + o_misc + 8);
@@ -157,7 +164,7 @@ template <bool TRACE>
 __device__ __forceinline__ void ts_trace(const FusedParams& p, int half, int& n, int it, int ev) {
   if constexpr (!TRACE) return;
   if (p.trace != nullptr && blockIdx.x == 0 && it >= 6 && it < 9) {
-    const int cap2 = p.trace_cap >> 1;
+    const int cap2 = p.trace_cap / 3;  // three writers: conversion thread 0, MMA lane 0, epilogue thread 0
     if (n < cap2) {
       const int i = half * cap2 + n;
       p.trace[1 + 2 * i] = (long long)it * 1000 + ev;
@@ -171,13 +178,42 @@ struct TsStageRegs {
   float4 v[2];
 };
 
+// Rows that arrive while the kernel runs (gated pass) are read with ld.global.cg: coherent at L2, where the copy
+// engine's writes land; ld.global.nc (__ldg) presumes data that is constant for the kernel's lifetime.
 __device__ __forceinline__ float4 ts_load_quad(const FusedParams& p, int64_t row, int jq) {
   const int j0 = jq * 4;
   float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
   if (row >= p.N || j0 >= p.d) return q;
   switch (p.layout) {
+    case kLayoutCodes4: {  // two columns per byte, low nibble = even column (bb_decode_codes)
+      const uint8_t* c = reinterpret_cast<const uint8_t*>(p.x) + row * p.ldx + (j0 >> 1);
+      const uint32_t b0 = __ldcg(c), b1 = (j0 + 2 < p.d) ? (uint32_t)__ldcg(c + 1) : 0u;
+      const float* t = p.code_table + (size_t)j0 * p.code_table_ld;
+      q.x = __ldg(t + (b0 & 15u));
+      if (j0 + 1 < p.d) q.y = __ldg(t + p.code_table_ld + (b0 >> 4));
+      if (j0 + 2 < p.d) q.z = __ldg(t + 2 * p.code_table_ld + (b1 & 15u));
+      if (j0 + 3 < p.d) q.w = __ldg(t + 3 * p.code_table_ld + (b1 >> 4));
+      return q;
+    }
+    case kLayoutCodes8: {
+      const uint8_t* c = reinterpret_cast<const uint8_t*>(p.x) + row * p.ldx + j0;
+      const float* t = p.code_table + (size_t)j0 * p.code_table_ld;
+      q.x = __ldg(t + __ldcg(c));
+      if (j0 + 1 < p.d) q.y = __ldg(t + p.code_table_ld + __ldcg(c + 1));
+      if (j0 + 2 < p.d) q.z = __ldg(t + 2 * p.code_table_ld + __ldcg(c + 2));
+      if (j0 + 3 < p.d) q.w = __ldg(t + 3 * p.code_table_ld + __ldcg(c + 3));
+      return q;
+    }
     case BB_ROW_MAJOR_F32: {
       const float* ptr = reinterpret_cast<const float*>(p.x) + row * p.ldx + j0;
+      if (p.ready_rows != nullptr) {
+        if (j0 + 3 < p.d && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)) return __ldcg(reinterpret_cast<const float4*>(ptr));
+        q.x = __ldcg(ptr);
+        if (j0 + 1 < p.d) q.y = __ldcg(ptr + 1);
+        if (j0 + 2 < p.d) q.z = __ldcg(ptr + 2);
+        if (j0 + 3 < p.d) q.w = __ldcg(ptr + 3);
+        return q;
+      }
       if (j0 + 3 < p.d && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)) return __ldg(reinterpret_cast<const float4*>(ptr));
       q.x = __ldg(ptr);
       if (j0 + 1 < p.d) q.y = __ldg(ptr + 1);
@@ -206,6 +242,29 @@ __device__ __forceinline__ float4 ts_load_quad(const FusedParams& p, int64_t row
   }
 }
 
+// Gated pass: block until the copy stream has published the rows of `tile` (acquire at system scope: the data
+// was written by the copy engine before the counter).  Bounded: after ~2 s the status word is raised and the
+// kernel carries on (the host reports the pass as failed) -- a missing publication must not hang the GPU.
+__device__ __forceinline__ void ts_wait_rows(const FusedParams& p, int tile) {
+  const long long last = (long long)(tile + 1) * kTileM;
+  const unsigned need = (unsigned)(last < p.N ? last : p.N);
+  unsigned have;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(p.ready_rows) : "memory");
+  if (have >= need) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (true) {
+    __nanosleep(64);
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(p.ready_rows) : "memory");
+    if (have >= need) return;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) {
+      if (p.gate_status != nullptr) *p.gate_status = 1;
+      return;
+    }
+  }
+}
+
 // Sixteen kernel values (scaled by ts_kscale) from sixteen accumulator values D = t / g, two at a time in packed
 // f32x2 arithmetic.  Matern-5/2: k = (1 + s + t/3) e^-s, s = sqrt(t) = sqrt(g) sqrt(D); Matern-3/2: (1 + s) e^-s;
 // RBF: 2^-t (the family constants 5 / 3 / log2(e)/2 are folded into the lengthscales by bb_model_build).
@@ -229,8 +288,143 @@ __device__ __forceinline__ unsigned long long ts_kernel_pair(float d0, float d1,
   }
 }
 
+// ---- MMA issuer ----------------------------------------------------------------------------------------------
+// The whole warp runs the loop (converged), one elected lane issues.  Order on the tensor pipe:
+//   DIST(0,s0) DIST(0,s1) | V(t,c0) V(t,c1) DIST(t+1,s0) V(t,c2) V(t,c3) DIST(t+1,s1) | ...
+// (a slab of D2 is overwritten by the next tile's distance GEMM right behind the V MMAs that read the A operand
+// stored in it -- the pipe executes in issue order).
+// CC > 0 fixes the number of 64-row K chunks at compile time (n_pad = 64 CC): every column count, instruction
+// descriptor and operand offset below becomes an immediate.  With n_pad read from the parameter block the
+// descriptor arithmetic in front of each batch of MMAs ran ~250 cycles on the single issuing thread, twelve batches
+// per tile -- a quarter of the tile time with the tensor pipe idle (profiles/r02_pipeline_trace_fused_ts_v3.txt).
+template <int CC, bool TRACE>
+__device__ __forceinline__ void ts_mma_role(const FusedParams& p, const TsSmem& s, uint32_t tmem_base, int lane) {
+  const int n_pad = CC > 0 ? CC * kChunk : p.n_pad;
+  const int C = CC > 0 ? CC : p.n_chunks;
+  const int C0 = C < 2 ? C : 2;
+  const uint32_t bt_split = (uint32_t)n_pad * kTsK2 * 2u;
+  const uint32_t a2_addr = smem_u32(s.a2), bt_addr = smem_u32(s.bt), lh_addr = smem_u32(s.lh);
+  const uint32_t ring_addr = smem_u32(s.ring);
+  const uint64_t a2_h = make_swk_desc<kTsK2>(a2_addr), a2_m = make_swk_desc<kTsK2>(a2_addr + kTsA2Split),
+                 a2_l = make_swk_desc<kTsK2>(a2_addr + 2 * kTsA2Split);
+  // descriptors differ from these bases only in the 14-bit start-address field (16-byte units; the operand images
+  // lie well inside the 256 KB window, so the additions below cannot carry out of the field)
+  const uint64_t bt_h0 = make_swk_desc<kTsK2>(bt_addr), lh_d0 = make_sw128_desc(lh_addr), ring_d0 = make_sw128_desc(ring_addr);
+  const uint32_t d2_addr = tmem_base + kTsD2Col0;
+  int mma_it = 0, mma_n = 0;
+  // distance GEMM of one slab (training columns [128 slab, ...)): six split products (2^-33)
+  auto issue_distance = [&](int slab) {
+    const int ncols = (n_pad - 128 * slab) < 128 ? (n_pad - 128 * slab) : 128;
+    const uint32_t idesc = make_idesc_f16(kTileM, ncols);
+    const uint64_t b_h = bt_h0 + (uint64_t)(((uint32_t)slab * 128u * (kTsK2 * 2u)) >> 4);
+    const uint64_t b_m = b_h + (uint64_t)(bt_split >> 4), b_l = b_m + (uint64_t)(bt_split >> 4);
+    const uint32_t d_addr = d2_addr + (uint32_t)(128 * slab);
+    if (elect_one()) {
+#pragma unroll
+      for (int kk = 0; kk < kTsK2 / 16; ++kk) {
+        const uint64_t ko = (uint64_t)(kk * 2);
+        umma_f16(d_addr, a2_h + ko, b_h + ko, idesc, kk > 0 ? 1u : 0u);
+        umma_f16(d_addr, a2_h + ko, b_m + ko, idesc, 1u);
+        umma_f16(d_addr, a2_m + ko, b_h + ko, idesc, 1u);
+        umma_f16(d_addr, a2_h + ko, b_l + ko, idesc, 1u);
+        umma_f16(d_addr, a2_l + ko, b_h + ko, idesc, 1u);
+        umma_f16(d_addr, a2_m + ko, b_m + ko, idesc, 1u);
+      }
+      umma_commit(&s.d2_full[slab]);
+    }
+    __syncwarp();
+    if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 250 + slab);
+  };
+  mbar_wait_relaxed(s.res_full, 0u);
+  uint32_t rs = 0, rph = 0;
+  // V MMAs of K chunk c: resident hi image (K*hi x Lhi, K*lo x Lhi), then the streamed lo pieces (K*hi x Llo)
+  auto issue_v_chunk = [&](int c, uint32_t par, uint32_t hi_off) {
+    const int rows_c = n_pad - c * kChunk;
+    mbar_wait_relaxed(&s.a_full[c], par);
+    tc_fence_after();
+    if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 210 + c);
+    const uint32_t a_col = d2_addr + (uint32_t)(c * kChunk);
+    if (elect_one()) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {  // K step kk only reaches columns >= 64c + 16kk
+        const uint32_t n_cols = (uint32_t)(rows_c - 16 * kk);
+        const uint64_t bd = lh_d0 + (uint64_t)((hi_off + (uint32_t)kk * 2048u) >> 4) + (uint64_t)(kk * 2);
+        const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + 16 * kk);
+        const uint32_t id = make_idesc_f16(kTileM, (int)n_cols);
+        umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, id, (c > 0 || kk > 0) ? 1u : 0u);
+        umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk + 8), bd, id, 1u);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r0 = 0; r0 < rows_c; r0 += 128) {
+      const int rows_p = rows_c - r0 < 128 ? rows_c - r0 : 128;
+      mbar_wait_relaxed(&s.r_full[rs], rph);
+      tc_fence_after();
+      const uint64_t b_d = ring_d0 + (uint64_t)((rs * kTsLoStage) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int skip = (r0 == 0) ? 16 * kk : 0;  // rows of this piece the K step cannot reach
+          const uint32_t n_cols = (uint32_t)(rows_p - skip);
+          const uint64_t bd = b_d + (uint64_t)(((uint32_t)skip * 128u) >> 4) + (uint64_t)(kk * 2);
+          const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + r0 + skip);
+          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, make_idesc_f16(kTileM, (int)n_cols), 1u);
+        }
+        umma_commit(&s.r_empty[rs]);
+      }
+      __syncwarp();
+      if (++rs == (uint32_t)kTsLoStages) {
+        rs = 0;
+        rph ^= 1u;
+      }
+    }
+    if (elect_one()) umma_commit(&s.vsub_full[c]);  // sub-block c of V has received its last contribution
+    __syncwarp();
+    if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 220 + c);
+  };
+  int j = 0;
+  int tile = blockIdx.x;
+  if (tile < p.num_tiles) {
+    mbar_wait_relaxed(s.a2_full, 0u);
+    tc_fence_after();
+    issue_distance(0);
+    if (C > 2) issue_distance(1);
+  }
+  for (; tile < p.num_tiles; tile += gridDim.x, ++j) {
+    const uint32_t par = (uint32_t)(j & 1);
+    const bool has_next = tile + (int)gridDim.x < p.num_tiles;
+    mma_it = j;
+    if (j > 0) mbar_wait_relaxed(s.v_empty, par ^ 1u);  // the previous tile's |V|^2 has been read
+    tc_fence_after();
+    if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, j, 200);
+    uint32_t hi_off = 0;
+#pragma unroll
+    for (int c = 0; c < (CC > 0 ? (CC < 2 ? CC : 2) : 2); ++c) {
+      if (c < C0) {
+        issue_v_chunk(c, par, hi_off);
+        hi_off += (uint32_t)(n_pad - c * kChunk) * 128u;
+      }
+    }
+    if (has_next) {
+      mbar_wait_relaxed(s.a2_full, par ^ 1u);  // the next tile's candidate rows are staged
+      tc_fence_after();
+      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, j, 260);
+      issue_distance(0);
+    }
+#pragma unroll
+    for (int c = 2; c < (CC > 0 ? CC : 4); ++c) {
+      if (c < C) {
+        issue_v_chunk(c, par, hi_off);
+        hi_off += (uint32_t)(n_pad - c * kChunk) * 128u;
+      }
+    }
+    if (has_next && C > 2) issue_distance(1);
+  }
+}
+
 template <int FAMILY, bool TASKS, bool TRACE>
-__global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams p) {
+__global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TsSmem s;
   ts_carve(smem_raw, p.n_pad, p.n_tasks, &s);
@@ -241,7 +435,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
   if (tid == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
 
   // ---- one-time setup ----
-  if (warp == kWarpMma && lane == 0) {
+  if (warp == kTsWarpMma && lane == 0) {
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s.a_full[i], kComputeWarps);
       mbar_init(&s.vsub_full[i], 1);
@@ -253,29 +447,31 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
     mbar_init(&s.d2_full[0], 1);
     mbar_init(&s.d2_full[1], 1);
     mbar_init(s.a2_full, kComputeWarps);
-    mbar_init(s.v_empty, kComputeWarps);
+    mbar_init(s.v_empty, kTsEpiWarps);
     mbar_init(s.res_full, 1);
+    mbar_init(&s.mean_full[0], kComputeWarps);
+    mbar_init(&s.mean_full[1], kComputeWarps);
     fence_mbar_init();
   }
-  if (warp == kWarpProducer) {
+  if (warp == kTsWarpProducer) {
     tmem_alloc(s.tmem_ptr, 512);
     tmem_relinquish();
   }
-  for (int e = tid; e < (int)(3 * kTsA2Split / 16); e += kFusedThreads)  // unused K columns stay zero for good
+  for (int e = tid; e < (int)(3 * kTsA2Split / 16); e += kTsThreads)  // unused K columns stay zero for good
     reinterpret_cast<uint4*>(s.a2)[e] = make_uint4(0u, 0u, 0u, 0u);
-  for (int e = tid; e < 32; e += kFusedThreads) {
+  for (int e = tid; e < 32; e += kTsThreads) {
     s.cscale_s[e] = e < p.d_pad ? __ldg(p.cand_scale + e) : 0.f;
     s.cshift_s[e] = e < p.d_pad ? __ldg(p.cand_shift + e) : 0.f;
   }
-  for (int e = tid; e < p.n_pad; e += kFusedThreads) {
+  for (int e = tid; e < p.n_pad; e += kTsThreads) {
     s.alpha_s[e] = __ldg(p.ts_alpha + e);
     s.ttask[e] = TASKS ? __ldg(p.train_task + e) : 0;
   }
-  for (int e = tid; e < p.n_tasks * p.n_tasks; e += kFusedThreads) s.tcov[e] = __ldg(p.task_covar + e);
-  for (int e = tid; e < p.n_tasks; e += kFusedThreads) s.meanc[e] = __ldg(p.mean_const + e);
-  for (int e = tid; e < 2 * kTileM; e += kFusedThreads) s.cand_task[e] = 0;
+  for (int e = tid; e < p.n_tasks * p.n_tasks; e += kTsThreads) s.tcov[e] = __ldg(p.task_covar + e);
+  for (int e = tid; e < p.n_tasks; e += kTsThreads) s.meanc[e] = __ldg(p.mean_const + e);
+  for (int e = tid; e < kTsTaskSlots * kTileM; e += kTsThreads) s.cand_task[e] = 0;
   if (p.has_acq && p.z != nullptr)
-    for (int e = tid; e < p.S; e += kFusedThreads) s.z_s[e] = __ldg(p.z + e);
+    for (int e = tid; e < p.S; e += kTsThreads) s.z_s[e] = __ldg(p.z + e);
   fence_proxy_async();  // the zero-filled A2 tile is read by the tensor-core (async) proxy
   tc_fence_before();
   __syncthreads();
@@ -299,9 +495,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
 
   if (warp < kComputeWarps) {
     // =====================================================================================================
-    // compute warps.  Conversion / epilogue: thread = TMEM lane (candidate row_e of the tile) x column group cg
-    // (16 of the 64 columns of a chunk).  Acquisition: warp (quarter q, cg) takes rows 32q + 8cg .. +7, four
-    // lanes per row.
+    // conversion warps.  Thread = TMEM lane (candidate row_e of the tile) x column group cg (16 of the 64
+    // columns of a chunk): candidate rows -> A2 operand panels, D2 -> kernel values -> K* operand in TMEM,
+    // mean partials sum_i k_i alpha_i -> shared memory for the epilogue warps.
     // =====================================================================================================
     const int row_e = tid & 127, cg = tid >> 7, quarter = warp & 3;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -316,17 +512,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
       const float c3 = (FAMILY == BB_KERNEL_RBF) ? -g : -kLog2e * sg;
       cst.c3 = pack2(c3, c3);
     }
-    const float inv_v_scale2 = p.inv_r_scale2 / (p.ts_kscale * p.ts_kscale);
-    long long best = kEmptyKey;
     TsStageRegs regs;
 
     auto prefetch = [&](int tile) {
       const int64_t row = (int64_t)tile * kTileM + row_e;
+      if (p.ready_rows != nullptr) ts_wait_rows(p, tile);
       regs.v[0] = (cg < dq) ? ts_load_quad(p, row, cg) : make_float4(0.f, 0.f, 0.f, 0.f);
       regs.v[1] = (cg + 4 < dq) ? ts_load_quad(p, row, cg + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    int trace_it = 0, trace_n = 0;  // test-only event trace: tile counter the next events are filed under
     // scaled candidate rows -> fp16 hi/mid/lo A2 panels; the thread that owns quad 7 appends |a|^2 P and P1
-    auto stage_a2 = [&](int buf) {
+    auto stage_a2 = [&](int slot) {
       float an = 0.f;
       float a7[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -337,7 +533,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
           const float4 q = regs.v[u];
           if (TASKS && p.task_col >= j0 && p.task_col < j0 + 4) {
             const float tv = (p.task_col == j0) ? q.x : (p.task_col == j0 + 1) ? q.y : (p.task_col == j0 + 2) ? q.z : q.w;
-            s.cand_task[buf * kTileM + row_e] = min(max(__float2int_rn(tv), 0), p.n_tasks - 1);
+            s.cand_task[slot * kTileM + row_e] = min(max(__float2int_rn(tv), 0), p.n_tasks - 1);
           }
           float a[4];
           a[0] = fmaf(q.x, s.cscale_s[j0], s.cshift_s[j0]);
@@ -361,6 +557,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
         }
       }
       s.an_part[cg * kTileM + row_e] = an;
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 121);
       if (cg != 3) {
         bar_quarter_arrive(2 + quarter);
       } else {
@@ -376,23 +573,22 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
         *reinterpret_cast<uint2*>(s.a2 + kTsA2Split + off) = mid;
         *reinterpret_cast<uint2*>(s.a2 + 2 * kTsA2Split + off) = lo;
       }
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 122);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(s.a2_full);
     };
 
-    const bool is_mc = p.has_acq && p.acq.kind <= BB_ACQ_QPI;
     // One K* chunk: D2 (TMEM) -> kernel values -> fp16 hi/lo written over the same TMEM columns; returns the
     // chunk's contribution to sum_i k_i alpha_i in `mean2`.
-    int trace_it = 0, trace_n = 0;  // test-only event trace: tile counter the next events are filed under
-    auto convert_chunk = [&](int c, int buf, unsigned long long& mean2) {
+    auto convert_chunk = [&](int c, int slot, unsigned long long& mean2) {
       float v[16];
       const uint32_t col = kTsD2Col0 + (uint32_t)(c * kChunk + cg * 16);
       tmem_ld16(tmem_base + lane_base + col, v);
       tmem_ld_wait();
       if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 100 + c);
       const int i0 = c * kChunk + cg * 16;
-      const float* tcrow = s.tcov + (TASKS ? s.cand_task[buf * kTileM + row_e] : 0) * p.n_tasks;
+      const float* tcrow = s.tcov + (TASKS ? s.cand_task[slot * kTileM + row_e] : 0) * p.n_tasks;
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -414,10 +610,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
       if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 110 + c);
     };
     // Schedule (software-pipelined over tiles; D2 lives in two 128-column slabs = chunks {0,1} and {2,3}):
-    //   iteration t:  [slab 1 of tile t ready]  stage A2(t+1), convert chunks 2,3 of tile t
+    //   iteration t:  [slab 1 of tile t ready]   stage A2(t+1), convert chunks 2,3 of tile t, publish the mean partials
     //                 [slab 0 of tile t+1 ready] convert chunks 0,1 of tile t+1      <- runs under V(t) on the tensor pipe
-    //                 epilogue + acquisition of tile t
-    // so the tensor pipe sees V(t,c0) V(t,c1) DIST(t+1,slab0) V(t,c2) V(t,c3) DIST(t+1,slab1) back to back.
+    // so the tensor pipe sees V(t,c0) V(t,c1) DIST(t+1,slab0) V(t,c2) V(t,c3) DIST(t+1,slab1) back to back, and the
+    // epilogue warps finish tile t (|V|^2, acquisition) while these warps are already converting tile t+1.
     const int C0 = C < 2 ? C : 2;  // chunks in slab 0
     int it = 0;
     int tile = blockIdx.x;
@@ -431,9 +627,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
       for (int c = 0; c < C0; ++c) convert_chunk(c, 0, mean_cur);
     }
     for (; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
+      const int buf = it & 1, slot = it & (kTsTaskSlots - 1), slot_next = (it + 1) & (kTsTaskSlots - 1);
       const uint32_t par = (uint32_t)(it & 1);
-      const int64_t row0 = (int64_t)tile * kTileM;
       const int next = tile + (int)gridDim.x;
       // ---- upper chunks of this tile; the A2 tile is free once this tile's distance GEMMs are complete ----
       trace_it = it;
@@ -443,131 +638,153 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
       }
       if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 161);
       if (next < p.num_tiles) {
-        stage_a2(buf ^ 1);
+        stage_a2(slot_next);
         if (next + (int)gridDim.x < p.num_tiles) prefetch(next + gridDim.x);
       }
       if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 120);
-      for (int c = 2; c < C; ++c) convert_chunk(c, buf, mean_cur);
+      for (int c = 2; c < C; ++c) convert_chunk(c, slot, mean_cur);
+      // mean partials of tile `it`: buffer it & 1 was last read by the epilogue of tile it - 2, which finished
+      // reading before it released the V accumulator -- and this tile's D2 could not exist before that
       s.mean_part[(buf * 4 + cg) * kTileM + row_e] = lo_of(mean_cur) + hi_of(mean_cur);
       mean_cur = 0ull;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.mean_full[buf]);
       // ---- lower chunks of the NEXT tile: their distance GEMM was issued behind V(t, c1) ----
       if (next < p.num_tiles) {
         mbar_wait(&s.d2_full[0], par ^ 1u);
         tc_fence_after();
         if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 160);
         trace_it = it + 1;
-        for (int c = 0; c < C0; ++c) convert_chunk(c, buf ^ 1, mean_cur);
+        for (int c = 0; c < C0; ++c) convert_chunk(c, slot_next, mean_cur);
         trace_it = it;
       }
-
-      // ---- |V|^2: the 64 columns of sub-block c are final once chunk c's MMAs have completed ----
-      {
-        unsigned long long ss2 = 0ull;
-        for (int sb = 0; sb < C; ++sb) {
-          float v[16];
-          mbar_wait(&s.vsub_full[sb], par);
-          tc_fence_after();
-          if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 130 + sb);
-          tmem_ld16(tmem_base + lane_base + (uint32_t)(sb * kChunk + cg * 16), v);
+    }
+    if (TRACE && tid == 0 && p.trace != nullptr && blockIdx.x == 0) p.trace[0] = p.trace_cap;
+  } else if (warp < kTsWarpProducer) {
+    // =====================================================================================================
+    // epilogue warps: warp 16 + q owns TMEM lanes 32q..32q+31, one candidate row per thread.
+    //   |V|^2 over the row's n_pad accumulator columns (sub-block sb is final once chunk sb's MMAs completed),
+    //   moments, acquisition value, running packed-key arg-max.  Everything after the accumulator has been read
+    //   runs under the NEXT tile's MMAs and conversions.
+    // =====================================================================================================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const float inv_v_scale2 = p.inv_r_scale2 / (p.ts_kscale * p.ts_kscale);
+    const bool is_mc = p.has_acq && p.acq.kind <= BB_ACQ_QPI;
+    const float log_tau = (p.has_acq && p.acq.kind == BB_ACQ_QLOGEI) ? logf(p.acq.tau_relu) : 0.f;
+    long long best = kEmptyKey;
+    int trace_n = 0;
+    const bool tr = (tid == kTsEpiWarp0 * 32);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1, slot = it & (kTsTaskSlots - 1);
+      const uint32_t par = (uint32_t)(it & 1);
+      unsigned long long ssa = 0ull, ssb = 0ull;
+      for (int sb = 0; sb < C; ++sb) {
+        mbar_wait_relaxed(&s.vsub_full[sb], par);
+        tc_fence_after();
+        if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 130 + sb);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[32];
+          tmem_ld32(tmem_base + lane_base + (uint32_t)(sb * kChunk + h * 32), v);
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const unsigned long long vv = pack2(v[2 * e], v[2 * e + 1]);
-            ss2 = fma2(vv, vv, ss2);
+            const unsigned long long va = pack2(v[4 * e], v[4 * e + 1]), vb = pack2(v[4 * e + 2], v[4 * e + 3]);
+            ssa = fma2(va, va, ssa);
+            ssb = fma2(vb, vb, ssb);
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s.v_empty);
-        if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 140);
-        s.var_part[(buf * 4 + cg) * kTileM + row_e] = lo_of(ss2) + hi_of(ss2);
       }
-      bar_quarter_sync(6 + quarter);
+      // inputs that the conversion warps overwrite two tiles later are read BEFORE the accumulator is released:
+      // V(t+1) waits for v_empty(t), DIST(t+2) follows V(t+1), and only then can those buffers be written again
+      mbar_wait_relaxed(&s.mean_full[buf], (uint32_t)((it >> 1) & 1));
+      const float mp = (s.mean_part[(buf * 4 + 0) * kTileM + r] + s.mean_part[(buf * 4 + 1) * kTileM + r]) +
+                       (s.mean_part[(buf * 4 + 2) * kTileM + r] + s.mean_part[(buf * 4 + 3) * kTileM + r]);
+      const int ctr = TASKS ? s.cand_task[slot * kTileM + r] : 0;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s.v_empty);
+      if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 140);
 
-      // ---- moments + acquisition: rows 32q + 8cg + (lane >> 2), four lanes per row ----
-      {
-        const int sub = lane & 3;
-        const int r = quarter * 32 + cg * 8 + (lane >> 2);
-        float mp = s.mean_part[(buf * 4 + sub) * kTileM + r];
-        float vp = s.var_part[(buf * 4 + sub) * kTileM + r];
-        mp += __shfl_xor_sync(0xffffffffu, mp, 1);
-        vp += __shfl_xor_sync(0xffffffffu, vp, 1);
-        mp += __shfl_xor_sync(0xffffffffu, mp, 2);
-        vp += __shfl_xor_sync(0xffffffffu, vp, 2);
-        const int ctr = TASKS ? s.cand_task[buf * kTileM + r] : 0;
-        const float kss = (TASKS || p.scaled) ? s.tcov[ctr * p.n_tasks + ctr] : 1.0f;
-        const float var_t = fmaxf(kss - vp * inv_v_scale2, 1e-10f);
-        const float mu = fmaf(p.y_std, s.meanc[ctr] + mp, p.y_mean);
-        const float var = p.y_std * p.y_std * var_t;
-        const int64_t row = row0 + r;
-        const bool live = row < p.N;
-        if (sub == 0 && live) {
-          if (p.mu) p.mu[row] = mu;
-          if (p.var) p.var[row] = var;
-        }
-        if (p.has_acq) {
-          float score = 0.f;
-          if (is_mc) {
-            float c0, c1, s0 = 0.f, s1 = 0.f;
-            mc_coef(p.acq, mu, var, c0, c1);
-            if (fast_mc) {
-              const bool fast = mc_row_fast_part(s.mc_tab, c0, c1, sub, s0, s1);
-              s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-              s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-              s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-              s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-              // rows outside the tabulated envelope: exact sum over all S samples, the whole warp per row
-              unsigned need = __ballot_sync(0xffffffffu, !fast && sub == 0);
-              while (need != 0u) {
-                const int b = __ffs(need) - 1;
-                need &= need - 1u;
-                const float e0 = __shfl_sync(0xffffffffu, c0, b), e1 = __shfl_sync(0xffffffffu, c1, b);
-                float a0, a1;
-                mc_row_exact_warp(s.z_s, p.S, e0, e1, lane, a0, a1);
-                if ((lane >> 2) == (b >> 2)) {
-                  s0 = a0;
-                  s1 = a1;
-                }
+      const float vp = (lo_of(ssa) + hi_of(ssa)) + (lo_of(ssb) + hi_of(ssb));
+      const float kss = (TASKS || p.scaled) ? s.tcov[ctr * p.n_tasks + ctr] : 1.0f;
+      const float var_t = fmaxf(kss - vp * inv_v_scale2, 1e-10f);
+      const float mu = fmaf(p.y_std, s.meanc[ctr] + mp, p.y_mean);
+      const float var = p.y_std * p.y_std * var_t;
+      const int64_t row = (int64_t)tile * kTileM + r;
+      const bool live = row < p.N;
+      if (live) {
+        if (p.mu) p.mu[row] = mu;
+        if (p.var) p.var[row] = var;
+      }
+      if (p.has_acq) {
+        float score = 0.f;
+        if (is_mc) {
+          float c0, c1, s0 = 0.f, s1 = 0.f;
+          mc_coef(p.acq, mu, var, c0, c1);
+          if (fast_mc) {
+            const bool fast = mc_row_fast(s.mc_tab, c0, c1, s0, s1);
+            if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 142);
+            // rows outside the tabulated envelope: exact sum over all S samples, the whole warp per row
+            unsigned need = __ballot_sync(0xffffffffu, !fast);
+            while (need != 0u) {
+              const int b = __ffs(need) - 1;
+              need &= need - 1u;
+              const float e0 = __shfl_sync(0xffffffffu, c0, b), e1 = __shfl_sync(0xffffffffu, c1, b);
+              float a0, a1;
+              mc_row_exact_warp(s.z_s, p.S, e0, e1, lane, a0, a1);
+              if (lane == b) {
+                s0 = a0;
+                s1 = a1;
               }
-            } else if (p.acq.kind != BB_ACQ_QUCB && p.acq.kind != BB_ACQ_QSR) {
-              const int per = p.S >> 2;  // S is a multiple of 16
-              mc_accumulate(p.acq.kind, c0, c1, reinterpret_cast<const float4*>(s.z_s + sub * per), per >> 2, s0, s1);
-              s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-              s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-              s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-              s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
             }
-            score = mc_finalize(p.acq, mu, var, s0, s1, p.S, s.zstat[0], s.zstat[1]);
-          } else if (sub == 0) {
-            score = analytic_value(p.acq, mu, var);
+          } else if (p.acq.kind != BB_ACQ_QUCB && p.acq.kind != BB_ACQ_QSR) {
+            // per-sample kinds without a table: the warp takes its 32 rows one after the other, lane l sums the
+            // sample groups l, l + 32, ... (fixed order: a row's value does not depend on where it is evaluated)
+            for (int b = 0; b < 32; ++b) {
+              const float e0 = __shfl_sync(0xffffffffu, c0, b), e1 = __shfl_sync(0xffffffffu, c1, b);
+              float a0, a1;
+              mc_row_groups_warp(p.acq.kind, s.z_s, p.S, e0, e1, lane, a0, a1);
+              if (lane == b) {
+                s0 = a0;
+                s1 = a1;
+              }
+            }
           }
-          if (sub == 0 && live) {
-            if (p.score) p.score[row] = score;
-            const bool ok = (p.keep == nullptr || p.keep[row] != 0) && !(score != score);
-            if (ok) {
-              const long long key = pack_key(score, (uint32_t)(row + p.index_offset));
-              best = key > best ? key : best;
-            }
+          if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 143);
+          score = (p.acq.kind == BB_ACQ_QLOGEI) ? log_tau + logf((s0 + 0.1f * s1) / (float)p.S)
+                                                 : mc_finalize(p.acq, mu, var, s0, s1, p.S, s.zstat[0], s.zstat[1]);
+        } else {
+          score = analytic_value(p.acq, mu, var);
+        }
+        if (live) {
+          if (p.score) p.score[row] = score;
+          const bool ok = (p.keep == nullptr || p.keep[row] != 0) && !(score != score);
+          if (ok) {
+            const long long key = pack_key(score, (uint32_t)(row + p.index_offset));
+            best = key > best ? key : best;
           }
         }
       }
-      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 150);
+      if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 150);
     }
     if (p.best_key != nullptr && p.has_acq) {
       for (int o = 16; o > 0; o >>= 1) {
         const long long other = __shfl_xor_sync(0xffffffffu, best, o);
         best = other > best ? other : best;
       }
-      if (lane == 0) s.best_red[warp] = best;
-      bar_compute();
-      if (tid == 0) {
+      if (lane == 0) s.best_red[quarter] = best;
+      asm volatile("bar.sync 6, 128;" ::: "memory");  // the four epilogue warps
+      if (quarter == 0 && lane == 0) {
         long long b = s.best_red[0];
-        for (int w = 1; w < kComputeWarps; ++w) b = s.best_red[w] > b ? s.best_red[w] : b;
+        for (int w = 1; w < kTsEpiWarps; ++w) b = s.best_red[w] > b ? s.best_red[w] : b;
         if (b != kEmptyKey) atomicMax(p.best_key, b);
       }
     }
-    if (TRACE && tid == 0 && p.trace != nullptr && blockIdx.x == 0) p.trace[0] = p.trace_cap;
-  } else if (warp == kWarpProducer) {
+  } else if (warp == kTsWarpProducer) {
     // =====================================================================================================
     // producer (TMA engine): resident images once, then the lo image of L^-1 piece by piece for every tile
     // =====================================================================================================
@@ -609,126 +826,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused_ts(const FusedParams
     }
     __syncwarp();
   } else {
-    // =====================================================================================================
-    // MMA issuer: the whole warp runs the loop (converged), one elected lane issues.  Order on the tensor pipe:
-    //   DIST(0,s0) DIST(0,s1) | V(t,c0) V(t,c1) DIST(t+1,s0) V(t,c2) V(t,c3) DIST(t+1,s1) | ...
-    // (a slab of D2 is overwritten by the next tile's distance GEMM right behind the V MMAs that read the A
-    // operand stored in it -- the pipe executes in issue order).
-    // =====================================================================================================
-    const uint32_t a2_addr = smem_u32(s.a2), bt_addr = smem_u32(s.bt), lh_addr = smem_u32(s.lh);
-    const uint64_t a2_h = make_swk_desc<kTsK2>(a2_addr), a2_m = make_swk_desc<kTsK2>(a2_addr + kTsA2Split),
-                   a2_l = make_swk_desc<kTsK2>(a2_addr + 2 * kTsA2Split);
-    const uint32_t d2_addr = tmem_base + kTsD2Col0;
-    const int C0 = C < 2 ? C : 2;
-    int mma_it = 0, mma_n = 0;
-    // distance GEMM of one slab (training columns [128 slab, ...)): six split products (2^-33)
-    auto issue_distance = [&](int slab) {
-      const int ncols = (p.n_pad - 128 * slab) < 128 ? (p.n_pad - 128 * slab) : 128;
-      const uint32_t idesc = make_idesc_f16(kTileM, ncols);
-      const uint32_t boff = (uint32_t)slab * 128u * (kTsK2 * 2u);  // 128 rows of 64 bytes
-      const uint64_t b_h = make_swk_desc<kTsK2>(bt_addr + boff), b_m = make_swk_desc<kTsK2>(bt_addr + bt_split + boff),
-                     b_l = make_swk_desc<kTsK2>(bt_addr + 2 * bt_split + boff);
-      const uint32_t d_addr = d2_addr + (uint32_t)(128 * slab);
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < kTsK2 / 16; ++kk) {
-          const uint64_t ko = (uint64_t)(kk * 2);
-          umma_f16(d_addr, a2_h + ko, b_h + ko, idesc, kk > 0 ? 1u : 0u);
-          umma_f16(d_addr, a2_h + ko, b_m + ko, idesc, 1u);
-          umma_f16(d_addr, a2_m + ko, b_h + ko, idesc, 1u);
-          umma_f16(d_addr, a2_h + ko, b_l + ko, idesc, 1u);
-          umma_f16(d_addr, a2_l + ko, b_h + ko, idesc, 1u);
-          umma_f16(d_addr, a2_m + ko, b_m + ko, idesc, 1u);
-        }
-        umma_commit(&s.d2_full[slab]);
-      }
-      __syncwarp();
-      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 250 + slab);
-    };
-    mbar_wait_relaxed(s.res_full, 0u);
-    uint32_t rs = 0, rph = 0;
-    // V MMAs of K chunk c: resident hi image (K*hi x Lhi, K*lo x Lhi), then the streamed lo pieces (K*hi x Llo)
-    auto issue_v_chunk = [&](int c, uint32_t par, uint32_t hi_off) {
-      const int rows_c = p.n_pad - c * kChunk;
-      mbar_wait_relaxed(&s.a_full[c], par);
-      tc_fence_after();
-      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 210 + c);
-      const uint32_t a_col = d2_addr + (uint32_t)(c * kChunk);
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {  // K step kk only reaches columns >= 64c + 16kk
-          const uint32_t n_cols = (uint32_t)(rows_c - 16 * kk);
-          const uint64_t bd = make_sw128_desc(lh_addr + hi_off + (uint32_t)kk * 2048u) + (uint64_t)(kk * 2);
-          const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + 16 * kk);
-          const uint32_t id = make_idesc_f16(kTileM, (int)n_cols);
-          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, id, (c > 0 || kk > 0) ? 1u : 0u);
-          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk + 8), bd, id, 1u);
-        }
-      }
-      __syncwarp();
-      for (int r0 = 0; r0 < rows_c; r0 += 128) {
-        const int rows_p = rows_c - r0 < 128 ? rows_c - r0 : 128;
-        mbar_wait_relaxed(&s.r_full[rs], rph);
-        tc_fence_after();
-        const uint32_t b_addr = smem_u32(s.ring + (size_t)rs * kTsLoStage);
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int skip = (r0 == 0) ? 16 * kk : 0;  // rows of this piece the K step cannot reach
-            const uint32_t n_cols = (uint32_t)(rows_p - skip);
-            const uint64_t bd = make_sw128_desc(b_addr + (uint32_t)skip * 128u) + (uint64_t)(kk * 2);
-            const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + r0 + skip);
-            umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, make_idesc_f16(kTileM, (int)n_cols), 1u);
-          }
-          umma_commit(&s.r_empty[rs]);
-        }
-        __syncwarp();
-        if (++rs == (uint32_t)kTsLoStages) {
-          rs = 0;
-          rph ^= 1u;
-        }
-      }
-      if (elect_one()) umma_commit(&s.vsub_full[c]);  // sub-block c of V has received its last contribution
-      __syncwarp();
-      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 220 + c);
-    };
-    int j = 0;
-    int tile = blockIdx.x;
-    if (tile < p.num_tiles) {
-      mbar_wait_relaxed(s.a2_full, 0u);
-      tc_fence_after();
-      issue_distance(0);
-      if (C > 2) issue_distance(1);
-    }
-    for (; tile < p.num_tiles; tile += gridDim.x, ++j) {
-      const uint32_t par = (uint32_t)(j & 1);
-      const bool has_next = tile + (int)gridDim.x < p.num_tiles;
-      mma_it = j;
-      if (j > 0) mbar_wait_relaxed(s.v_empty, par ^ 1u);  // the previous tile's |V|^2 has been read
-      tc_fence_after();
-      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, j, 200);
-      uint32_t hi_off = 0;
-      for (int c = 0; c < C0; ++c) {
-        issue_v_chunk(c, par, hi_off);
-        hi_off += (uint32_t)(p.n_pad - c * kChunk) * 128u;
-      }
-      if (has_next) {
-        mbar_wait_relaxed(s.a2_full, par ^ 1u);  // the next tile's candidate rows are staged
-        tc_fence_after();
-        if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, j, 260);
-        issue_distance(0);
-      }
-      for (int c = 2; c < C; ++c) {
-        issue_v_chunk(c, par, hi_off);
-        hi_off += (uint32_t)(p.n_pad - c * kChunk) * 128u;
-      }
-      if (has_next && C > 2) issue_distance(1);
-    }
+    // MMA issuer (ts_mma_role): n_pad = 256, the headline shape, runs the fully constant-folded instance
+    if (p.n_pad == 4 * kChunk) ts_mma_role<4, TRACE>(p, s, tmem_base, lane);
+    else ts_mma_role<0, TRACE>(p, s, tmem_base, lane);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpProducer) tmem_dealloc(tmem_base, 512);
+  if (warp == kTsWarpProducer) tmem_dealloc(tmem_base, 512);
 }
 
 // ============================================================================================================
@@ -1123,6 +1228,7 @@ int try_kmat_ts(const bb_model* m, const void* d_x, int32_t layout, int64_t N, i
 // Shape envelope of this kernel; everything else runs fused_tc.cu / fused.cu.
 bool fused_ts_supported(const FusedParams& p, int max_smem) {
   if (p.timg_l == nullptr || p.timg_b == nullptr || p.ts_alpha == nullptr) return false;
+  if (p.layout > BB_COL_MAJOR_F64 && p.layout != kLayoutCodes4 && p.layout != kLayoutCodes8) return false;
   if (p.n_pad > 256 || p.d > kTsColSq || p.family == BB_KERNEL_MATERN12) return false;
   if (p.has_acq && (p.S > 512 || (p.S & 15) != 0)) return false;
   if (p.n_tasks > kMaxTasks) return false;
@@ -1138,7 +1244,7 @@ static int launch_ts_one2(FusedParams& p, int grid, size_t smem, cudaStream_t st
     BB_CUDA(cudaFuncSetAttribute(k_fused_ts<FAMILY, TASKS, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured_for = dev;
   }
-  k_fused_ts<FAMILY, TASKS, TRACE><<<grid, kFusedThreads, smem, stream>>>(p);
+  k_fused_ts<FAMILY, TASKS, TRACE><<<grid, kTsThreads, smem, stream>>>(p);
   BB_LAUNCH_CHECK();
   return BB_OK;
 }

@@ -6,12 +6,15 @@
 // ~70 us of host time per block, more than the GPU needs for a block of 125,000 rows (60 us).
 // Replaces: SubspaceDiscrete.transform + to_tensor + optimize_acqf_discrete over a host-resident comp-rep
 // (baybe/recommenders/pure/bayesian/botorch/discrete.py:120-126).
+#include <cuda.h>
+
 #include "fused_common.cuh"
 
 namespace bb {
 int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, int64_t ldx, const bb_acq_spec* acq,
                  const float* d_z, int32_t S, const uint8_t* d_keep, float* d_mu, float* d_var, float* d_score,
-                 int64_t* d_best_key, int64_t index_offset, cudaStream_t stream, const WideCross* wc);
+                 int64_t* d_best_key, int64_t index_offset, cudaStream_t stream, const WideCross* wc,
+                 const StreamGate* gate);
 }
 extern "C" int bb_decode_codes(const uint8_t* d_codes, int32_t bits, int64_t N, int32_t d, int64_t ld_bytes,
                                const float* d_table, int32_t table_ld, float* d_out, int64_t ldo, void* stream);
@@ -75,10 +78,108 @@ extern "C" int bb_score_fused_host(const bb_model* m, const bb_acq_spec* a, cons
       ldx = d;
     }
     rc = launch_fused(m, x, dev_layout, rows, ldx, a, d_z, S, d_keep ? d_keep + lo : nullptr, nullptr, nullptr,
-                      d_score ? d_score + lo : nullptr, d_best_key, index_offset + lo, stream, nullptr);
+                      d_score ? d_score + lo : nullptr, d_best_key, index_offset + lo, stream, nullptr, nullptr);
     if (rc != BB_OK) break;
     BB_CUDA(cudaEventRecord(freed[slot], stream));
   }
   for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
   return rc;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// bb_score_fused_overlapped -- the end-to-end pass as ONE kernel launch.
+//
+// The fused kernel is launched first, over all N rows of a device staging buffer that is still EMPTY; the host
+// matrix then follows on the copy stream in growing row blocks, and after each block the copy stream publishes the
+// number of rows that have landed (cuStreamWriteValue32 into *d_ready -- a stream-ordered memory operation, no
+// kernel: every SM is occupied by the persistent scoring kernel).  The kernel's conversion warps take tiles in row
+// order and wait (ld.acquire.sys) until their tile is published, so scoring proceeds at the pace of the PCIe copy
+// and the pass costs max(copy, compute) plus the first block's latency, with no per-block launch, decode kernel or
+// fp32 intermediate: level codes are expanded in the kernel's staging step.  Shapes outside the headline kernel's
+// envelope return BB_ERR_UNSUPPORTED before anything is enqueued (callers then use bb_score_fused_host).
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+extern "C" int bb_score_fused_overlapped(const bb_model* m, const bb_acq_spec* a, const void* h_x, int32_t host_format,
+                                         int64_t N, int64_t ld, const float* d_table, int32_t table_ld, void* d_stage,
+                                         int64_t stage_bytes, uint32_t* d_ready, int32_t* d_status,
+                                         const uint8_t* d_keep, const float* d_z, int32_t S, float* d_score,
+                                         int64_t* d_best_key, int64_t index_offset, void* stream_,
+                                         void* copy_stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_, copy = (cudaStream_t)copy_stream_;
+  BB_CHECK_ARG(m && m->abi_version == BB_ABI_VERSION && a, "bb_score_fused_overlapped: model / acquisition spec missing");
+  BB_CHECK_ARG(N >= 0 && N < (1ll << 32), "bb_score_fused_overlapped: row count outside the 32-bit publication counter");
+  BB_CHECK_ARG(d_stage && d_ready && d_status && d_best_key, "bb_score_fused_overlapped: staging / counter / status / key missing");
+  BB_CHECK_ARG(stream != copy, "bb_score_fused_overlapped: the copy stream must differ from the compute stream");
+  const int d = m->d;
+  size_t row_bytes;
+  StreamGate gate;
+  gate.ready_rows = d_ready;
+  gate.status = d_status;
+  gate.code_table = d_table;
+  gate.code_table_ld = table_ld;
+  switch (host_format) {
+    case BB_HOST_ROWS_F32: row_bytes = (size_t)ld * 4; gate.layout = BB_ROW_MAJOR_F32; gate.code_table = nullptr; break;
+    case BB_HOST_CODES4: row_bytes = (size_t)ld; gate.layout = kLayoutCodes4; break;
+    case BB_HOST_CODES8: row_bytes = (size_t)ld; gate.layout = kLayoutCodes8; break;
+    default:
+      set_error("bb_score_fused_overlapped: host format %d is not covered (float64 rows: bb_score_fused_host)", host_format);
+      return BB_ERR_UNSUPPORTED;
+  }
+  if (gate.layout >= kLayoutCodes4) {
+    const int bits = gate.layout == kLayoutCodes4 ? 4 : 8;
+    BB_CHECK_ARG(d_table && table_ld >= 1 && table_ld <= (1 << bits), "bb_score_fused_overlapped: value table missing / too wide");
+    BB_CHECK_ARG(ld >= (bits == 8 ? d : (d + 1) / 2), "bb_score_fused_overlapped: code rows shorter than d columns");
+  } else {
+    BB_CHECK_ARG(ld >= d, "bb_score_fused_overlapped: leading dimension smaller than d");
+  }
+  BB_CHECK_ARG((int64_t)(row_bytes * (size_t)N) <= stage_bytes, "bb_score_fused_overlapped: staging buffer too small");
+  BB_CHECK_SUPPORTED(fused_gate_supported(m, a, S), "bb_score_fused_overlapped: shape outside the headline kernel's envelope");
+  static WriteValue32Fn write32 = nullptr;
+  if (write32 == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    BB_CUDA(cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qres));
+    BB_CHECK_SUPPORTED(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuStreamWriteValue32 is not available");
+    write32 = reinterpret_cast<WriteValue32Fn>(fn);
+  }
+  int rc = bb_best_init(d_best_key, stream);
+  if (rc != BB_OK || N == 0) return rc;
+  BB_CHECK_ARG(h_x != nullptr, "bb_score_fused_overlapped: host matrix is null");
+  // counter and status back to zero on the compute stream, ahead of the kernel and (through the event) of the copies
+  BB_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
+  if (write32((CUstream)stream, (CUdeviceptr)(uintptr_t)d_ready, 0u, 0u) != CUDA_SUCCESS) {
+    set_error("cuStreamWriteValue32 failed on the compute stream");
+    return BB_ERR_CUDA;
+  }
+  cudaEvent_t ev;
+  BB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  BB_CUDA(cudaEventRecord(ev, stream));  // earlier readers of the staging buffer are done; the counter is reset
+  BB_CUDA(cudaStreamWaitEvent(copy, ev, 0));
+  cudaEventDestroy(ev);
+  rc = launch_fused(m, d_stage, BB_ROW_MAJOR_F32, N, ld, a, d_z, S, d_keep, nullptr, nullptr, d_score, d_best_key,
+                    index_offset, stream, nullptr, &gate);
+  if (rc != BB_OK) {  // nothing will consume the rows: still publish, so that a half-issued pass cannot stall later work
+    write32((CUstream)copy, (CUdeviceptr)(uintptr_t)d_ready, (cuuint32_t)N, 0u);
+    return rc;
+  }
+  // growing blocks: the first one small (the kernel idles until it lands), later ones large (few API calls)
+  int64_t lo = 0, rows = 16384;
+  while (lo < N) {
+    const int64_t n = (N - lo) < rows ? (N - lo) : rows;
+    const cudaError_t e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d_stage) + (size_t)lo * row_bytes,
+                                          reinterpret_cast<const uint8_t*>(h_x) + (size_t)lo * row_bytes,
+                                          (size_t)n * row_bytes, cudaMemcpyHostToDevice, copy);
+    lo += n;
+    // publish even after a failed copy: the kernel must never be left waiting
+    const CUresult w = write32((CUstream)copy, (CUdeviceptr)(uintptr_t)d_ready, (cuuint32_t)(e == cudaSuccess ? lo : N), 0u);
+    if (e != cudaSuccess || w != CUDA_SUCCESS) {
+      if (w == CUDA_SUCCESS && lo < N) write32((CUstream)copy, (CUdeviceptr)(uintptr_t)d_ready, (cuuint32_t)N, 0u);
+      set_error("bb_score_fused_overlapped: host->device copy / publication failed: %s", cudaGetErrorString(e));
+      return BB_ERR_CUDA;
+    }
+    if (rows < 262144) rows *= 2;
+  }
+  return BB_OK;
 }

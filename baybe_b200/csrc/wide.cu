@@ -414,7 +414,7 @@ static int launch_kmat_one(WideParams& p, int sms, int max_smem, cudaStream_t st
   p.stages = BITS ? 4 : 2;
   const size_t smem = wide_carve<BITS>(nullptr, p, nullptr);
   BB_CHECK_SUPPORTED(smem <= (size_t)max_smem, "wide kernel-matrix path: shared-memory budget exceeded (%zu bytes)", smem);
-  BB_CUDA(cudaFuncSetAttribute(k_kmat_tc<FAMILY, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BB_SMEM_OPTIN_ONCE((k_kmat_tc<FAMILY, BITS>));
   const int grid = p.num_items < sms ? p.num_items : sms;
   k_kmat_tc<FAMILY, BITS><<<grid, kFusedThreads, smem, stream>>>(p);
   BB_LAUNCH_CHECK();
@@ -469,10 +469,11 @@ static int launch_kmat_cols(const bb_model* m, const WideColumns& c, const void*
   p.vec_ok = ((ldk & 3) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) ? 1 : 0;
   p.num_items = (int)((N + kWTileM - 1) / kWTileM) * p.n_halves;
   p.bits_vec = (bits && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (m->d & 127) == 0) ? 1 : 0;
-  int dev = 0, max_smem = 0, sms = 0;
-  BB_CUDA(cudaGetDevice(&dev));
-  BB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  BB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int max_smem = 0, sms = 0;
+  {
+    const int rc_lim = device_limits(&sms, &max_smem);
+    if (rc_lim != BB_OK) return rc_lim;
+  }
   switch (m->family) {
     case BB_KERNEL_MATERN32: return launch_kmat_family<BB_KERNEL_MATERN32>(p, bits, sms, max_smem, stream);
     case BB_KERNEL_MATERN52: return launch_kmat_family<BB_KERNEL_MATERN52>(p, bits, sms, max_smem, stream);

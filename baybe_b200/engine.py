@@ -260,12 +260,17 @@ class DeviceGP:
 
     STREAM_MIN_ROWS = 262_144
     STREAM_BLOCKS = 8
+    OVERLAPPED_HOST_PASS = True  # single-launch gated pass where the headline kernel covers the shape
 
     def _host_pass(self, acq: AcqConfig, h: torch.Tensor, fmt: str, ld: int, row_bytes: int, table, zf, keep,
                    index_offset: int, want_scores: bool):
         """One ``bb_score_fused_host`` call: H2D of row blocks on the side stream overlapped with decode + scoring."""
         lib = _lib.load()
         N = h.shape[0]
+        if self.OVERLAPPED_HOST_PASS and fmt != "rows_f64" and N > 0 and not self.model.wide:
+            out = self._host_pass_overlapped(lib, acq, h, fmt, ld, row_bytes, table, zf, keep, index_offset, want_scores)
+            if out is not None:
+                return out
         rows = -(-N // self.STREAM_BLOCKS)
         rows = max(-(-rows // 128) * 128, 128)
         coded = fmt.startswith("codes")
@@ -292,6 +297,42 @@ class DeviceGP:
                 C.c_void_p(self._copy_stream.cuda_stream)), "bb_score_fused_host")
             self._copy_stream.wait_stream(main)  # later work on the side stream stays ordered behind this pass
         return score, key
+
+    def _host_pass_overlapped(self, lib, acq, h, fmt, ld, row_bytes, table, zf, keep, index_offset, want_scores):
+        """``bb_score_fused_overlapped``: one kernel launch that consumes the rows while the copy stream delivers
+        them.  Returns None when the shape is outside the headline kernel's envelope (caller falls back)."""
+        N = h.shape[0]
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream()
+            if not hasattr(self, "_copy_stream"):
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            need = N * row_bytes
+            if getattr(self, "_stage_all", None) is None or self._stage_all.numel() < need:
+                self._stage_all = torch.empty(need, dtype=torch.uint8, device=self.device)
+                self._gate = torch.zeros(2, dtype=torch.int32, device=self.device)  # [rows landed, status]
+            score = torch.empty(N if want_scores else 0, dtype=torch.float32, device=self.device)
+            key = torch.empty(1, dtype=torch.int64, device=self.device)
+            c_acq = acq.to_c()
+            S = 0 if zf is None else zf.numel()
+            rc = lib.bb_score_fused_overlapped(
+                C.byref(self.model), C.byref(c_acq), C.c_void_p(h.data_ptr()), _lib.HOST_FORMAT[fmt], N, ld,
+                _ptr(table), 0 if table is None else table.shape[1], _ptr(self._stage_all), self._stage_all.numel(),
+                C.c_void_p(self._gate.data_ptr()), C.c_void_p(self._gate.data_ptr() + 4), _ptr(keep), _ptr(zf), S,
+                _ptr(score) if want_scores else None, _ptr(key), int(index_offset), _stream_ptr(),
+                C.c_void_p(self._copy_stream.cuda_stream))
+            if rc == _lib.BB_ERR_UNSUPPORTED:
+                return None
+            _lib.check(rc, "bb_score_fused_overlapped")
+            self._copy_stream.wait_stream(main)
+            self._gated_pass_pending = True
+        return score, key
+
+    def check_host_pass(self) -> None:
+        """Raise if the last overlapped host pass saw rows that were never published (synchronises)."""
+        if getattr(self, "_gated_pass_pending", False):
+            self._gated_pass_pending = False
+            if int(self._gate[1].item()) != 0:
+                raise RuntimeError("bb_score_fused_overlapped: host rows were not published within the time-out")
 
     def _score_streamed(self, acq: AcqConfig, x: torch.Tensor, zf, keep, index_offset: int, want_scores: bool):
         if x.shape[1] != self.d:

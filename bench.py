@@ -309,14 +309,14 @@ def run_b200(args):
         return finish(key)
 
     def step_e2e():
-        # public API call with the HOST candidate set in its level-coded form (4-bit codes + value table): row blocks
-        # are copied on a side stream, expanded on the device (bb_decode_codes) and scored; all bytes cross PCIe
+        # public API call with the HOST candidate set in its level-coded form (4-bit codes + value table): the fused
+        # kernel is launched once and consumes row tiles as the copy stream delivers them; all bytes cross PCIe
         # inside the step
         _, key = gp.score_coded(acq, codes_host, table, bits, z, index_offset=offset, want_scores=False)
         return finish(key)
 
     def step_e2e_f32():
-        # same with the float32 host matrix (80 B per candidate): streamed in 8 row blocks, PCIe-bound
+        # same with the float32 host matrix (80 B per candidate): PCIe-bound
         _, key = gp.score(acq, x_host, z, index_offset=offset, want_scores=False)
         return finish(key)
 
@@ -326,6 +326,7 @@ def run_b200(args):
     e2e_ms = timed(step_e2e, steps, warmup)
     key_coded = int(key_host.item())
     e2e32_ms = timed(step_e2e_f32, max(3, steps // 4), 2) / max(3, steps // 4)
+    gp.check_host_pass()
     if peer is not None:
         peer.check()
 
@@ -386,8 +387,10 @@ def run_b200(args):
             },
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(codes_host.numel() + table.numel() * 4), "d2h_bytes_per_step": 8,
-                    "api": f"DeviceGP.score_coded(pinned host {bits}-bit level codes + value table) -> bb_score_fused_host -> host "
-                           "arg-max key; H2D in 8 row blocks overlapped with decode + scoring; scores bit-identical to the float32 matrix",
+                    "api": f"DeviceGP.score_coded(pinned host {bits}-bit level codes + value table) -> bb_score_fused_overlapped "
+                           "-> host arg-max key; ONE kernel launch that consumes row tiles as the copy stream publishes "
+                           "them (growing H2D blocks + cuStreamWriteValue32), codes expanded in the kernel's staging step; "
+                           "scores bit-identical to the float32 matrix",
                     "fp32_matrix": {"value": world * N_PER_GPU / (e2e32_ms * 1e-3), "h2d_bytes_per_step": x_host.numel() * 4,
                                     "api": "DeviceGP.score(pinned host fp32 matrix)"}},
             "gpu_launches": launches,

@@ -321,6 +321,22 @@ int bb_score_fused_host(const bb_model* m, const bb_acq_spec* a, const void* h_x
                         float* const* d_rows, int64_t block_rows, const uint8_t* d_keep, const float* d_z, int32_t S,
                         float* d_score, int64_t* d_best_key, int64_t index_offset, void* stream, void* copy_stream);
 
+/* ---- the same pass as ONE kernel launch (shapes of the headline kernel: n_pad <= 256, d <= 30, S <= 512; float32
+ * rows or level codes).  The fused kernel is launched first over a device staging buffer (d_stage, stage_bytes >=
+ * N * row bytes) that is still empty; the host matrix follows on `copy_stream` in growing row blocks, and after every
+ * block the copy stream publishes the number of rows landed into *d_ready (cuStreamWriteValue32, no kernel).  The
+ * kernel takes row tiles in order and waits (ld.acquire.sys on *d_ready) until its tile is published; level codes
+ * are expanded in its staging step, so there is no per-block launch, decode kernel or fp32 intermediate and the
+ * pass costs max(copy, compute) + the first block's latency.  *d_status is raised to 1 if rows were not published
+ * within ~2 s (the kernel never hangs; the caller must treat the pass as failed).  Returns BB_ERR_UNSUPPORTED,
+ * with nothing enqueued, for shapes / formats outside the envelope: fall back to bb_score_fused_host.
+ * Replaces: the same reference path as bb_score_fused_host (botorch/discrete.py:120-126). */
+int bb_score_fused_overlapped(const bb_model* m, const bb_acq_spec* a, const void* h_x, int32_t host_format, int64_t N,
+                              int64_t ld, const float* d_table, int32_t table_ld, void* d_stage, int64_t stage_bytes,
+                              uint32_t* d_ready, int32_t* d_status, const uint8_t* d_keep, const float* d_z, int32_t S,
+                              float* d_score, int64_t* d_best_key, int64_t index_offset, void* stream,
+                              void* copy_stream);
+
 /* ---- test-only diagnostic: plain fp32 SIMT posterior (no tensor cores), used by the GPU
  * tests to separate tcgen05-path errors from formula errors.  Not called by the product. -- */
 int bb_debug_posterior_simt(const bb_model* m, const void* d_x, int32_t layout, int64_t N,

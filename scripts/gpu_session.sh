@@ -37,6 +37,9 @@ for st in $STAGES; do
       tail -8 $OUT/r02_sanitizer_memcheck.txt
       timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python scripts/ts_first_light.py n64_d4 cfg1 > $OUT/r02_sanitizer_racecheck.txt 2>&1; echo "racecheck rc=$?"
       tail -8 $OUT/r02_sanitizer_racecheck.txt ;;
+    campaign)
+      timeout 600 python -m pytest tests/test_gpu_campaign.py -m gpu -q --timeout 300 -p no:cacheprovider > $OUT/pytest_gpu_campaign.txt 2>&1; echo "campaign rc=$?"
+      tail -15 $OUT/pytest_gpu_campaign.txt ;;
     trace)
       timeout 200 python scripts/trace_timeline.py score ts > $OUT/r02_pipeline_trace_fused_ts.txt 2>&1; echo "trace rc=$?"
       head -130 $OUT/r02_pipeline_trace_fused_ts.txt ;;

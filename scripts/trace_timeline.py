@@ -27,8 +27,8 @@ n = min(int(h[0]), cap)
 ev = sorted(((int(h[2 + 2 * i]), int(h[1 + 2 * i])) for i in range(n) if int(h[2 + 2 * i]) != 0))
 t0 = ev[0][0]
 if len(sys.argv) > 2 and sys.argv[2] == "ts":  # event ids of fused_ts.cu
-    names = {100: "C chunk in regs", 110: "C chunk arrived", 120: "C stage_a2 done", 130: "C vsub ok", 140: "C v_empty arrive",
-             150: "C acquisition done", 160: "C d2 slab0(next) ok", 161: "C d2 slab1 ok", 200: "M v_empty ok",
+    names = {100: "C chunk in regs", 110: "C chunk arrived", 120: "C stage_a2 done", 121: "C  a2 stored", 122: "C  a2 quarter-synced", 130: "E vsub ok", 140: "E v_empty arrive", 142: "E  table part done", 143: "E  exact rows done",
+             150: "E acquisition done", 160: "C d2 slab0(next) ok", 161: "C d2 slab1 ok", 200: "M v_empty ok",
              210: "M a_full ok", 220: "M V chunk issued", 250: "M DIST issued slab", 260: "M a2_full ok"}
     for clk, code in ev:
         it, e = divmod(code, 1000)

@@ -87,8 +87,12 @@ def test_config2_one_million_candidates(cuda_device):
     assert torch.equal(vals, ref_vals)
 
 
-def test_streamed_host_matrix_equals_resident_scoring(cuda_device):
-    """The e2e path (host matrix streamed in row blocks) must be bit-identical to the resident one."""
+@pytest.mark.parametrize("overlapped", [True, False])
+def test_streamed_host_matrix_equals_resident_scoring(cuda_device, overlapped, monkeypatch):
+    """The e2e paths -- ONE gated launch that consumes the rows while the copy stream delivers them
+    (bb_score_fused_overlapped), or row blocks scored launch by launch (bb_score_fused_host) -- must be
+    bit-identical to the resident one."""
+    monkeypatch.setattr(DeviceGP, "OVERLAPPED_HOST_PASS", overlapped)
     w = numeric_grid_workload(N=600_001, d=20, n=256, seed=3)  # ragged last block
     gp = DeviceGP(device=cuda_device, **w.gp_kwargs())
     z = sobol_normal_samples(512, 1, seed=5)
@@ -99,14 +103,22 @@ def test_streamed_host_matrix_equals_resident_scoring(cuda_device):
     s_res, k_res = gp.score(acq, x_host.to(cuda_device), z[:, 0], keep=keep, index_offset=1000)
     s_str, k_str = gp.score(acq, x_host, z[:, 0], keep=keep, index_offset=1000)
     assert torch.equal(s_res, s_str) and int(k_res.item()) == int(k_str.item())
+    gp.check_host_pass()
     s64, k64 = gp.score(acq, torch.from_numpy(w.candidates), z[:, 0], keep=keep, index_offset=1000)  # pageable fp64
     assert torch.equal(s_res, s64) and int(k_res.item()) == int(k64.item())
+    s32, k32 = gp.score(acq, torch.from_numpy(w.candidates).to(torch.float32), z[:, 0], keep=keep, index_offset=1000)  # pageable fp32
+    assert torch.equal(s_res, s32) and int(k_res.item()) == int(k32.item())
+    gp.check_host_pass()
 
 
-def test_level_coded_candidates_score_bit_identically(cuda_device):
-    """The compact exact form of a discrete space (4- or 8-bit level codes + value table, bb_decode_codes) through
-    bb_score_fused_host (pinned host codes, H2D overlapped with decode + scoring) and from device-resident codes."""
+@pytest.mark.parametrize("overlapped", [True, False])
+def test_level_coded_candidates_score_bit_identically(cuda_device, overlapped, monkeypatch):
+    """The compact exact form of a discrete space (4- or 8-bit level codes + value table) from pinned host codes --
+    expanded inside the gated single-launch pass (bb_score_fused_overlapped) or block by block (bb_decode_codes +
+    bb_score_fused_host) -- and from device-resident codes."""
     from baybe_b200.bits import decode_levels, encode_levels
+
+    monkeypatch.setattr(DeviceGP, "OVERLAPPED_HOST_PASS", overlapped)
 
     for levels, bits_expected in ((11, 4), (40, 8)):
         w = numeric_grid_workload(N=300_017, d=20, n=256, seed=4, levels=levels)  # ragged last block
@@ -127,8 +139,30 @@ def test_level_coded_candidates_score_bit_identically(cuda_device):
         assert torch.equal(s_res, s_dev) and int(k_res.item()) == int(k_dev.item())
         _, k2 = gp.score_coded(acq, ch, table, bits, z[:, 0], keep=keep, index_offset=77, want_scores=False)  # buffers reused
         assert int(k2.item()) == int(k_res.item())
+        gp.check_host_pass()
     with pytest.raises(ValueError):
         gp.score_coded(acq, ch[:, :5].contiguous(), table, bits, z[:, 0])
+
+
+def test_overlapped_pass_small_ragged_and_masked(cuda_device):
+    """bb_score_fused_overlapped on sets smaller than its first copy block, with a ragged last tile, several
+    acquisition kinds and the posterior-free key only."""
+    from baybe_b200.bits import encode_levels
+
+    for N in (1, 130, 777, 20_001):
+        w = numeric_grid_workload(N=N, d=20, n=100, seed=N)
+        gp = DeviceGP(device=cuda_device, **w.gp_kwargs())
+        z = sobol_normal_samples(256, 1, seed=9)
+        for kind in ("qLogEI", "qEI", "UCB"):
+            acq = AcqConfig(kind=kind, best_f=gp.best_f(AcqConfig(kind=kind)))
+            x32 = torch.from_numpy(w.candidates).to(torch.float32)
+            s_res, k_res = gp.score(acq, x32.to(cuda_device), z[:, 0], index_offset=5)
+            s_h, k_h = gp.score(acq, x32.pin_memory(), z[:, 0], index_offset=5)
+            assert torch.equal(s_res, s_h) and int(k_res.item()) == int(k_h.item())
+            codes, table, bits = encode_levels(w.candidates)
+            s_c, k_c = gp.score_coded(acq, torch.from_numpy(codes).pin_memory(), table, bits, z[:, 0], index_offset=5)
+            assert torch.equal(s_res, s_c) and int(k_res.item()) == int(k_c.item())
+            gp.check_host_pass()
 
 
 def test_config5_four_tasks_one_million_candidates(cuda_device):
