@@ -52,6 +52,7 @@ struct TsSmem {
   long long* best_red;
   uint32_t* tmem_ptr;
   float* zstat;
+  volatile unsigned* ready_cache;
 };
 
 __host__ __device__ inline uint32_t ts_hi_bytes(int n_pad) {  // sum over chunks of (n_pad - 64c) rows x 128 B
@@ -112,6 +113,7 @@ __host__ __device__ inline size_t ts_carve(uint8_t* base, int n_pad, int n_tasks
     s->best_red = reinterpret_cast<long long*>(base + o_best);
     s->tmem_ptr = reinterpret_cast<uint32_t*>(base + o_misc);
     s->zstat = reinterpret_cast<float*>(base + o_misc + 8);
+    s->ready_cache = reinterpret_cast<volatile unsigned*>(base + o_misc + 16);
   }
   return off;
 }
@@ -245,24 +247,38 @@ __device__ __forceinline__ float4 ts_load_quad(const FusedParams& p, int64_t row
 // Gated pass: block until the copy stream has published the rows of `tile` (acquire at system scope: the data
 // was written by the copy engine before the counter).  Bounded: after ~2 s the status word is raised and the
 // kernel carries on (the host reports the pass as failed) -- a missing publication must not hang the GPU.
-__device__ __forceinline__ void ts_wait_rows(const FusedParams& p, int tile) {
+// ONE thread per CTA polls: every thread of every CTA reading the same word made that L2 line the bottleneck of
+// the whole pass (75,000 requests per tile step).  The value it sees is handed to the other conversion threads
+// through shared memory + the conversion warps' barrier, and kept in a register: publications run far ahead of
+// the tiles, so most tiles need no load at all.  Called by all 512 conversion threads (uniform `have`).
+__device__ __forceinline__ unsigned ts_wait_rows(const FusedParams& p, volatile unsigned* cache_s, int tile, unsigned have) {
   const long long last = (long long)(tile + 1) * kTileM;
   const unsigned need = (unsigned)(last < p.N ? last : p.N);
-  unsigned have;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(p.ready_rows) : "memory");
-  if (have >= need) return;
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  while (true) {
-    __nanosleep(64);
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(p.ready_rows) : "memory");
-    if (have >= need) return;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 2000000000ull) {
-      if (p.gate_status != nullptr) *p.gate_status = 1;
-      return;
+  if (have >= need) return have;
+  if (threadIdx.x == 0) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready_rows) : "memory");
+    if (v < need) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (true) {
+        __nanosleep(256);
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready_rows) : "memory");
+        if (v >= need) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) {
+          if (p.gate_status != nullptr) *p.gate_status = 1;
+          v = 0xffffffffu;  // give up waiting for good: the pass is reported as failed
+          break;
+        }
+      }
     }
+    *cache_s = v;
   }
+  bar_compute();  // the 512 conversion threads; also orders their loads of the rows behind thread 0's acquire
+  const unsigned v = *cache_s;
+  bar_compute();  // the word may be rewritten by the next call
+  return v;
 }
 
 // Sixteen kernel values (scaled by ts_kscale) from sixteen accumulator values D = t / g, two at a time in packed
@@ -513,10 +529,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
       cst.c3 = pack2(c3, c3);
     }
     TsStageRegs regs;
+    unsigned rows_have = 0;  // gated pass: rows known to be published (uniform over the conversion threads)
 
     auto prefetch = [&](int tile) {
       const int64_t row = (int64_t)tile * kTileM + row_e;
-      if (p.ready_rows != nullptr) ts_wait_rows(p, tile);
+      if (p.ready_rows != nullptr) rows_have = ts_wait_rows(p, s.ready_cache, tile, rows_have);
       regs.v[0] = (cg < dq) ? ts_load_quad(p, row, cg) : make_float4(0.f, 0.f, 0.f, 0.f);
       regs.v[1] = (cg + 4 < dq) ? ts_load_quad(p, row, cg + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
@@ -676,8 +693,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
     long long best = kEmptyKey;
     int trace_n = 0;
     const bool tr = (tid == kTsEpiWarp0 * 32);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    // |V|^2, mean partial and task id of this thread's row of tile `it`; releases the V accumulator.
+    // Inputs that the conversion warps overwrite two tiles later are read BEFORE the accumulator is released:
+    // V(t+1) waits for v_empty(t), DIST(t+2) follows V(t+1), and only then can those buffers be written again.
+    auto read_tile = [&](int it, float& vp, float& mp, int& ctr) {
       const int buf = it & 1, slot = it & (kTsTaskSlots - 1);
       const uint32_t par = (uint32_t)(it & 1);
       unsigned long long ssa = 0ull, ssb = 0ull;
@@ -698,18 +717,32 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
           }
         }
       }
-      // inputs that the conversion warps overwrite two tiles later are read BEFORE the accumulator is released:
-      // V(t+1) waits for v_empty(t), DIST(t+2) follows V(t+1), and only then can those buffers be written again
       mbar_wait_relaxed(&s.mean_full[buf], (uint32_t)((it >> 1) & 1));
-      const float mp = (s.mean_part[(buf * 4 + 0) * kTileM + r] + s.mean_part[(buf * 4 + 1) * kTileM + r]) +
-                       (s.mean_part[(buf * 4 + 2) * kTileM + r] + s.mean_part[(buf * 4 + 3) * kTileM + r]);
-      const int ctr = TASKS ? s.cand_task[slot * kTileM + r] : 0;
+      mp = (s.mean_part[(buf * 4 + 0) * kTileM + r] + s.mean_part[(buf * 4 + 1) * kTileM + r]) +
+           (s.mean_part[(buf * 4 + 2) * kTileM + r] + s.mean_part[(buf * 4 + 3) * kTileM + r]);
+      ctr = TASKS ? s.cand_task[slot * kTileM + r] : 0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s.v_empty);
       if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 140);
-
-      const float vp = (lo_of(ssa) + hi_of(ssa)) + (lo_of(ssb) + hi_of(ssb));
+      vp = (lo_of(ssa) + hi_of(ssa)) + (lo_of(ssb) + hi_of(ssb));
+    };
+    int it = 0;
+    bool have_next = false;  // the next tile's accumulator has already been read (while exact rows were pending)
+    float vp_n = 0.f, mp_n = 0.f;
+    int ctr_n = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      float vp, mp;
+      int ctr;
+      if (have_next) {
+        vp = vp_n;
+        mp = mp_n;
+        ctr = ctr_n;
+        have_next = false;
+      } else {
+        read_tile(it, vp, mp, ctr);
+      }
+      const bool more = tile + (int)gridDim.x < p.num_tiles;
       const float kss = (TASKS || p.scaled) ? s.tcov[ctr * p.n_tasks + ctr] : 1.0f;
       const float var_t = fmaxf(kss - vp * inv_v_scale2, 1e-10f);
       const float mu = fmaf(p.y_std, s.meanc[ctr] + mp, p.y_mean);
@@ -725,33 +758,34 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
         if (is_mc) {
           float c0, c1, s0 = 0.f, s1 = 0.f;
           mc_coef(p.acq, mu, var, c0, c1);
+          unsigned need = 0u;  // rows of this warp that take a whole-warp sum over all S samples
           if (fast_mc) {
             const bool fast = mc_row_fast(s.mc_tab, c0, c1, s0, s1);
-            if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 142);
-            // rows outside the tabulated envelope: exact sum over all S samples, the whole warp per row
-            unsigned need = __ballot_sync(0xffffffffu, !fast);
-            while (need != 0u) {
-              const int b = __ffs(need) - 1;
-              need &= need - 1u;
-              const float e0 = __shfl_sync(0xffffffffu, c0, b), e1 = __shfl_sync(0xffffffffu, c1, b);
-              float a0, a1;
-              mc_row_exact_warp(s.z_s, p.S, e0, e1, lane, a0, a1);
-              if (lane == b) {
-                s0 = a0;
-                s1 = a1;
+            need = __ballot_sync(0xffffffffu, !fast);  // outside the tabulated envelope
+          } else if (p.acq.kind != BB_ACQ_QUCB && p.acq.kind != BB_ACQ_QSR) {
+            need = 0xffffffffu;  // per-sample kinds without a table
+          }
+          if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 142);
+          while (need != 0u) {
+            // The slow rows must not hold up the tensor pipe: if the next tile's accumulator is complete, read it
+            // (and release it) first, then come back.
+            if (more && !have_next) {
+              const bool done = mbar_try_wait(&s.vsub_full[C - 1], (uint32_t)((it + 1) & 1));
+              if (__any_sync(0xffffffffu, done)) {
+                read_tile(it + 1, vp_n, mp_n, ctr_n);
+                have_next = true;
               }
             }
-          } else if (p.acq.kind != BB_ACQ_QUCB && p.acq.kind != BB_ACQ_QSR) {
-            // per-sample kinds without a table: the warp takes its 32 rows one after the other, lane l sums the
-            // sample groups l, l + 32, ... (fixed order: a row's value does not depend on where it is evaluated)
-            for (int b = 0; b < 32; ++b) {
-              const float e0 = __shfl_sync(0xffffffffu, c0, b), e1 = __shfl_sync(0xffffffffu, c1, b);
-              float a0, a1;
-              mc_row_groups_warp(p.acq.kind, s.z_s, p.S, e0, e1, lane, a0, a1);
-              if (lane == b) {
-                s0 = a0;
-                s1 = a1;
-              }
+            const int b = __ffs(need) - 1;
+            need &= need - 1u;
+            const float e0 = __shfl_sync(0xffffffffu, c0, b), e1 = __shfl_sync(0xffffffffu, c1, b);
+            float a0, a1;
+            // fixed summation order per row: a row's value does not depend on where it is evaluated
+            if (fast_mc) mc_row_exact_warp(s.z_s, p.S, e0, e1, lane, a0, a1);
+            else mc_row_groups_warp(p.acq.kind, s.z_s, p.S, e0, e1, lane, a0, a1);
+            if (lane == b) {
+              s0 = a0;
+              s1 = a1;
             }
           }
           if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 143);
