@@ -191,6 +191,68 @@ __device__ __forceinline__ void mc_table_setup(float* __restrict__ tab, const fl
   __syncthreads();
 }
 
+// The same table built by a GRID once per call (fused_ts.cu: rebuilding it in each of the 148 persistent CTAs took
+// ~23 us of every launch): every CTA repeats the cheap top-16 step, warp w of CTA b then fills entry 8 b + w with a
+// lane-parallel sum (fixed order: lane partials over e = lane, lane + 32, ..., xor-tree).  CTA 0 also stores the
+// top-16 block and the validity flag.  out: kMcRows floats in global memory.
+__device__ __forceinline__ void mc_table_grid_part(float* __restrict__ tab, const float* __restrict__ z_s, int S,
+                                                   float sgn, float* __restrict__ out) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    float vals[16];
+    const int per_lane = S >> 5;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) vals[j] = j < per_lane ? sgn * z_s[j * 32 + lane] : -INFINITY;
+    for (int k = 0; k < kMcK; ++k) {
+      float m = -INFINITY;
+      int mj = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (vals[j] > m) {
+          m = vals[j];
+          mj = j;
+        }
+      float wm = m;
+      for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+      const unsigned who = __ballot_sync(0xffffffffu, m == wm);
+      if (lane == (int)(__ffs(who) - 1)) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j == mj) vals[j] = -INFINITY;
+      }
+      if (lane == 0) tab[kMcTop + k] = wm;
+    }
+  }
+  __syncthreads();
+  const float thr = tab[kMcTop + kMcK - 1], w0 = tab[kMcTop + kMcJ];
+  if (blockIdx.x == 0) {
+    if (warp == 1) {
+      int cnt = 0;
+      for (int e = lane; e < S; e += 32) cnt += (sgn * z_s[e] >= thr) ? 1 : 0;
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane == 0) out[kMcOk] = (cnt == kMcK) ? 1.f : 0.f;
+    }
+    if (tid < kMcK) out[kMcTop + tid] = tab[kMcTop + tid];
+  }
+  const int j = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (j <= kMcNT) {
+    float f = (float)(S - kMcK);
+    if (j > 0) {
+      const float a = (float)kMcNT / (float)j;
+      const float w = w0 - 1.0f + a;
+      const float cut = thr - w;
+      float acc = 0.f;
+      for (int e = lane; e < S; e += 32) {
+        const float d0 = fmaf(sgn, z_s[e], -w);
+        acc += d0 < cut ? fast_rcp(d0 * d0) : 0.f;
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      f = acc * a * a;
+    }
+    if (lane == 0) out[j] = f;
+  }
+}
+
 // (s0, s1) of one row from the table; false (and s0 = s1 = 0) if the row lies outside the envelope.
 __device__ __forceinline__ bool mc_row_fast(const float* __restrict__ tab, float c0, float c1, float& s0,
                                             float& s1) {
@@ -217,6 +279,45 @@ __device__ __forceinline__ bool mc_row_fast(const float* __restrict__ tab, float
     }
     const float inv = 1.0f / ac1;
     const float a = fmaf(-t9, inv, 1.0f);  // w - zeta_(9) + 1 >= 1, no cancellation
+    const float v = 1.0f / a;
+    const float x = v * (float)kMcNT;
+    const int i = min((int)x, kMcNT - 1);
+    const float fr = x - (float)i;
+    const float f0 = tab[i], f1 = tab[i + 1];
+    const float q = v * inv;
+    s1 = fmaf(fmaf(fr, f1 - f0, f0), q * q, s1);
+  }
+  return fast;
+}
+
+// mc_row_fast with the sixteen tabulated zeta and the validity flag held in registers by the caller (one warp
+// that evaluates a row per thread for the whole kernel: fused_ts.cu); identical arithmetic.
+__device__ __forceinline__ bool mc_row_fast_z(const float* __restrict__ tab, const float (&zt)[kMcK], bool tab_ok,
+                                              float c0, float c1, float& s0, float& s1) {
+  const float ac1 = fabsf(c1);
+  const float t9 = fmaf(ac1, zt[kMcJ], c0);
+  const float t17 = fmaf(ac1, zt[kMcK - 1], c0);
+  const bool fast = tab_ok && ac1 > 1e-30f && t9 <= 0.f && t17 <= -1024.f;
+  s0 = 0.f;
+  s1 = 0.f;
+  if (fast) {
+    float tmin = 1e30f;
+#pragma unroll
+    for (int k = 0; k < kMcK; ++k) {
+      const float t = fmaf(ac1, zt[k], c0);
+      s0 += fmaxf(t, 0.f);
+      s1 += fast_rcp(fmaf(t, t, 1.0f));
+      tmin = fminf(tmin, fabsf(t));
+    }
+    if (tmin < 30.f) {
+#pragma unroll 1
+      for (int k = 0; k < kMcK; ++k) {
+        const float t = fabsf(fmaf(ac1, tab[kMcTop + k], c0));
+        if (t < 30.f) s0 += softplus_tail(t);
+      }
+    }
+    const float inv = 1.0f / ac1;
+    const float a = fmaf(-t9, inv, 1.0f);
     const float v = 1.0f / a;
     const float x = v * (float)kMcNT;
     const int i = min((int)x, kMcNT - 1);

@@ -550,6 +550,16 @@ __global__ void __launch_bounds__(kFusedThreads) k_mc_table(const float* __restr
   for (int e = threadIdx.x; e < kMcRows; e += blockDim.x) out[e] = tab[e];
 }
 
+// Grid version for the headline kernel: 65 CTAs x 8 warps, one table entry per warp (acq_math.cuh).
+__global__ void __launch_bounds__(256) k_mc_table_grid(const float* __restrict__ z, int S, float sgn,
+                                                       float* __restrict__ out) {
+  __shared__ float z_s[512];
+  __shared__ float tab[kMcRows];
+  for (int e = threadIdx.x; e < S; e += blockDim.x) z_s[e] = __ldg(z + e);
+  __syncthreads();
+  mc_table_grid_part(tab, z_s, S, sgn, out);
+}
+
 template <int FAMILY, int LAG, bool PRE = false, int GMAX = 1>
 static int launch_one(FusedParams& p, int grid, size_t smem, cudaStream_t stream) {
   BB_SMEM_OPTIN_ONCE((k_fused<FAMILY, LAG, PRE, GMAX>));
@@ -772,6 +782,12 @@ int launch_fused(const bb_model* m, const void* d_x, int32_t layout, int64_t N, 
   }();
   if (!ts_off && !m->wide && fused_ts_supported(p, max_smem)) {  // headline kernel (fused_ts.cu)
     const int grid_ts = p.num_tiles < sms ? p.num_tiles : sms;
+    if (m->d_mc_table != nullptr && mc_table_applicable(p.has_acq, p.acq, p.S) && grid_ts > 8) {
+      // qLogEI table once per call instead of once per persistent CTA (short launches keep the in-kernel build)
+      k_mc_table_grid<<<(kMcNT + 8) / 8, 256, 0, stream>>>(p.z, p.S, p.acq.obj_scale < 0.f ? -1.f : 1.f, m->d_mc_table);
+      BB_LAUNCH_CHECK();
+      p.mc_table = m->d_mc_table;
+    }
     return launch_fused_ts(p, grid_ts, stream);
   }
   BB_CHECK_SUPPORTED(gate == nullptr, "the overlapped host pass needs the headline kernel's shape envelope");

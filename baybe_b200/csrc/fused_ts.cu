@@ -17,8 +17,18 @@
 //     FMNMX, MUFU.SQRT, MUFU.EX2 and packed f32x2 arithmetic: 8 instructions per kernel value (19 before).
 //   * The hi image of L^-1 and the training rows are RESIDENT in shared memory; only the lo image (80 KB per tile at
 //     n_pad = 256) streams from L2 through a 3-stage bulk-copy ring.
-//   * The acquisition of a row is evaluated by four lanes of ONE warp (rows are redistributed after the
-//     |V|^2 / mean partials meet in shared memory), not redundantly by the four warps that share the row.
+//   * FOUR EPILOGUE WARPS (one per TMEM lane quarter, one candidate row per thread) read the V accumulator, form
+//     the moments and evaluate the acquisition function while the 16 conversion warps are already converting the
+//     next tile: with that work on the conversion warps a tile took 11.4 k cycles, 5.1 k of them |V|^2 +
+//     acquisition.  Whole-warp rows (qLogEI rows outside the table's envelope) never hold the tensor pipe up: the
+//     epilogue warp polls for the next tile's accumulator between such rows and serves it first.
+//   * The MMA issue loop is instantiated with a compile-time chunk count for n_pad = 256: the descriptor arithmetic
+//     in front of every MMA batch (~250 cycles on the one issuing thread, twelve batches per tile) becomes immediates.
+//   * The qLogEI table is built once per call (k_mc_table_grid) instead of once per persistent CTA (~23 us).
+//   * Gated end-to-end pass (bb_score_fused_overlapped): the kernel can be launched over rows that are still on
+//     their way from the host; one thread per CTA watches the copy stream's publication counter.
+// 704 threads: warps 0-15 conversion, 16-19 epilogue, 20 bulk-copy producer, 21 MMA issuer (80 registers each: the
+// allocation unit is 512 registers per warp, so 22 warps cap a thread at 80).
 //
 // Tensor memory: columns [0, n_pad) V accumulator; [256, 256 + n_pad) D2, overwritten in place by the A operand.
 // Reference path replaced: see fused.cu.
@@ -48,7 +58,7 @@ struct TsSmem {
   uint8_t *lh, *ring, *bt, *a2;
   float *alpha_s, *z_s, *mc_tab, *tcov, *meanc, *cscale_s, *cshift_s, *an_part, *mean_part, *var_part;
   int32_t *ttask, *cand_task;
-  uint64_t *a_full, *vsub_full, *r_full, *r_empty, *d2_full, *a2_full, *v_empty, *res_full, *mean_full;
+  uint64_t *a_full, *vsub_full, *r_full, *r_empty, *d2_full, *a2_full, *v_empty, *res_full, *mean_full, *vlast_full;
   long long* best_red;
   uint32_t* tmem_ptr;
   float* zstat;
@@ -110,6 +120,7 @@ __host__ __device__ inline size_t ts_carve(uint8_t* base, int n_pad, int n_tasks
     s->v_empty = b + 19;
     s->res_full = b + 20;
     s->mean_full = b + 21;  // [2]
+    s->vlast_full = b + 23; // [4]: 16-column groups of the LAST sub-block (final one K step after the other)
     s->best_red = reinterpret_cast<long long*>(base + o_best);
     s->tmem_ptr = reinterpret_cast<uint32_t*>(base + o_misc);
     s->zstat = reinterpret_cast<float*>(base + o_misc + 8);
@@ -360,6 +371,37 @@ __device__ __forceinline__ void ts_mma_role(const FusedParams& p, const TsSmem& 
     tc_fence_after();
     if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 210 + c);
     const uint32_t a_col = d2_addr + (uint32_t)(c * kChunk);
+    if (c == C - 1) {
+      // LAST chunk (64 rows, one streamed piece): the accumulator cannot be handed to the next tile before the
+      // epilogue has read this sub-block, and nothing but one distance slab is left to cover that read.  So its
+      // 16-column groups are finished and committed one K step after the other (hi x hi, lo x hi, hi x lo per step):
+      // the epilogue reads group kk while the pipe works on kk + 1, and only the last 16 columns are exposed.
+      mbar_wait_relaxed(&s.r_full[rs], rph);
+      tc_fence_after();
+      const uint64_t b_d = ring_d0 + (uint64_t)((rs * kTsLoStage) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t n_cols = (uint32_t)(rows_c - 16 * kk);
+          const uint64_t bd = lh_d0 + (uint64_t)((hi_off + (uint32_t)kk * 2048u) >> 4) + (uint64_t)(kk * 2);
+          const uint64_t bl = b_d + (uint64_t)(((uint32_t)(16 * kk) * 128u) >> 4) + (uint64_t)(kk * 2);
+          const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + 16 * kk);
+          const uint32_t id = make_idesc_f16(kTileM, (int)n_cols);
+          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, id, (c > 0 || kk > 0) ? 1u : 0u);
+          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk + 8), bd, id, 1u);
+          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bl, id, 1u);
+          umma_commit(&s.vlast_full[kk]);  // columns 64c + 16kk .. +15 have received their last contribution
+        }
+        umma_commit(&s.r_empty[rs]);
+      }
+      __syncwarp();
+      if (++rs == (uint32_t)kTsLoStages) {
+        rs = 0;
+        rph ^= 1u;
+      }
+      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 220 + c);
+      return;
+    }
     if (elect_one()) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {  // K step kk only reaches columns >= 64c + 16kk
@@ -467,6 +509,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
     mbar_init(s.res_full, 1);
     mbar_init(&s.mean_full[0], kComputeWarps);
     mbar_init(&s.mean_full[1], kComputeWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(&s.vlast_full[i], 1);
     fence_mbar_init();
   }
   if (warp == kTsWarpProducer) {
@@ -506,8 +549,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
     }
   }
   const bool fast_mc = mc_table_applicable(p.has_acq, p.acq, p.S);
-  if (fast_mc) mc_table_setup(s.mc_tab, s.z_s, p.S, p.acq.obj_scale < 0.f ? -1.f : 1.f);  // contains __syncthreads
-  else __syncthreads();                                                                  // zstat visible to everyone
+  if (fast_mc && p.mc_table != nullptr) {  // built once per call by k_mc_table_grid
+    for (int e = tid; e < kMcRows; e += kTsThreads) s.mc_tab[e] = __ldg(p.mc_table + e);
+    __syncthreads();
+  } else if (fast_mc) {
+    mc_table_setup(s.mc_tab, s.z_s, p.S, p.acq.obj_scale < 0.f ? -1.f : 1.f);  // contains __syncthreads
+  } else {
+    __syncthreads();  // zstat visible to everyone
+  }
 
   if (warp < kComputeWarps) {
     // =====================================================================================================
@@ -531,9 +580,28 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
     TsStageRegs regs;
     unsigned rows_have = 0;  // gated pass: rows known to be published (uniform over the conversion threads)
 
+    // the resident layout (fp32 rows, every quad a full aligned 16 bytes) takes one predicated 128-bit load per
+    // quad; the layout decision and the address checks of ts_load_quad ran ~130 instructions per thread and tile
+    const bool gated = p.ready_rows != nullptr;
+    const bool fast_rows = p.layout == BB_ROW_MAJOR_F32 && (p.ldx & 3) == 0 && (p.d & 3) == 0 &&
+                           (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
     auto prefetch = [&](int tile) {
       const int64_t row = (int64_t)tile * kTileM + row_e;
-      if (p.ready_rows != nullptr) rows_have = ts_wait_rows(p, s.ready_cache, tile, rows_have);
+      if (gated) rows_have = ts_wait_rows(p, s.ready_cache, tile, rows_have);
+      if (fast_rows) {
+        const float4* base = reinterpret_cast<const float4*>(p.x) + row * (p.ldx >> 2) + cg;
+        const bool q0 = row < p.N && 4 * cg < p.d, q1 = row < p.N && 4 * (cg + 4) < p.d;
+        regs.v[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        regs.v[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gated) {
+          if (q0) regs.v[0] = __ldcg(base);
+          if (q1) regs.v[1] = __ldcg(base + 4);
+        } else {
+          if (q0) regs.v[0] = __ldg(base);
+          if (q1) regs.v[1] = __ldg(base + 4);
+        }
+        return;
+      }
       regs.v[0] = (cg < dq) ? ts_load_quad(p, row, cg) : make_float4(0.f, 0.f, 0.f, 0.f);
       regs.v[1] = (cg + 4 < dq) ? ts_load_quad(p, row, cg + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
@@ -693,6 +761,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
     long long best = kEmptyKey;
     int trace_n = 0;
     const bool tr = (tid == kTsEpiWarp0 * 32);
+    float zt[kMcK];  // the sixteen largest zeta of the qLogEI table: registers, not 16 shared-memory reads per row
+#pragma unroll
+    for (int k = 0; k < kMcK; ++k) zt[k] = fast_mc ? s.mc_tab[kMcTop + k] : 0.f;
+    const bool tab_ok = fast_mc && s.mc_tab[kMcOk] != 0.f;
     // |V|^2, mean partial and task id of this thread's row of tile `it`; releases the V accumulator.
     // Inputs that the conversion warps overwrite two tiles later are read BEFORE the accumulator is released:
     // V(t+1) waits for v_empty(t), DIST(t+2) follows V(t+1), and only then can those buffers be written again.
@@ -700,7 +772,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
       const int buf = it & 1, slot = it & (kTsTaskSlots - 1);
       const uint32_t par = (uint32_t)(it & 1);
       unsigned long long ssa = 0ull, ssb = 0ull;
-      for (int sb = 0; sb < C; ++sb) {
+      for (int sb = 0; sb < C - 1; ++sb) {
         mbar_wait_relaxed(&s.vsub_full[sb], par);
         tc_fence_after();
         if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 130 + sb);
@@ -715,6 +787,22 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
             ssa = fma2(va, va, ssa);
             ssb = fma2(vb, vb, ssb);
           }
+        }
+      }
+      // last sub-block: 16 columns at a time, each group as soon as its K step has completed
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float v[16];
+        mbar_wait_relaxed(&s.vlast_full[kk], par);
+        tc_fence_after();
+        if (tr && kk == 0) ts_trace<TRACE>(p, 2, trace_n, it, 130 + C - 1);
+        tmem_ld16(tmem_base + lane_base + (uint32_t)((C - 1) * kChunk + 16 * kk), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const unsigned long long va = pack2(v[4 * e], v[4 * e + 1]), vb = pack2(v[4 * e + 2], v[4 * e + 3]);
+          ssa = fma2(va, va, ssa);
+          ssb = fma2(vb, vb, ssb);
         }
       }
       mbar_wait_relaxed(&s.mean_full[buf], (uint32_t)((it >> 1) & 1));
@@ -760,7 +848,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
           mc_coef(p.acq, mu, var, c0, c1);
           unsigned need = 0u;  // rows of this warp that take a whole-warp sum over all S samples
           if (fast_mc) {
-            const bool fast = mc_row_fast(s.mc_tab, c0, c1, s0, s1);
+            const bool fast = mc_row_fast_z(s.mc_tab, zt, tab_ok, c0, c1, s0, s1);
             need = __ballot_sync(0xffffffffu, !fast);  // outside the tabulated envelope
           } else if (p.acq.kind != BB_ACQ_QUCB && p.acq.kind != BB_ACQ_QSR) {
             need = 0xffffffffu;  // per-sample kinds without a table
@@ -770,7 +858,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
             // The slow rows must not hold up the tensor pipe: if the next tile's accumulator is complete, read it
             // (and release it) first, then come back.
             if (more && !have_next) {
-              const bool done = mbar_try_wait(&s.vsub_full[C - 1], (uint32_t)((it + 1) & 1));
+              const bool done = mbar_test_wait(&s.vlast_full[3], (uint32_t)((it + 1) & 1));
               if (__any_sync(0xffffffffu, done)) {
                 read_tile(it + 1, vp_n, mp_n, ctr_n);
                 have_next = true;

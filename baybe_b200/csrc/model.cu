@@ -111,6 +111,7 @@ static BlobLayout make_layout(int n, int d, int T) {
     L.timg_l = take(2 * tile_bytes);
     L.timg_b = take((size_t)3 * L.n_pad * 64);
     L.ts_alpha = take(sizeof(float) * L.n_pad);
+    if (!L.wide) L.mc_table = take(sizeof(float) * 1024);  // per-call qLogEI table (k_mc_table_grid)
   }
   L.total = off;
   return L;
@@ -667,7 +668,7 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
   std::vector<double> lo(d), inv_range(d), inv_ls(d), centre(d, 0.0), xn((size_t)n * d);
   for (int j = 0; j < d; ++j) {
     double r = desc->upper[j] - desc->lower[j];
-    if (fabs(r) < 1e-12) r = 1.0;  // botorch Normalize: degenerate range -> 1
+    if (fabs(r) < 1e-8) r = 1.0;  // botorch Normalize(min_range = 1e-8): degenerate range -> 1
     lo[j] = desc->lower[j];
     inv_range[j] = 1.0 / r;
     double ls = desc->lengthscale[j];
@@ -999,6 +1000,7 @@ extern "C" int bb_model_build(const bb_model_desc* desc, void* d_blob, size_t bl
     out->d_timg_l = B + L.timg_l;
     out->d_timg_b = B + L.timg_b;
     out->d_ts_alpha = (const float*)(B + L.ts_alpha);
+    if (!L.wide) out->d_mc_table = (float*)(B + L.mc_table);
     out->ts_sa = ts_sa;
     out->ts_aug_sq = ts_aug_sq;
     out->ts_aug_one = ts_aug_one;

@@ -265,7 +265,7 @@ class GaussianProcessSurrogate:
         active = [j for j in range(d) if j != task_col]
         hp = dict(self.hyperparameters) if self.hyperparameters is not None else None
         if hp is None:
-            rng = np.where(np.abs(bounds[1] - bounds[0]) < 1e-12, 1.0, bounds[1] - bounds[0])
+            rng = np.where(np.abs(bounds[1] - bounds[0]) < 1e-8, 1.0, bounds[1] - bounds[0])
             Xn = (train_x - bounds[0]) / rng
             ys = train_y.std(ddof=1) if len(train_y) > 1 else 1.0
             ys = ys if ys >= 1e-8 else 1.0

@@ -261,7 +261,9 @@ def build_model(
     num_idx = [i for i in range(d) if i != spec.task_idx]
     lo = bounds[0].clone()
     rng = (bounds[1] - bounds[0]).clone()
-    rng = torch.where(rng.abs() < 1e-12, torch.ones_like(rng), rng)
+    # botorch Normalize(min_range=1e-8): a column whose range is (almost) zero is left unscaled  [U: botorch 0.16.1
+    # input.py, Normalize.__init__ / _update_coefficients -- threshold restated from memory]
+    rng = torch.where(rng.abs() < 1e-8, torch.ones_like(rng), rng)
     if spec.task_idx is not None:
         lo[spec.task_idx] = 0.0
         rng[spec.task_idx] = 1.0
