@@ -130,17 +130,27 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    import os
+
+    # diagnostic only (scripts/ab_kernel.py): time another build of the SAME library on the same box
+    variant = os.environ.get("BB_LIB_VARIANT")
+    path = LIB_PATH if not variant else LIB_PATH.parent / "variants" / f"{variant}.so"
+    if not path.exists():
         raise NativeLibraryError(
-            f"{LIB_PATH} not found: build it with `python -m baybe_b200.build` "
+            f"{path} not found: build it with `python -m baybe_b200.build` "
             "(baybe_b200 has no CPU fallback)"
         )
     try:
-        lib = C.CDLL(str(LIB_PATH))
+        lib = C.CDLL(str(path))
     except OSError as e:  # pragma: no cover - depends on the environment
-        raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+        raise NativeLibraryError(f"cannot load {path}: {e}") from e
     for name, (res, args) in _SIGNATURES.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            if variant:  # an older build may lack newer entry points
+                continue
+            raise
         fn.restype = res
         fn.argtypes = args
     if lib.bb_abi_version() != ABI_VERSION:

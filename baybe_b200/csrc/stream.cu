@@ -101,6 +101,9 @@ extern "C" int bb_score_fused_host(const bb_model* m, const bb_acq_spec* a, cons
 // envelope return BB_ERR_UNSUPPORTED before anything is enqueued (callers then use bb_score_fused_host).
 // ------------------------------------------------------------------------------------------------------------
 typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+// growing copy blocks: 32 k rows first (the kernel idles until they land), then x4 up to 2 M rows per block -- four
+// blocks for 1M rows.  Every block costs a copy + a publication, each with its own DMA start-up latency.
+constexpr int64_t kGateFirstBlock = 32768, kGateMaxBlock = 2097152;
 
 extern "C" int bb_score_fused_overlapped(const bb_model* m, const bb_acq_spec* a, const void* h_x, int32_t host_format,
                                          int64_t N, int64_t ld, const float* d_table, int32_t table_ld, void* d_stage,
@@ -146,24 +149,26 @@ extern "C" int bb_score_fused_overlapped(const bb_model* m, const bb_acq_spec* a
     write32 = reinterpret_cast<WriteValue32Fn>(fn);
   }
   // How the copy stream publishes "rows landed":
-  //   1  cuStreamWriteValue32 (stream-ordered memory operation with a system-wide memory barrier in front): default
   //   0  a 4-byte H2D copy from a constant pinned table of cumulative block ends (plain DMA, ordered behind the
-  //      block's copy on the same stream)
-  // Both measured within 5 % of each other (profiles/r02_time_e2e.txt); BB_GATE_PUBLISH=0 selects the DMA form.
+  //      block's copy on the same stream): default
+  //   1  cuStreamWriteValue32 (stream-ordered memory operation with a system-wide memory barrier in front)
+  // On an idle GPU both cost the same (profiles/r02_time_e2e.txt: 0.44 / 0.41 ms per pass); issued while earlier
+  // work is still draining on the compute stream, as in bench.py's timed loop, the write-value form doubled the pass
+  // (0.80 ms against 0.40 ms).  BB_GATE_PUBLISH=1 selects it for diagnosis.
   static const int publish_mode = [] {
     const char* e = getenv("BB_GATE_PUBLISH");
-    return (e != nullptr && e[0] == '0') ? 0 : 1;
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
   }();
   constexpr int kMaxBlocks = 64;
   static uint32_t* h_ends = nullptr;  // pinned, written once: cumulative ends of the growing-block schedule
   if (h_ends == nullptr) {
     uint32_t* t = nullptr;
     BB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&t), kMaxBlocks * sizeof(uint32_t), cudaHostAllocDefault));
-    uint64_t end = 0, rows_k = 16384;
+    uint64_t end = 0, rows_k = kGateFirstBlock;
     for (int k = 0; k < kMaxBlocks; ++k) {
       end += rows_k;
       t[k] = end > 0xffffffffull ? 0xffffffffu : (uint32_t)end;  // a value >= N publishes everything
-      if (rows_k < 262144) rows_k *= 2;
+      if (rows_k < kGateMaxBlock) rows_k *= 4;
     }
     h_ends = t;
   }
@@ -176,22 +181,28 @@ extern "C" int bb_score_fused_overlapped(const bb_model* m, const bb_acq_spec* a
   if (rc != BB_OK || N == 0) return rc;
   BB_CHECK_ARG(h_x != nullptr, "bb_score_fused_overlapped: host matrix is null");
   // counter and status back to zero on the compute stream, ahead of the kernel and (through the event) of the copies
-  BB_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
-  if (write32((CUstream)stream, (CUdeviceptr)(uintptr_t)d_ready, 0u, 0u) != CUDA_SUCCESS) {
-    set_error("cuStreamWriteValue32 failed on the compute stream");
-    return BB_ERR_CUDA;
+  // (every driver call counts here: the pass is ~0.3 ms of GPU work, a call ~5 us of host time)
+  if (reinterpret_cast<uint8_t*>(d_status) == reinterpret_cast<uint8_t*>(d_ready) + 4) {
+    BB_CUDA(cudaMemsetAsync(d_ready, 0, 8, stream));  // adjacent words: one operation
+  } else {
+    BB_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
+    BB_CUDA(cudaMemsetAsync(d_ready, 0, sizeof(uint32_t), stream));
   }
-  cudaEvent_t ev;
-  BB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  static thread_local cudaEvent_t ev = nullptr;  // one event per host thread, re-recorded every pass
+  static thread_local int ev_dev = -1;
+  int dev_now = 0;
+  BB_CUDA(cudaGetDevice(&dev_now));
+  if (ev == nullptr || ev_dev != dev_now) {
+    BB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ev_dev = dev_now;
+  }
   BB_CUDA(cudaEventRecord(ev, stream));  // earlier readers of the staging buffer are done; the counter is reset
   BB_CUDA(cudaStreamWaitEvent(copy, ev, 0));
-  cudaEventDestroy(ev);
   rc = launch_fused(m, d_stage, BB_ROW_MAJOR_F32, N, ld, a, d_z, S, d_keep, nullptr, nullptr, d_score, d_best_key,
                     index_offset, stream, nullptr, &gate);
   if (rc != BB_OK) return rc;  // no kernel was launched: nothing waits for rows
-  // growing blocks: the first one small (the kernel idles until it lands), later ones large (few API calls);
   // block k ends at h_ends[k] (or N)
-  int64_t lo = 0, rows = 16384;
+  int64_t lo = 0, rows = kGateFirstBlock;
   for (int k = 0; lo < N; ++k) {
     const int64_t n = (N - lo) < rows ? (N - lo) : rows;
     const cudaError_t e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d_stage) + (size_t)lo * row_bytes,
@@ -205,7 +216,7 @@ extern "C" int bb_score_fused_overlapped(const bb_model* m, const bb_acq_spec* a
       set_error("bb_score_fused_overlapped: host->device copy / publication failed: %s", cudaGetErrorString(e));
       return BB_ERR_CUDA;
     }
-    if (rows < 262144) rows *= 2;
+    if (rows < kGateMaxBlock) rows *= 4;
   }
   return BB_OK;
 }

@@ -55,10 +55,11 @@ def _workload(n_rows: int, shard: int = 0):
     return base, other.candidates
 
 
-def _ncu_traffic_bytes(names=("r02_k_fused_ts_ncu_full_summary.txt", "r01_k_fused_tc_ncu_full_summary.txt")):
+def _ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the committed ncu
-    --set full capture (profiles/, one launch at this exact workload)."""
-    for name in names:
+    --set full capture (profiles/, one launch at this exact workload): the newest k_fused_ts summary."""
+    names = sorted(p.name for p in (ROOT / "profiles").glob("r0*_k_fused_ts*_ncu_full_summary.txt"))[::-1]
+    for name in names + ["r01_k_fused_tc_ncu_full_summary.txt"]:
         f = ROOT / "profiles" / name
         if not f.exists():
             continue
@@ -369,7 +370,7 @@ def run_b200(args):
                              "2048-row chunks, torch float64",
                    "single_pass_value": r["single_pass_value"],
                    "single_pass_note": "50,000-row sample scored in one unchunked pass (best of 2), same thread count"}
-        launches = (2 + (1 if world > 1 else 0)) * steps  # key init + fused kernel (+ one-warp peer reduction)
+        launches = (3 + (1 if world > 1 else 0)) * steps  # key init + qLogEI table + fused kernel (+ one-warp peer reduction)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -37,6 +37,8 @@ for st in $STAGES; do
       tail -8 $OUT/r02_sanitizer_memcheck.txt
       timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python scripts/ts_first_light.py n64_d4 cfg1 > $OUT/r02_sanitizer_racecheck.txt 2>&1; echo "racecheck rc=$?"
       tail -8 $OUT/r02_sanitizer_racecheck.txt ;;
+    ab)   # same-box A/B of library builds (scripts/build_variant.sh), two rounds to see drift
+      for r in 1 2; do for v in $(ls baybe_b200/_C/variants/ | sed 's/.so$//') ""; do BB_LIB_VARIANT=$v timeout 120 python scripts/ab_kernel.py 2>&1 | grep -E "variant|Error" | tee -a $OUT/ab_kernel.txt; done; done ;;
     e2e)
       for m in 1 0; do BB_GATE_PUBLISH=$m timeout 200 python scripts/time_e2e.py 1 > $OUT/time_e2e_m$m.txt 2>&1; echo "e2e mode $m rc=$?"; grep -v Warn $OUT/time_e2e_m$m.txt | tail -7; done
       timeout 200 python scripts/time_e2e.py 0 > $OUT/time_e2e_blocks.txt 2>&1; echo "e2e blocks rc=$?"; tail -7 $OUT/time_e2e_blocks.txt ;;
