@@ -20,6 +20,7 @@ ACQ_KIND = {
     "UCB": 5, "EI": 6, "LogEI": 7, "PI": 8, "PM": 9, "PSTD": 10,
 }
 MC_KINDS = ("qLogEI", "qEI", "qUCB", "qSR", "qPI")
+NEI_KINDS = ("qNEI",)  # evaluated by baybe_b200/hybrid.py (conditional form + bb_nei_reduce), not by the fused kernels
 MAX_PENDING = 31
 MAX_TRAIN = 1024
 
@@ -116,6 +117,7 @@ _SIGNATURES = {
                                       C.POINTER(_vp), C.POINTER(_vp), _i64, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     "bb_score_fused_overlapped": (C.c_int, [C.POINTER(Model), C.POINTER(AcqSpec), _vp, _i32, _i64, _i64, _vp, _i32, _vp,
                                             _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
+    "bb_nei_reduce": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _i64, _vp, _vp]),
     "bb_decode_codes": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _vp, _i32, _vp, _i64, _vp]),
     "bb_peer_slots_init": (C.c_int, [_vp, _vp, _vp]),
     "bb_allreduce_best": (C.c_int, [C.POINTER(PeerGroup), _vp, C.c_uint32, _vp, _vp, _vp]),

@@ -19,6 +19,7 @@ __all__ = [
     "qLogExpectedImprovement", "ProbabilityOfImprovement", "qProbabilityOfImprovement",
     "UpperConfidenceBound", "qUpperConfidenceBound", "convert_acqf",
     "PM", "PSTD", "qSR", "EI", "qEI", "LogEI", "qLogEI", "PI", "qPI", "UCB", "qUCB",
+    "qNoisyExpectedImprovement", "qNEI",
 ]
 
 
@@ -176,11 +177,21 @@ class qUpperConfidenceBound(AcquisitionFunction):
         return {"beta": self.beta}
 
 
+@define(frozen=True)
+class qNoisyExpectedImprovement(AcquisitionFunction):
+    """acquisition/acqfs.py:227-232.  Evaluated by ``baybe_b200.hybrid`` (hybrid search spaces); ``prune_baseline``
+    is accepted for compatibility: the engine keeps every baseline point (its cost is one GEMM column each)."""
+
+    abbreviation: ClassVar[str] = "qNEI"
+    prune_baseline: bool = field(default=True, validator=instance_of(bool))
+
+
+qNEI = qNoisyExpectedImprovement
 PM, PSTD, qSR = PosteriorMean, PosteriorStandardDeviation, qSimpleRegret
 EI, qEI, LogEI, qLogEI = ExpectedImprovement, qExpectedImprovement, LogExpectedImprovement, qLogExpectedImprovement
 PI, qPI, UCB, qUCB = ProbabilityOfImprovement, qProbabilityOfImprovement, UpperConfidenceBound, qUpperConfidenceBound
 
-_BY_NAME = {c.__name__: c for c in (PM, PSTD, qSR, EI, qEI, LogEI, qLogEI, PI, qPI, UCB, qUCB)}
+_BY_NAME = {c.__name__: c for c in (PM, PSTD, qSR, EI, qEI, LogEI, qLogEI, PI, qPI, UCB, qUCB, qNEI)}
 _BY_NAME.update({c.abbreviation: c for c in list(_BY_NAME.values())})
 
 

@@ -100,7 +100,7 @@ class EngineAcquisitionFunction:
 class B200BotorchRecommender(BayesianRecommender):
     """``BotorchRecommender`` for discrete search spaces with the scoring path on the B200 engine."""
 
-    compatibility: ClassVar[SearchSpaceType] = SearchSpaceType.DISCRETE
+    compatibility: ClassVar[SearchSpaceType] = SearchSpaceType.HYBRID
     supports_discrete_subset_generating_constraints: ClassVar[bool] = True
 
     _surrogate_model = field(alias="surrogate_model", factory=GaussianProcessSurrogate)
@@ -145,6 +145,32 @@ class B200BotorchRecommender(BayesianRecommender):
         if subspace_discrete.n_subsets > 0:
             return self._recommend_discrete_with_subsets(subspace_discrete, candidates_exp, batch_size)
         return self._recommend_discrete_without_subsets(subspace_discrete, candidates_exp, batch_size)
+
+    # ---- hybrid spaces (botorch/core.py:221-250 -> hybrid.py:30-161): search by scoring on the device -----------
+    def _recommend_hybrid(self, searchspace, candidates_exp: pd.DataFrame, batch_size: int) -> pd.DataFrame:
+        from baybe_b200.hybrid import recommend_hybrid
+
+        assert self._objective is not None and self._context is not None
+        cfg, _, pending = self._context
+        if cfg.kind != "qNEI":
+            raise IncompatibleAcquisitionFunctionError(
+                "hybrid search spaces are served with qNoisyExpectedImprovement on the B200 engine "
+                f"(got '{cfg.kind}')")
+        if searchspace.continuous.has_interpoint_constraints or searchspace.continuous.constraints_lin_eq or \
+                searchspace.continuous.constraints_lin_ineq:
+            raise IncompatibilityError("continuous constraints are not supported by the B200 hybrid search")
+        disc = searchspace.discrete.transform(candidates_exp)  # comp-rep of the discrete part, comes first
+        cb = searchspace.continuous.comp_rep_bounds.to_numpy(dtype=np.float64)
+        pend = None
+        if pending is not None and len(pending) > 0:
+            pend = searchspace.transform(pending, allow_extra=True).to_numpy(dtype=np.float64)
+        pts, idx, value = recommend_hybrid(self._surrogate_model.device_gp, cfg, disc.to_numpy(dtype=np.float64), cb,
+                                           batch_size, pend, self.n_mc_samples, _draw_sampler_seed())
+        self._last_acq_values[:] = [value]
+        rec_disc = searchspace.discrete.exp_rep.loc[disc.index[idx]]
+        rec_cont = pd.DataFrame(pts[:, disc.shape[1]:], columns=searchspace.continuous.parameter_names,
+                                index=rec_disc.index)
+        return pd.concat([rec_disc, rec_cont], axis=1)
 
     def _recommend_discrete_without_subsets(self, subspace_discrete, candidates_exp, batch_size) -> pd.Index:
         cfg, searchspace, pending = self._context

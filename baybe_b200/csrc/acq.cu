@@ -441,3 +441,58 @@ extern "C" int bb_topk(const float* d_score, const uint8_t* d_keep, int64_t N, i
   }
   return BB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// qNEI / qLogNEI-style noisy improvement of ONE new point per row, conditional on joint samples of a conditioning
+// set C = [baseline; pending] (acquisition/acqfs.py:227-240, X_baseline from _builder.py:319-324).
+// With the joint Cholesky taken in the order [C ; x], the sample path of the new point is
+//   f_x,s = mu_x + r_x . Z_C[s,:] + sqrt(max(var_x - |r_x|^2, 0)) z_x,s ,      r_x = Sigma_xC L_C^-T ,
+// and the value of x is  mean_s relu( o(f_x,s) - g_s ),  g_s = max(o over the samples of C)  (the marginal gain of
+// adding x to the pending set; the part that does not depend on x is added by the caller).
+// d_out row i = [ Delta_i[0..S) = r_i . Z_C^T | r_i[0..m) ]  (one GEMM of the caller: Sigma_XC @ [W | L_C^-T]).
+// One warp per row: |r|^2 by a shuffle reduction, then the S samples in lane-strided order (fixed order).
+// ------------------------------------------------------------------------------------------------------------
+namespace bb {
+__global__ void __launch_bounds__(256) k_nei_reduce(const float* __restrict__ out, int64_t ld, int S, int m,
+                                                    const float* __restrict__ mu, const float* __restrict__ var,
+                                                    const float* __restrict__ zx, const float* __restrict__ g,
+                                                    float obj_scale, float obj_shift, int64_t N,
+                                                    float* __restrict__ score) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp0; i < N; i += nwarps) {
+    const float* row = out + i * ld;
+    float r2 = 0.f;
+    for (int j = lane; j < m; j += 32) {
+      const float r = row[S + j];
+      r2 = fmaf(r, r, r2);
+    }
+    for (int o = 16; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    const float sc = sqrtf(fmaxf(var[i] - r2, 0.f));
+    const float m0 = mu[i];
+    float acc = 0.f;
+    for (int s = lane; s < S; s += 32) {
+      const float f = m0 + row[s] + sc * zx[s];
+      acc += fmaxf(fmaf(obj_scale, f, obj_shift) - g[s], 0.f);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) score[i] = acc / (float)S;
+  }
+}
+}  // namespace bb
+
+extern "C" int bb_nei_reduce(const float* d_out, int64_t ld, int32_t S, int32_t m, const float* d_mu,
+                             const float* d_var, const float* d_zx, const float* d_g, float obj_scale,
+                             float obj_shift, int64_t N, float* d_score, void* stream) {
+  BB_CHECK_ARG(N >= 0 && S >= 1 && m >= 0 && ld >= (int64_t)S + m, "bb_nei_reduce: bad shape (N=%lld S=%d m=%d ld=%lld)",
+               (long long)N, S, m, (long long)ld);
+  if (N == 0) return BB_OK;
+  BB_CHECK_ARG(d_out && d_mu && d_var && d_zx && d_g && d_score, "bb_nei_reduce: null buffer");
+  const int64_t want = (N * 32 + 255) / 256;
+  const int grid = (int)(want < (int64_t)kSMs * 16 ? want : (int64_t)kSMs * 16);
+  bb::k_nei_reduce<<<grid, 256, 0, (cudaStream_t)stream>>>(d_out, ld, S, m, d_mu, d_var, d_zx, d_g, obj_scale, obj_shift,
+                                                         N, d_score);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}

@@ -198,6 +198,9 @@ __device__ __forceinline__ void mc_table_setup(float* __restrict__ tab, const fl
 __device__ __forceinline__ void mc_table_grid_part(float* __restrict__ tab, const float* __restrict__ z_s, int S,
                                                    float sgn, float* __restrict__ out) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the scoring kernel that follows on the stream may start its prologue now; it synchronises on this grid's
+  // completion (griddepcontrol.wait) before it reads `out`
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 0) {
     float vals[16];
     const int per_lane = S >> 5;
@@ -290,58 +293,6 @@ __device__ __forceinline__ bool mc_row_fast(const float* __restrict__ tab, float
   return fast;
 }
 
-// 1 / x for x >= 1 on the FMA pipe: integer first guess (|error| < 13 %), three Newton steps (-> 5e-8 relative).
-// The epilogue warps of fused_ts.cu share their schedulers' MIO / XU queues with conversion warps that keep them full
-// of MUFU and tensor-memory traffic; a MUFU.RCP issued there waits its turn behind ~a hundred cycles of those.
-__device__ __forceinline__ float rcp_fma_ge1(float x) {
-  float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
-  float e = fmaf(-x, r, 1.0f);
-  r = fmaf(r, e, r);
-  e = fmaf(-x, r, 1.0f);
-  r = fmaf(r, e, r);
-  e = fmaf(-x, r, 1.0f);
-  return fmaf(r, e, r);
-}
-
-// mc_row_fast with the sixteen tabulated zeta and the validity flag held in registers by the caller (one warp
-// that evaluates a row per thread for the whole kernel: fused_ts.cu); identical arithmetic.
-__device__ __forceinline__ bool mc_row_fast_z(const float* __restrict__ tab, const float (&zt)[kMcK], bool tab_ok,
-                                              float c0, float c1, float& s0, float& s1) {
-  const float ac1 = fabsf(c1);
-  const float t9 = fmaf(ac1, zt[kMcJ], c0);
-  const float t17 = fmaf(ac1, zt[kMcK - 1], c0);
-  const bool fast = tab_ok && ac1 > 1e-30f && t9 <= 0.f && t17 <= -1024.f;
-  s0 = 0.f;
-  s1 = 0.f;
-  if (fast) {
-    float tmin = 1e30f;
-#pragma unroll
-    for (int k = 0; k < kMcK; ++k) {
-      const float t = fmaf(ac1, zt[k], c0);
-      s0 += fmaxf(t, 0.f);
-      s1 += rcp_fma_ge1(fmaf(t, t, 1.0f));
-      tmin = fminf(tmin, fabsf(t));
-    }
-    if (tmin < 30.f) {
-#pragma unroll 1
-      for (int k = 0; k < kMcK; ++k) {
-        const float t = fabsf(fmaf(ac1, tab[kMcTop + k], c0));
-        if (t < 30.f) s0 += softplus_tail(t);
-      }
-    }
-    const float inv = 1.0f / ac1;
-    const float a = fmaf(-t9, inv, 1.0f);
-    const float v = 1.0f / a;
-    const float x = v * (float)kMcNT;
-    const int i = min((int)x, kMcNT - 1);
-    const float fr = x - (float)i;
-    const float f0 = tab[i], f1 = tab[i + 1];
-    const float q = v * inv;
-    s1 = fmaf(fmaf(fr, f1 - f0, f0), q * q, s1);
-  }
-  return fast;
-}
-
 // mc_row_fast split over the four lanes that share a row in fused_ts.cu: lane `sub` (0..3) evaluates the exact
 // terms k = sub, sub+4, sub+8, sub+12 of the sixteen, lane 0 adds the tabulated tail; the caller sums (s0, s1) over
 // the four lanes (fixed order: the value of a row does not depend on where it is evaluated).  The envelope test
@@ -412,31 +363,6 @@ __device__ __forceinline__ void mc_row_groups_warp(int kind, const float* __rest
   const float4* z4 = reinterpret_cast<const float4*>(z_s);
   const int G = S >> 2;
   for (int g = lane; g < G; g += 32) mc_accumulate(kind, c0, c1, z4 + g, 1, a0, a1);
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-  }
-}
-
-// mc_row_exact_warp with the reciprocals on the FMA pipe (fused_ts.cu's epilogue warps, see rcp_fma_ge1).
-__device__ __forceinline__ void mc_row_exact_warp_fma(const float* __restrict__ z_s, int S, float c0, float c1, int lane,
-                                                      float& a0, float& a1) {
-  float b0 = 0.f, b1 = 0.f;
-  a0 = 0.f;
-  a1 = 0.f;
-  for (int e = lane; e < S; e += 64) {  // S is a multiple of 64 on this path; two independent chains
-    const float t = fmaf(c1, z_s[e], c0), u = fmaf(c1, z_s[e + 32], c0);
-    a0 += fmaxf(t, 0.f);
-    b0 += fmaxf(u, 0.f);
-    a1 += rcp_fma_ge1(fmaf(t, t, 1.0f));
-    b1 += rcp_fma_ge1(fmaf(u, u, 1.0f));
-    if (fminf(fabsf(t), fabsf(u)) < 30.f) {
-      if (fabsf(t) < 30.f) a0 += softplus_tail(fabsf(t));
-      if (fabsf(u) < 30.f) b0 += softplus_tail(fabsf(u));
-    }
-  }
-  a0 += b0;
-  a1 += b1;
   for (int o = 16; o > 0; o >>= 1) {
     a0 += __shfl_xor_sync(0xffffffffu, a0, o);
     a1 += __shfl_xor_sync(0xffffffffu, a1, o);

@@ -20,14 +20,19 @@
 //   * FOUR EPILOGUE WARPS (one per TMEM lane quarter, one candidate row per thread) read the V accumulator, form
 //     the moments and evaluate the acquisition function while the 16 conversion warps are already converting the
 //     next tile: with that work on the conversion warps a tile took 11.4 k cycles, 5.1 k of them |V|^2 +
-//     acquisition.  Whole-warp rows (qLogEI rows outside the table's envelope) never hold the tensor pipe up: the
-//     epilogue warp polls for the next tile's accumulator between such rows and serves it first.
+//     acquisition.
 //   * The MMA issue loop is instantiated with a compile-time chunk count for n_pad = 256: the descriptor arithmetic
 //     in front of every MMA batch (~250 cycles on the one issuing thread, twelve batches per tile) becomes immediates.
-//   * The qLogEI table is built once per call (k_mc_table_grid) instead of once per persistent CTA (~23 us).
+//   * The qLogEI table is built once per call (k_mc_table_grid, overlapped with this kernel's prologue by programmatic
+//     dependent launch) instead of once per persistent CTA (~23 us of every launch).
 //   * Gated end-to-end pass (bb_score_fused_overlapped): the kernel can be launched over rows that are still on
 //     their way from the host; one thread per CTA watches the copy stream's publication counter.
-// 704 threads: warp 0 MMA issuer, 1 bulk-copy producer, 2-5 epilogue, 6-21 conversion (80 registers each: the
+// Tried on top of this and REJECTED by same-box A/B timing (profiles/r02_ab_kernel_variants.txt): serving the next
+// tile's accumulator between whole-warp rows (+7 %), an incremental accumulator reader with FMA-pipe reciprocals
+// (+5 %), per-K-step commits of the last sub-block, lowest warp ids for the single-warp roles (no effect), a
+// two-stage accumulator release with a column-split first chunk (+5 %): each shortens one wait in the event trace and
+// lengthens the tensor pipe's own time (more, smaller MMAs; more tensor-memory traffic) by more.
+// 704 threads: warps 0-15 conversion, 16-19 epilogue, 20 bulk-copy producer, 21 MMA issuer (80 registers each: the
 // allocation unit is 512 registers per warp, so 22 warps cap a thread at 80).
 //
 // Tensor memory: columns [0, n_pad) V accumulator; [256, 256 + n_pad) D2, overwritten in place by the A operand.
@@ -49,20 +54,16 @@ constexpr uint32_t kTsD2Col0 = 256;
 constexpr uint32_t kTsA2Split = 128u * kTsK2 * 2u;  // one fp16 panel of the candidate tile: 8 KB
 // Warp roles of k_fused_ts: 16 conversion warps (stage candidate rows, D2 -> K* operand), 4 epilogue warps (one per
 // TMEM lane quarter: |V|^2, moments, acquisition, arg-max), the bulk-copy producer and the MMA issuer.
-// The latency-critical single warps get the LOWEST warp ids: with the roles in the order conversion, epilogue,
-// producer, MMA the epilogue warps ran at ~15-30 cycles per instruction whenever the conversion warps of their
-// scheduler were busy (profiles/r02_pipeline_trace_fused_ts_v6.txt) -- the warp schedulers favour older (lower-id) warps.
-constexpr int kTsWarpMma = 0, kTsWarpProducer = 1, kTsEpiWarp0 = 2, kTsEpiWarps = 4;
-constexpr int kTsConvWarp0 = kTsEpiWarp0 + kTsEpiWarps;         // 6: sixteen conversion warps
-constexpr int kTsThreads = (kTsConvWarp0 + kComputeWarps) * 32;  // 704
+constexpr int kTsEpiWarp0 = kComputeWarps, kTsEpiWarps = 4;
+constexpr int kTsWarpProducer = kTsEpiWarp0 + kTsEpiWarps, kTsWarpMma = kTsWarpProducer + 1;
+constexpr int kTsThreads = (kTsWarpMma + 1) * 32;  // 704
 constexpr int kTsTaskSlots = 4;                    // candidate task ids of the tiles in flight
 
 struct TsSmem {
   uint8_t *lh, *ring, *bt, *a2;
   float *alpha_s, *z_s, *mc_tab, *tcov, *meanc, *cscale_s, *cshift_s, *an_part, *mean_part, *var_part;
   int32_t *ttask, *cand_task;
-  uint64_t *a_full, *vsub_full, *r_full, *r_empty, *d2_full, *a2_full, *v_empty, *res_full, *mean_full, *vlast_full,
-      *v_part;
+  uint64_t *a_full, *vsub_full, *r_full, *r_empty, *d2_full, *a2_full, *v_empty, *res_full, *mean_full;
   long long* best_red;
   uint32_t* tmem_ptr;
   float* zstat;
@@ -124,8 +125,6 @@ __host__ __device__ inline size_t ts_carve(uint8_t* base, int n_pad, int n_tasks
     s->v_empty = b + 19;
     s->res_full = b + 20;
     s->mean_full = b + 21;  // [2]
-    s->vlast_full = b + 23; // [4]: 16-column groups of the LAST sub-block (final one K step after the other)
-    s->v_part = b + 27;     // all sub-blocks but the last have been read: columns [0, n_pad - 64) may be overwritten
     s->best_red = reinterpret_cast<long long*>(base + o_best);
     s->tmem_ptr = reinterpret_cast<uint32_t*>(base + o_misc);
     s->zstat = reinterpret_cast<float*>(base + o_misc + 8);
@@ -271,7 +270,7 @@ __device__ __forceinline__ unsigned ts_wait_rows(const FusedParams& p, volatile 
   const long long last = (long long)(tile + 1) * kTileM;
   const unsigned need = (unsigned)(last < p.N ? last : p.N);
   if (have >= need) return have;
-  if (threadIdx.x == kTsConvWarp0 * 32) {
+  if (threadIdx.x == 0) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready_rows) : "memory");
     if (v < need) {
@@ -369,8 +368,6 @@ __device__ __forceinline__ void ts_mma_role(const FusedParams& p, const TsSmem& 
   };
   mbar_wait_relaxed(s.res_full, 0u);
   uint32_t rs = 0, rph = 0;
-  bool have_prev = false;  // a previous tile's accumulator has to be released before this tile's first chunk
-  uint32_t prev_par = 0;
   // V MMAs of K chunk c: resident hi image (K*hi x Lhi, K*lo x Lhi), then the streamed lo pieces (K*hi x Llo)
   auto issue_v_chunk = [&](int c, uint32_t par, uint32_t hi_off) {
     const int rows_c = n_pad - c * kChunk;
@@ -378,120 +375,6 @@ __device__ __forceinline__ void ts_mma_role(const FusedParams& p, const TsSmem& 
     tc_fence_after();
     if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 210 + c);
     const uint32_t a_col = d2_addr + (uint32_t)(c * kChunk);
-    if (c == 0 && C >= 2) {
-      // FIRST chunk of a tile, in two column ranges.  Its MMAs (accumulate = 0) overwrite the whole accumulator, but
-      // the previous tile's LAST sub-block is still being read when the pipe gets here (those columns are final only
-      // after that tile's very last MMA, and tensor-memory reads take ~300+ cycles each under load: ~1300 cycles with
-      // nothing but one distance slab to cover them).  So columns [0, n_pad - 64) -- released by the epilogue as soon
-      // as the earlier sub-blocks are read -- are started first, and only the 64-column remainder waits for the
-      // final release.  Twelve more (small) MMAs per tile against ~1000 idle pipe cycles.
-      const uint32_t wpar = prev_par;  // parity of the PREVIOUS tile's releases
-      const int na = n_pad - kChunk;   // columns of part a
-      if (have_prev) mbar_wait_relaxed(s.v_part, wpar);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t bd = lh_d0 + (uint64_t)(((uint32_t)kk * 2048u) >> 4) + (uint64_t)(kk * 2);
-          const uint32_t d_addr = tmem_base + (uint32_t)(16 * kk);
-          const uint32_t id = make_idesc_f16(kTileM, na - 16 * kk);
-          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, id, kk > 0 ? 1u : 0u);
-          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk + 8), bd, id, 1u);
-        }
-      }
-      __syncwarp();
-      // streamed lo pieces of part a: rows [r0, min(r0 + 128, na)); the piece that also holds the last 64 rows stays
-      // in its ring stage until part b has used it
-      uint32_t rs_b = 0, rph_b = 0;
-      for (int r0 = 0; r0 < rows_c; r0 += 128) {
-        const int rows_p = rows_c - r0 < 128 ? rows_c - r0 : 128;
-        const bool holds_b = (r0 + rows_p == rows_c);
-        const int rows_a = holds_b ? rows_p - kChunk : rows_p;
-        mbar_wait_relaxed(&s.r_full[rs], rph);
-        tc_fence_after();
-        const uint64_t b_d = ring_d0 + (uint64_t)((rs * kTsLoStage) >> 4);
-        if (elect_one()) {
-          if (rows_a > 0) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const int skip = (r0 == 0) ? 16 * kk : 0;
-              if (rows_a - skip > 0) {
-                const uint64_t bd = b_d + (uint64_t)(((uint32_t)skip * 128u) >> 4) + (uint64_t)(kk * 2);
-                umma_f16_ts(tmem_base + (uint32_t)(r0 + skip), a_col + (uint32_t)(16 * kk), bd,
-                            make_idesc_f16(kTileM, rows_a - skip), 1u);
-              }
-            }
-          }
-          if (!holds_b) umma_commit(&s.r_empty[rs]);
-        }
-        __syncwarp();
-        if (holds_b) {
-          rs_b = rs;
-          rph_b = rph;
-        }
-        if (++rs == (uint32_t)kTsLoStages) {
-          rs = 0;
-          rph ^= 1u;
-        }
-      }
-      (void)rph_b;
-      // part b: the last 64 columns
-      if (have_prev) mbar_wait_relaxed(s.v_empty, wpar);
-      tc_fence_after();
-      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 200);
-      {
-        const uint64_t b_d = ring_d0 + (uint64_t)((rs_b * kTsLoStage) >> 4);
-        const int r_in_piece = (rows_c - kChunk) & 127;  // first row of part b inside its piece
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t bd = lh_d0 + (uint64_t)(((uint32_t)na * 128u) >> 4) + (uint64_t)(kk * 2);
-            const uint64_t bl = b_d + (uint64_t)(((uint32_t)r_in_piece * 128u) >> 4) + (uint64_t)(kk * 2);
-            const uint32_t d_addr = tmem_base + (uint32_t)na;
-            const uint32_t id = make_idesc_f16(kTileM, kChunk);
-            umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, id, kk > 0 ? 1u : 0u);
-            umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk + 8), bd, id, 1u);
-            umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bl, id, 1u);
-          }
-          umma_commit(&s.r_empty[rs_b]);
-          umma_commit(&s.vsub_full[0]);  // sub-block 0 of V has received its last contribution
-        }
-        __syncwarp();
-      }
-      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 220 + c);
-      return;
-    }
-    if (c == C - 1) {
-      // LAST chunk (64 rows, one streamed piece): the accumulator cannot be handed to the next tile before the
-      // epilogue has read this sub-block, and nothing but one distance slab is left to cover that read.  So its
-      // 16-column groups are finished and committed one K step after the other (hi x hi, lo x hi, hi x lo per step):
-      // the epilogue reads group kk while the pipe works on kk + 1, and only the last 16 columns are exposed.
-      mbar_wait_relaxed(&s.r_full[rs], rph);
-      tc_fence_after();
-      const uint64_t b_d = ring_d0 + (uint64_t)((rs * kTsLoStage) >> 4);
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint32_t n_cols = (uint32_t)(rows_c - 16 * kk);
-          const uint64_t bd = lh_d0 + (uint64_t)((hi_off + (uint32_t)kk * 2048u) >> 4) + (uint64_t)(kk * 2);
-          const uint64_t bl = b_d + (uint64_t)(((uint32_t)(16 * kk) * 128u) >> 4) + (uint64_t)(kk * 2);
-          const uint32_t d_addr = tmem_base + (uint32_t)(c * kChunk + 16 * kk);
-          const uint32_t id = make_idesc_f16(kTileM, (int)n_cols);
-          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bd, id, (c > 0 || kk > 0) ? 1u : 0u);
-          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk + 8), bd, id, 1u);
-          umma_f16_ts(d_addr, a_col + (uint32_t)(16 * kk), bl, id, 1u);
-          umma_commit(&s.vlast_full[kk]);  // columns 64c + 16kk .. +15 have received their last contribution
-        }
-        umma_commit(&s.r_empty[rs]);
-      }
-      __syncwarp();
-      if (++rs == (uint32_t)kTsLoStages) {
-        rs = 0;
-        rph ^= 1u;
-      }
-      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, mma_it, 220 + c);
-      return;
-    }
     if (elect_one()) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {  // K step kk only reaches columns >= 64c + 16kk
@@ -543,13 +426,9 @@ __device__ __forceinline__ void ts_mma_role(const FusedParams& p, const TsSmem& 
     const uint32_t par = (uint32_t)(j & 1);
     const bool has_next = tile + (int)gridDim.x < p.num_tiles;
     mma_it = j;
-    have_prev = j > 0;
-    prev_par = par ^ 1u;
-    if (C < 2) {  // a single sub-block: nothing to split, wait for the full release here
-      if (j > 0) mbar_wait_relaxed(s.v_empty, par ^ 1u);  // the previous tile's |V|^2 has been read
-      tc_fence_after();
-      if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, j, 200);
-    }
+    if (j > 0) mbar_wait_relaxed(s.v_empty, par ^ 1u);  // the previous tile's |V|^2 has been read
+    tc_fence_after();
+    if (lane == 0) ts_trace<TRACE>(p, 1, mma_n, j, 200);
     uint32_t hi_off = 0;
 #pragma unroll
     for (int c = 0; c < (CC > 0 ? (CC < 2 ? CC : 2) : 2); ++c) {
@@ -603,8 +482,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
     mbar_init(s.res_full, 1);
     mbar_init(&s.mean_full[0], kComputeWarps);
     mbar_init(&s.mean_full[1], kComputeWarps);
-    for (int i = 0; i < 4; ++i) mbar_init(&s.vlast_full[i], 1);
-    mbar_init(s.v_part, kTsEpiWarps);
     fence_mbar_init();
   }
   if (warp == kTsWarpProducer) {
@@ -645,7 +522,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
   }
   const bool fast_mc = mc_table_applicable(p.has_acq, p.acq, p.S);
   if (fast_mc && p.mc_table != nullptr) {  // built once per call by k_mc_table_grid
-    for (int e = tid; e < kMcRows; e += kTsThreads) s.mc_tab[e] = __ldg(p.mc_table + e);
+    // programmatic dependent launch: everything above ran while the table kernel was still in flight
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int e = tid; e < kMcRows; e += kTsThreads) s.mc_tab[e] = __ldcg(p.mc_table + e);
     __syncthreads();
   } else if (fast_mc) {
     mc_table_setup(s.mc_tab, s.z_s, p.S, p.acq.obj_scale < 0.f ? -1.f : 1.f);  // contains __syncthreads
@@ -653,15 +532,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
     __syncthreads();  // zstat visible to everyone
   }
 
-  if (warp >= kTsConvWarp0) {
+  if (warp < kComputeWarps) {
     // =====================================================================================================
     // conversion warps.  Thread = TMEM lane (candidate row_e of the tile) x column group cg (16 of the 64
     // columns of a chunk): candidate rows -> A2 operand panels, D2 -> kernel values -> K* operand in TMEM,
     // mean partials sum_i k_i alpha_i -> shared memory for the epilogue warps.
     // =====================================================================================================
-    // a warp reaches TMEM lanes 32 (warp % 4) .. +31: the row follows the hardware quarter, the column group the rest
-    const int quarter = warp & 3, cg = (warp - kTsConvWarp0) >> 2, row_e = quarter * 32 + lane;
-    const bool t0 = (tid == kTsConvWarp0 * 32);  // event-trace writer of this role
+    const int row_e = tid & 127, cg = tid >> 7, quarter = warp & 3;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int dq = p.d_pad >> 2;
     TsConsts cst;
@@ -675,8 +552,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
       cst.c3 = pack2(c3, c3);
     }
     TsStageRegs regs;
-    unsigned rows_have = 0;  // gated pass: rows known to be published (uniform over the conversion threads)
 
+    unsigned rows_have = 0;  // gated pass: rows known to be published (uniform over the conversion threads)
     // the resident layout (fp32 rows, every quad a full aligned 16 bytes) takes one predicated 128-bit load per
     // quad; the layout decision and the address checks of ts_load_quad ran ~130 instructions per thread and tile
     const bool gated = p.ready_rows != nullptr;
@@ -702,6 +579,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
       regs.v[0] = (cg < dq) ? ts_load_quad(p, row, cg) : make_float4(0.f, 0.f, 0.f, 0.f);
       regs.v[1] = (cg + 4 < dq) ? ts_load_quad(p, row, cg + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+
     int trace_it = 0, trace_n = 0;  // test-only event trace: tile counter the next events are filed under
     // scaled candidate rows -> fp16 hi/mid/lo A2 panels; the thread that owns quad 7 appends |a|^2 P and P1
     auto stage_a2 = [&](int slot) {
@@ -739,7 +617,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
         }
       }
       s.an_part[cg * kTileM + row_e] = an;
-      if (t0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 121);
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 121);
       if (cg != 3) {
         bar_quarter_arrive(2 + quarter);
       } else {
@@ -755,7 +633,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
         *reinterpret_cast<uint2*>(s.a2 + kTsA2Split + off) = mid;
         *reinterpret_cast<uint2*>(s.a2 + 2 * kTsA2Split + off) = lo;
       }
-      if (t0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 122);
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 122);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(s.a2_full);
@@ -768,7 +646,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
       const uint32_t col = kTsD2Col0 + (uint32_t)(c * kChunk + cg * 16);
       tmem_ld16(tmem_base + lane_base + col, v);
       tmem_ld_wait();
-      if (t0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 100 + c);
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 100 + c);
       const int i0 = c * kChunk + cg * 16;
       const float* tcrow = s.tcov + (TASKS ? s.cand_task[slot * kTileM + row_e] : 0) * p.n_tasks;
       uint32_t hi[8], lo[8];
@@ -789,7 +667,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.a_full[c]);
-      if (t0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 110 + c);
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, trace_it, 110 + c);
     };
     // Schedule (software-pipelined over tiles; D2 lives in two 128-column slabs = chunks {0,1} and {2,3}):
     //   iteration t:  [slab 1 of tile t ready]   stage A2(t+1), convert chunks 2,3 of tile t, publish the mean partials
@@ -818,12 +696,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
         mbar_wait(&s.d2_full[1], par);
         tc_fence_after();
       }
-      if (t0) ts_trace<TRACE>(p, 0, trace_n, it, 161);
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 161);
       if (next < p.num_tiles) {
         stage_a2(slot_next);
         if (next + (int)gridDim.x < p.num_tiles) prefetch(next + gridDim.x);
       }
-      if (t0) ts_trace<TRACE>(p, 0, trace_n, it, 120);
+      if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 120);
       for (int c = 2; c < C; ++c) convert_chunk(c, slot, mean_cur);
       // mean partials of tile `it`: buffer it & 1 was last read by the epilogue of tile it - 2, which finished
       // reading before it released the V accumulator -- and this tile's D2 could not exist before that
@@ -835,16 +713,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
       if (next < p.num_tiles) {
         mbar_wait(&s.d2_full[0], par ^ 1u);
         tc_fence_after();
-        if (t0) ts_trace<TRACE>(p, 0, trace_n, it, 160);
+        if (tid == 0) ts_trace<TRACE>(p, 0, trace_n, it, 160);
         trace_it = it + 1;
         for (int c = 0; c < C0; ++c) convert_chunk(c, slot_next, mean_cur);
         trace_it = it;
       }
     }
-    if (TRACE && t0 && p.trace != nullptr && blockIdx.x == 0) p.trace[0] = p.trace_cap;
-  } else if (warp >= kTsEpiWarp0) {
+    if (TRACE && tid == 0 && p.trace != nullptr && blockIdx.x == 0) p.trace[0] = p.trace_cap;
+  } else if (warp < kTsWarpProducer) {
     // =====================================================================================================
-    // epilogue warps (2..5): a warp owns TMEM lanes 32 (warp % 4) .. +31, one candidate row per thread.
+    // epilogue warps: warp 16 + q owns TMEM lanes 32q..32q+31, one candidate row per thread.
     //   |V|^2 over the row's n_pad accumulator columns (sub-block sb is final once chunk sb's MMAs completed),
     //   moments, acquisition value, running packed-key arg-max.  Everything after the accumulator has been read
     //   runs under the NEXT tile's MMAs and conversions.
@@ -858,97 +736,40 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
     long long best = kEmptyKey;
     int trace_n = 0;
     const bool tr = (tid == kTsEpiWarp0 * 32);
-    float zt[kMcK];  // the sixteen largest zeta of the qLogEI table: registers, not 16 shared-memory reads per row
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1, slot = it & (kTsTaskSlots - 1);
+      const uint32_t par = (uint32_t)(it & 1);
+      unsigned long long ssa = 0ull, ssb = 0ull;
+      for (int sb = 0; sb < C; ++sb) {
+        mbar_wait_relaxed(&s.vsub_full[sb], par);
+        tc_fence_after();
+        if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 130 + sb);
 #pragma unroll
-    for (int k = 0; k < kMcK; ++k) zt[k] = fast_mc ? s.mc_tab[kMcTop + k] : 0.f;
-    const bool tab_ok = fast_mc && s.mc_tab[kMcOk] != 0.f;
-    // ---- incremental reader of the V accumulator -------------------------------------------------------------
-    // |V|^2 of this thread's row is accumulated in steps: steps 0 .. C-2 are the full 64-column sub-blocks (final
-    // once their chunk's MMAs completed), steps C-1 .. C+2 the four 16-column groups of the last sub-block.  The
-    // reader belongs to ONE tile at a time (rd_it); between the phases of the previous tile's acquisition the warp
-    // takes whatever steps have become ready (non-blocking), so that when the last MMA of a tile completes only a
-    // 16-column read separates the tensor pipe from its next accumulation.  The order of the additions is fixed, so
-    // a row's value does not depend on how the steps were interleaved.
-    // Inputs that the conversion warps overwrite two tiles later (mean partials, task ids) are read BEFORE the
-    // accumulator is released: V(t+1) waits for v_empty(t), DIST(t+2) follows V(t+1), and only then can those
-    // buffers be written again.
-    int rd_it = 0, rd_step = 0;
-    bool rd_done = false;
-    unsigned long long ssa = 0ull, ssb = 0ull;
-    float vp_r = 0.f, mp_r = 0.f;
-    int ctr_r = 0;
-    auto pump = [&](bool block) {
-      const uint32_t par = (uint32_t)(rd_it & 1);
-      while (!rd_done) {
-        if (rd_step < C - 1) {
-          uint64_t* bar = &s.vsub_full[rd_step];
-          if (block) mbar_wait_relaxed(bar, par);
-          else if (!__any_sync(0xffffffffu, mbar_test_wait(bar, par))) return;
-          tc_fence_after();
-          if (tr) ts_trace<TRACE>(p, 2, trace_n, rd_it, 130 + rd_step);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float v[32];
-            tmem_ld32(tmem_base + lane_base + (uint32_t)(rd_step * kChunk + h * 32), v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const unsigned long long va = pack2(v[4 * e], v[4 * e + 1]), vb = pack2(v[4 * e + 2], v[4 * e + 3]);
-              ssa = fma2(va, va, ssa);
-              ssb = fma2(vb, vb, ssb);
-            }
-          }
-          ++rd_step;
-          if (rd_step == C - 1) {  // every sub-block but the last is read: the next tile may overwrite those columns
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s.v_part);
-          }
-        } else if (rd_step < C + 3) {
-          const int kk = rd_step - (C - 1);
-          uint64_t* bar = &s.vlast_full[kk];
-          if (block) mbar_wait_relaxed(bar, par);
-          else if (!__any_sync(0xffffffffu, mbar_test_wait(bar, par))) return;
-          tc_fence_after();
-          if (tr && kk == 0) ts_trace<TRACE>(p, 2, trace_n, rd_it, 130 + C - 1);
-          float v[16];
-          tmem_ld16(tmem_base + lane_base + (uint32_t)((C - 1) * kChunk + 16 * kk), v);
+        for (int h = 0; h < 2; ++h) {
+          float v[32];
+          tmem_ld32(tmem_base + lane_base + (uint32_t)(sb * kChunk + h * 32), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < 8; ++e) {
             const unsigned long long va = pack2(v[4 * e], v[4 * e + 1]), vb = pack2(v[4 * e + 2], v[4 * e + 3]);
             ssa = fma2(va, va, ssa);
             ssb = fma2(vb, vb, ssb);
           }
-          ++rd_step;
-        } else {
-          const int buf = rd_it & 1, slot = rd_it & (kTsTaskSlots - 1);
-          mbar_wait_relaxed(&s.mean_full[buf], (uint32_t)((rd_it >> 1) & 1));  // published long before the last MMA
-          mp_r = (s.mean_part[(buf * 4 + 0) * kTileM + r] + s.mean_part[(buf * 4 + 1) * kTileM + r]) +
-                 (s.mean_part[(buf * 4 + 2) * kTileM + r] + s.mean_part[(buf * 4 + 3) * kTileM + r]);
-          ctr_r = TASKS ? s.cand_task[slot * kTileM + r] : 0;
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s.v_empty);
-          if (tr) ts_trace<TRACE>(p, 2, trace_n, rd_it, 140);
-          vp_r = (lo_of(ssa) + hi_of(ssa)) + (lo_of(ssb) + hi_of(ssb));
-          rd_done = true;
         }
       }
-    };
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      pump(true);  // the rest of tile `it`
-      const float vp = vp_r, mp = mp_r;
-      const int ctr = ctr_r;
-      const bool more = tile + (int)gridDim.x < p.num_tiles;
-      if (more) {  // the reader moves on to the next tile; its steps are taken at the check points below
-        rd_it = it + 1;
-        rd_step = 0;
-        rd_done = false;
-        ssa = 0ull;
-        ssb = 0ull;
-      }
+      // inputs that the conversion warps overwrite two tiles later are read BEFORE the accumulator is released:
+      // V(t+1) waits for v_empty(t), DIST(t+2) follows V(t+1), and only then can those buffers be written again
+      mbar_wait_relaxed(&s.mean_full[buf], (uint32_t)((it >> 1) & 1));
+      const float mp = (s.mean_part[(buf * 4 + 0) * kTileM + r] + s.mean_part[(buf * 4 + 1) * kTileM + r]) +
+                       (s.mean_part[(buf * 4 + 2) * kTileM + r] + s.mean_part[(buf * 4 + 3) * kTileM + r]);
+      const int ctr = TASKS ? s.cand_task[slot * kTileM + r] : 0;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s.v_empty);
+      if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 140);
+
+      const float vp = (lo_of(ssa) + hi_of(ssa)) + (lo_of(ssb) + hi_of(ssb));
       const float kss = (TASKS || p.scaled) ? s.tcov[ctr * p.n_tasks + ctr] : 1.0f;
       const float var_t = fmaxf(kss - vp * inv_v_scale2, 1e-10f);
       const float mu = fmaf(p.y_std, s.meanc[ctr] + mp, p.y_mean);
@@ -964,34 +785,39 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_fused_ts(const FusedParams p)
         if (is_mc) {
           float c0, c1, s0 = 0.f, s1 = 0.f;
           mc_coef(p.acq, mu, var, c0, c1);
-          unsigned need = 0u;  // rows of this warp that take a whole-warp sum over all S samples
           if (fast_mc) {
-            const bool fast = mc_row_fast_z(s.mc_tab, zt, tab_ok, c0, c1, s0, s1);
-            need = __ballot_sync(0xffffffffu, !fast);  // outside the tabulated envelope
-          } else if (p.acq.kind != BB_ACQ_QUCB && p.acq.kind != BB_ACQ_QSR) {
-            need = 0xffffffffu;  // per-sample kinds without a table
-          }
-          if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 142);
-          if (more) pump(false);
-          while (need != 0u) {
-            const int b = __ffs(need) - 1;
-            need &= need - 1u;
-            const float e0 = __shfl_sync(0xffffffffu, c0, b), e1 = __shfl_sync(0xffffffffu, c1, b);
-            float a0, a1;
-            // fixed summation order per row: a row's value does not depend on where it is evaluated
-            if (fast_mc) mc_row_exact_warp_fma(s.z_s, p.S, e0, e1, lane, a0, a1);
-            else mc_row_groups_warp(p.acq.kind, s.z_s, p.S, e0, e1, lane, a0, a1);
-            if (lane == b) {
-              s0 = a0;
-              s1 = a1;
+            const bool fast = mc_row_fast(s.mc_tab, c0, c1, s0, s1);
+            if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 142);
+            // rows outside the tabulated envelope: exact sum over all S samples, the whole warp per row
+            unsigned need = __ballot_sync(0xffffffffu, !fast);
+            while (need != 0u) {
+              const int b = __ffs(need) - 1;
+              need &= need - 1u;
+              const float e0 = __shfl_sync(0xffffffffu, c0, b), e1 = __shfl_sync(0xffffffffu, c1, b);
+              float a0, a1;
+              mc_row_exact_warp(s.z_s, p.S, e0, e1, lane, a0, a1);
+              if (lane == b) {
+                s0 = a0;
+                s1 = a1;
+              }
             }
-            if (more) pump(false);  // the slow rows must not hold up the tensor pipe
+          } else if (p.acq.kind != BB_ACQ_QUCB && p.acq.kind != BB_ACQ_QSR) {
+            // per-sample kinds without a table: the warp takes its 32 rows one after the other, lane l sums the
+            // sample groups l, l + 32, ... (fixed order: a row's value does not depend on where it is evaluated)
+            for (int b = 0; b < 32; ++b) {
+              const float e0 = __shfl_sync(0xffffffffu, c0, b), e1 = __shfl_sync(0xffffffffu, c1, b);
+              float a0, a1;
+              mc_row_groups_warp(p.acq.kind, s.z_s, p.S, e0, e1, lane, a0, a1);
+              if (lane == b) {
+                s0 = a0;
+                s1 = a1;
+              }
+            }
           }
           if (tr) ts_trace<TRACE>(p, 2, trace_n, it, 143);
           score = (p.acq.kind == BB_ACQ_QLOGEI) ? log_tau + logf((s0 + 0.1f * s1) / (float)p.S)
                                                  : mc_finalize(p.acq, mu, var, s0, s1, p.S, s.zstat[0], s.zstat[1]);
         } else {
-          if (more) pump(false);
           score = analytic_value(p.acq, mu, var);
         }
         if (live) {
@@ -1477,6 +1303,24 @@ static int launch_ts_one2(FusedParams& p, int grid, size_t smem, cudaStream_t st
   if (configured_for != dev) {
     BB_CUDA(cudaFuncSetAttribute(k_fused_ts<FAMILY, TASKS, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured_for = dev;
+  }
+  if (p.mc_table != nullptr) {
+    // the table kernel launched just before on this stream releases its dependents at once
+    // (griddepcontrol.launch_dependents): this kernel's prologue overlaps it and waits (griddepcontrol.wait) only
+    // before it reads the table
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)kTsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BB_CUDA(cudaLaunchKernelEx(&cfg, k_fused_ts<FAMILY, TASKS, TRACE>, p));
+    return BB_OK;
   }
   k_fused_ts<FAMILY, TASKS, TRACE><<<grid, kTsThreads, smem, stream>>>(p);
   BB_LAUNCH_CHECK();

@@ -11,6 +11,7 @@ Replaces the L1 layer of SURVEY.md section 1: ``model.posterior`` / ``acqf.forwa
 from __future__ import annotations
 
 import ctypes as C
+import os
 import itertools
 import math
 import threading
@@ -76,14 +77,16 @@ class AcqConfig:
     tau_pi: float = 1e-3
 
     def __post_init__(self):
-        if self.kind not in _lib.ACQ_KIND:
+        if self.kind not in _lib.ACQ_KIND and self.kind not in _lib.NEI_KINDS:
             raise ValueError(f"unsupported acquisition function {self.kind!r}")
 
     @property
     def is_mc(self) -> bool:
-        return self.kind in _lib.MC_KINDS
+        return self.kind in _lib.MC_KINDS or self.kind in _lib.NEI_KINDS
 
     def to_c(self) -> _lib.AcqSpec:
+        if self.kind in _lib.NEI_KINDS:
+            raise NotImplementedError(f"{self.kind} is evaluated by baybe_b200.hybrid.NeiScorer, not by the fused kernels")
         return _lib.AcqSpec(
             _lib.ACQ_KIND[self.kind], int(self.maximize), self.best_f, self.beta, self.obj_scale,
             self.obj_shift, self.tau_relu, self.tau_max, self.tau_pi,
@@ -183,6 +186,7 @@ class DeviceGP:
         tcv = None if task_covar is None else np.ascontiguousarray(np.asarray(task_covar, dtype=np.float64))
         self.n, self.d, self.n_tasks = n, d, T
         self.family, self.task_col = family, task_col
+        self.outputscale = None if outputscale is None else float(outputscale)
         self._keepalive = (tx, ty, bnd, ls, nz, mc, tcv)
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
         lo_arr, hi_arr = np.ascontiguousarray(bnd[0]), np.ascontiguousarray(bnd[1])
@@ -260,7 +264,10 @@ class DeviceGP:
 
     STREAM_MIN_ROWS = 262_144
     STREAM_BLOCKS = 8
-    OVERLAPPED_HOST_PASS = True  # single-launch gated pass where the headline kernel covers the shape
+    # single-launch gated pass where the headline kernel covers the shape.  BB_OVERLAPPED_HOST_PASS=0 selects the
+    # block-wise pass: needed under ncu, whose kernel serialisation keeps the copy stream from making progress while
+    # the gated kernel waits for it (every such launch then runs into its 2 s time-out)
+    OVERLAPPED_HOST_PASS = os.environ.get("BB_OVERLAPPED_HOST_PASS", "1") != "0"
 
     def _host_pass(self, acq: AcqConfig, h: torch.Tensor, fmt: str, ld: int, row_bytes: int, table, zf, keep,
                    index_offset: int, want_scores: bool):

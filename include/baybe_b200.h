@@ -337,6 +337,17 @@ int bb_score_fused_overlapped(const bb_model* m, const bb_acq_spec* a, const voi
                               float* d_score, int64_t* d_best_key, int64_t index_offset, void* stream,
                               void* copy_stream);
 
+/* ---- noisy expected improvement of one new point per row, conditional on joint samples of C = [baseline; pending]
+ * (qNoisyExpectedImprovement, baybe/acquisition/acqfs.py:227-232; X_baseline = training inputs,
+ * acquisition/_builder.py:319-324; used by the hybrid recommender, recommenders/pure/bayesian/botorch/hybrid.py:30-161).
+ * d_out [N, ld >= S + m]: row i = [ r_i . Z_C^T (S values) | r_i (m values) ] with r_i = Sigma_iC L_C^-T, produced by
+ * the caller's GEMM; d_mu / d_var: marginal posterior of the rows (original units); d_zx [S]: the new point's own
+ * base samples; d_g [S]: per-sample incumbent max(o over the samples of C).  score_i = mean_s relu(o(mu_i +
+ * out_i[s] + sqrt(max(var_i - |r_i|^2, 0)) zx_s) - g_s), o(y) = obj_scale * y + obj_shift. */
+int bb_nei_reduce(const float* d_out, int64_t ld, int32_t S, int32_t m, const float* d_mu, const float* d_var,
+                  const float* d_zx, const float* d_g, float obj_scale, float obj_shift, int64_t N, float* d_score,
+                  void* stream);
+
 /* ---- test-only diagnostic: plain fp32 SIMT posterior (no tensor cores), used by the GPU
  * tests to separate tcgen05-path errors from formula errors.  Not called by the product. -- */
 int bb_debug_posterior_simt(const bb_model* m, const void* d_x, int32_t layout, int64_t N,

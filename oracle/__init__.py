@@ -22,6 +22,7 @@ from oracle.reference_path import (  # noqa: F401
     KernelSpec,
     acq_values,
     acq_values_joint,
+    acq_values_qnei,
     best_f_from_training,
     build_model,
     kernel_matrix,

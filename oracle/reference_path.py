@@ -552,6 +552,50 @@ def acq_values_joint(
     return out
 
 
+def acq_values_qnei(
+    model: GPModel, acq: AcqSpec, X: np.ndarray | torch.Tensor, X_pending: np.ndarray | torch.Tensor | None,
+    z: torch.Tensor, X_baseline: np.ndarray | torch.Tensor | None = None,
+) -> torch.Tensor:
+    """qNoisyExpectedImprovement of [x*; X_pending] for every row x* of X (baybe/acquisition/acqfs.py:227-232;
+    ``X_baseline`` = the training inputs, acquisition/_builder.py:319-324; no baseline pruning):
+        mean_s relu( max_{x*, pending} o(f_s) - max_{baseline} o(f_s) )
+    over joint posterior samples f = mean + chol(cov) z  [U: botorch qNoisyExpectedImprovement._sample_forward].
+    The joint Cholesky is taken in the order [baseline; pending; x*] -- z: (S, nb + p + 1), last column = the new
+    point.  botorch orders the q-batch first, i.e. it pairs the same base samples with other rows: the two agree in
+    distribution, single values differ by Monte-Carlo error; THIS order is the one the device path reproduces."""
+    X = torch.as_tensor(np.asarray(X), dtype=DTYPE)
+    d = X.shape[1]
+    Xb = (model.Xn * model.rng + model.lo) if X_baseline is None else torch.as_tensor(np.asarray(X_baseline), dtype=DTYPE)
+    P = torch.empty(0, d, dtype=DTYPE) if X_pending is None else torch.as_tensor(np.asarray(X_pending), dtype=DTYPE).reshape(-1, d)
+    C = torch.cat([Xb, P], dim=0)
+    nb, p = Xb.shape[0], P.shape[0]
+    m = nb + p
+    z = z.to(DTYPE)
+    assert z.shape[1] == m + 1
+    Cn = _normalise(C, model.lo, model.rng)
+    _, mC, VC = _standardised_posterior(model, Cn)
+    covCC = kernel_matrix(model.spec, Cn, Cn) - VC @ VC.T
+    covCC.diagonal().copy_(_kernel_diag(model.spec, Cn) - (VC * VC).sum(-1))
+    covCC = covCC * model.y_std**2
+    LC = _chol_with_jitter(covCC.unsqueeze(0))[0]
+    muC = model.y_mean + model.y_std * mC
+    FC = muC.unsqueeze(0) + z[:, :m] @ LC.T  # (S, m)
+    oC = acq.obj_scale * FC + acq.obj_shift
+    best = oC[:, :nb].amax(-1)
+    pend_max = oC[:, nb:].amax(-1) if p > 0 else torch.full_like(best, -float("inf"))
+    Xn = _normalise(X, model.lo, model.rng)
+    _, mX, VX = _standardised_posterior(model, Xn)
+    varX = (_kernel_diag(model.spec, Xn) - (VX * VX).sum(-1)) * model.y_std**2
+    covXC = (kernel_matrix(model.spec, Xn, Cn) - VX @ VC.T) * model.y_std**2  # (N, m)
+    R = torch.linalg.solve_triangular(LC, covXC.T, upper=False).T  # (N, m) = covXC L_C^-T
+    cond_sd = (varX - (R * R).sum(-1)).clamp_min(0.0).sqrt()
+    muX = model.y_mean + model.y_std * mX
+    fx = muX.unsqueeze(0) + z[:, :m] @ R.T + z[:, m : m + 1] * cond_sd.unsqueeze(0)  # (S, N)
+    ox = acq.obj_scale * fx + acq.obj_shift
+    top = torch.maximum(ox, pend_max.unsqueeze(-1))
+    return (top - best.unsqueeze(-1)).clamp_min(0.0).mean(0)
+
+
 # --------------------------------------------------------------------------------------
 # A.7 optimize_acqf_discrete
 # --------------------------------------------------------------------------------------

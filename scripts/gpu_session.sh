@@ -29,7 +29,7 @@ for st in $STAGES; do
       BB_FORCE_KERNEL=tc timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_n1_tc.json 2> $OUT/bench_n1_tc.err; echo "bench rc=$?"
       cat $OUT/bench_n1_tc.json | cut -c1-1500 ;;
     ncu)
-      timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1; echo "ncu list rc=$?"
+      BB_OVERLAPPED_HOST_PASS=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1; echo "ncu list rc=$?"
       timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_fused_ts -s 3 -c 1 -f -o $OUT/prof_fused_ts_r02 python scripts/profile_target.py fused > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
       tail -3 $OUT/ncu_full.log ;;
     sanitizer)

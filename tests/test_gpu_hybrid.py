@@ -1,0 +1,91 @@
+"""SURVEY.md 8f-2 (BASELINE config 3): noisy expected improvement on the device and the hybrid (discrete x continuous)
+search that uses it.  The oracle (`oracle.acq_values_qnei`) restates qNoisyExpectedImprovement with the joint Cholesky
+in the order [baseline; pending; new point], the order the device path reproduces; botorch's own ordering pairs the
+base samples with other rows (same distribution, Monte-Carlo-level differences) -- see oracle/reference_path.py."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from baybe_b200 import AcqConfig, DeviceGP
+from baybe_b200.hybrid import HybridSearch, NeiScorer, recommend_hybrid
+from baybe_b200.synthetic import numeric_grid_workload
+from tests.helpers import oracle_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(n=24, d=6, N=700, seed=0):
+    w = numeric_grid_workload(N=N, d=d, n=n, seed=seed)
+    return w, oracle_model(w)
+
+
+@pytest.mark.parametrize("p", [0, 1, 4])
+@pytest.mark.parametrize("minimise", [False, True])
+def test_qnei_matches_oracle(cuda_device, p, minimise):
+    """Full qNEI value of [x; pending] for 700 candidates: device (K* kernel + posterior/cross kernel + one GEMM +
+    bb_nei_reduce) against the float64 joint-Cholesky oracle on the same base samples."""
+    w, om = _problem(seed=3 + p)
+    gp = DeviceGP(device=cuda_device, **w.gp_kwargs())
+    a = -1.0 if minimise else 1.0
+    acq = AcqConfig(kind="qNEI", obj_scale=a, obj_shift=0.25)
+    sc = NeiScorer(gp, acq, n_samples=256, seed=11)
+    pend = w.candidates[-p:] if p else np.empty((0, w.candidates.shape[1]))
+    sc.set_pending(pend)
+    x = torch.from_numpy(w.candidates[:600]).to(cuda_device, torch.float32)
+    got = sc.score(x).double().cpu() + sc.const
+    oacq = oracle.AcqSpec("qEI", obj_scale=a, obj_shift=0.25)
+    ref = oracle.acq_values_qnei(om, oacq, w.candidates[:600], pend, sc.z.cpu())
+    scale = float(ref.abs().max())
+    assert scale > 1e-3, "degenerate test problem"
+    err = float((got - ref).abs().max())
+    # float32 kernel rows / moments and an fp32 GEMM against float64: 2e-4 of the largest value
+    assert err <= 2e-4 * max(scale, 1.0), (err, scale)
+    assert int(got.argmax()) == int(ref.argmax()) or float(ref.max() - ref[int(got.argmax())]) <= 2e-4 * max(scale, 1.0)
+
+
+def test_hybrid_batch_is_as_good_as_an_exhaustive_oracle_search(cuda_device):
+    """8f-2 end to end on a small hybrid space (2 discrete x 2 continuous columns, 12 configurations, q = 3): the
+    batch found by scoring sweeps must reach the joint qNEI value of a greedy search over a dense oracle grid."""
+    rng = np.random.default_rng(5)
+    d_disc, d_cont, n = 2, 2, 20
+    disc_levels = np.array([[a, b] for a in (0.0, 0.5, 1.0) for b in (0.0, 1 / 3, 2 / 3, 1.0)])
+    train_x = np.hstack([disc_levels[rng.integers(0, len(disc_levels), n)], rng.random((n, d_cont))])
+    f = lambda x: np.sin(3 * x[:, 0]) + 0.5 * np.cos(4 * x[:, 2] - 1) * (1 + x[:, 1]) - (x[:, 3] - 0.6) ** 2  # noqa: E731
+    train_y = f(train_x) + 0.05 * rng.standard_normal(n)
+    bounds = np.array([[0.0] * 4, [1.0] * 4])
+    kw = dict(train_x=train_x, train_y=train_y, bounds=bounds, family="matern52", lengthscale=[0.6, 0.8, 0.4, 0.5],
+              noise=2e-2, mean_const=0.1, outputscale=1.3)
+    gp = DeviceGP(device=cuda_device, **kw)
+    spec = oracle.KernelSpec(family="matern52", lengthscale=np.array(kw["lengthscale"]), active_dims=[0, 1, 2, 3], outputscale=1.3)
+    om = oracle.build_model(spec, train_x, train_y, bounds, noise=2e-2, mean_const=0.1)
+    acq = AcqConfig(kind="qNEI")
+    q, S, seed = 3, 256, 2
+    pts, idx, value = recommend_hybrid(gp, acq, disc_levels, np.array([[0.0, 0.0], [1.0, 1.0]]), q, None, S, seed,
+                                       HybridSearch(n_sobol=512, n_seeds=32, n_local=64, n_rounds=5))
+    assert pts.shape == (q, 4) and all(np.allclose(pts[j, :2], disc_levels[idx[j]]) for j in range(q))
+    assert (pts[:, 2:] >= 0).all() and (pts[:, 2:] <= 1).all()
+    # oracle value of the device's batch (same sample convention: point j is the "new point" given points < j)
+    oacq = oracle.AcqSpec("qEI")
+    sc = NeiScorer(gp, acq, S, seed)
+    sc.set_pending(pts[: q - 1])
+    sc._setup()
+    dev_val = float(oracle.acq_values_qnei(om, oacq, pts[q - 1:], pts[: q - 1], sc.z.cpu())[0])
+    assert abs(dev_val - value) <= 2e-4 * max(1.0, abs(dev_val)), (dev_val, value)
+    # exhaustive greedy search of the oracle over a 33 x 33 grid per configuration
+    g = np.linspace(0, 1, 33)
+    grid = np.array([[a, b, u, v] for a, b in disc_levels for u in g for v in g])
+    chosen = np.empty((0, 4))
+    ref_val = 0.0
+    for j in range(q):
+        s2 = NeiScorer(gp, acq, S, seed)
+        s2.set_pending(chosen)
+        s2._setup()
+        vals = oracle.acq_values_qnei(om, oacq, grid, chosen, s2.z.cpu())
+        k = int(vals.argmax())
+        ref_val = float(vals[k])
+        chosen = np.vstack([chosen, grid[k]])
+    # a continuous search must not lose against the grid (it may win: the grid is coarse)
+    assert dev_val >= ref_val - 5e-3 * max(1.0, abs(ref_val)), (dev_val, ref_val)

@@ -315,3 +315,28 @@ def test_standardize_and_noise_conventions():
     var_ref = np.var(y, ddof=1) * float(1.0 - ks @ Kinv @ ks.T)
     mu, var = oracle.posterior(m, xs)
     assert abs(float(mu) - mu_ref) < 1e-10 and abs(float(var) - var_ref) < 1e-10
+
+
+def test_qnei_conditional_form_equals_the_joint_cholesky():
+    """acq_values_qnei (conditional form: samples of [baseline; pending] once, the new point from its Cholesky row)
+    against the definition evaluated candidate by candidate from the full joint posterior of
+    [baseline; pending; x] (oracle.posterior_joint + Cholesky), same base samples."""
+    from oracle import reference_path as rp
+
+    w = numeric_grid_workload(N=60, d=4, n=12, seed=0)
+    om = oracle_model(w)
+    nb = 12
+    for p, a in ((0, 1.0), (2, 1.0), (3, -1.0)):
+        acq = oracle.AcqSpec("qEI", obj_scale=a, obj_shift=0.1)
+        P = w.candidates[:p]
+        z = oracle.sobol_normal_samples(128, nb + p + 1, 3)
+        got = oracle.acq_values_qnei(om, acq, w.candidates[5:17], P, z)
+        ref = []
+        for x in w.candidates[5:17]:
+            A = np.vstack([w.train_x, P, x[None]]) if p else np.vstack([w.train_x, x[None]])
+            mu, cov = rp.posterior_joint(om, A)
+            L = rp._chol_with_jitter(cov.unsqueeze(0))[0]
+            o = a * (mu[None] + z @ L.T) + 0.1
+            ref.append(float((o[:, nb:].amax(-1) - o[:, :nb].amax(-1)).clamp_min(0).mean()))
+        assert np.abs(np.array(ref) - got.numpy()).max() < 1e-7
+        assert float(got.max()) > 0
