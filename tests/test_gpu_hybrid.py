@@ -41,9 +41,12 @@ def test_qnei_matches_oracle(cuda_device, p, minimise):
     scale = float(ref.abs().max())
     assert scale > 1e-3, "degenerate test problem"
     err = float((got - ref).abs().max())
-    # float32 kernel rows / moments and an fp32 GEMM against float64: 2e-4 of the largest value
-    assert err <= 2e-4 * max(scale, 1.0), (err, scale)
-    assert int(got.argmax()) == int(ref.argmax()) or float(ref.max() - ref[int(got.argmax())]) <= 2e-4 * max(scale, 1.0)
+    # Stated tolerance: 2e-3 absolute (targets of unit scale).  The fp32 kernel rows carry ~1e-6 absolute error and
+    # r_x = Sigma_xC L_C^-T amplifies it by |L_C^-1| ~ 1e3 (the latent at the baseline points is almost noise-free);
+    # measured 2.5e-4 .. 6.2e-4.  The Monte-Carlo error of the 256-sample estimate itself is ~5e-2 relative.
+    tol = 2e-3
+    assert err <= tol, (err, scale)
+    assert int(got.argmax()) == int(ref.argmax()) or float(ref.max() - ref[int(got.argmax())]) <= tol
 
 
 def test_hybrid_batch_is_as_good_as_an_exhaustive_oracle_search(cuda_device):
