@@ -22,6 +22,8 @@ __all__ = ["PeerReduce", "get_peer_reduce"]
 class PeerReduce:
     """Slots of this rank + mapped slots of all peers; create it collectively (every rank, same order)."""
 
+    kind = "peer"
+
     def __init__(self, device: torch.device):
         import torch.distributed as dist
 
@@ -52,7 +54,12 @@ class PeerReduce:
             if r == self.rank:
                 base = self.buf.data_ptr()
             else:
-                st = torch.UntypedStorage._new_shared_cuda(*inf)  # cudaIpcOpenMemHandle (lazy peer access)
+                # cudaIpcOpenMemHandle(cudaIpcMemLazyEnablePeerAccess) must run with THIS rank's device current: it
+                # is the opening device that gets peer access to the exporter.  torch opens under a guard for the
+                # device index in the tuple -- the exporter's index as shipped; opened that way the pointer is only
+                # valid for the exporter's device and a kernel on this device faults (first 2-GPU run, round 2).
+                inf = (self.device.index,) + tuple(inf[1:])
+                st = torch.UntypedStorage._new_shared_cuda(*inf)
                 self._peer_storages.append(st)
                 base = st.data_ptr() + off
             group.d_key[r] = base
@@ -83,6 +90,27 @@ class PeerReduce:
             raise RuntimeError("bb_allreduce_best: a peer rank did not arrive within the time-out")
 
 
+class NcclReduce:
+    """Escape hatch (BB_PEER_REDUCE=0): the same reduction as one host-issued ``ncclAllReduce(MAX, int64)`` -- the
+    round-1 path, kept for boxes on which CUDA IPC peer mappings are unavailable.  Not the default."""
+
+    kind = "nccl"
+
+    def __init__(self, device: torch.device):
+        self.device = torch.device(device)
+        self.out = torch.empty(1, dtype=torch.int64, device=self.device)
+
+    def allreduce_best(self, key: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+
+        self.out.copy_(key)
+        dist.all_reduce(self.out, op=dist.ReduceOp.MAX)
+        return self.out
+
+    def check(self) -> None:
+        return None
+
+
 _instances: dict = {}
 
 
@@ -91,5 +119,7 @@ def get_peer_reduce(device) -> PeerReduce:
     dev = torch.device(device)
     key = (dev.type, dev.index)
     if key not in _instances:
-        _instances[key] = PeerReduce(dev)
+        import os
+
+        _instances[key] = NcclReduce(dev) if os.environ.get("BB_PEER_REDUCE", "1") == "0" else PeerReduce(dev)
     return _instances[key]

@@ -379,8 +379,10 @@ def run_b200(args):
             "notes": {
                 "layout": "fp32 row-major, resident in HBM",
                 "l2": "flushed between timed steps (256 MiB write, untimed)",
-                "reduction": "bb_allreduce_best: one warp per rank, atomicMax.sys into every peer's slot over NVLink "
-                             "(CUDA IPC mapped), no host-issued collective" if world > 1 else "single GPU",
+                "reduction": ("single GPU" if world == 1 else
+                              "bb_allreduce_best: one warp per rank, atomicMax.sys into every peer's slot over NVLink "
+                              "(CUDA IPC mapped), no host-issued collective" if peer.kind == "peer" else
+                              "BB_PEER_REDUCE=0: host-issued ncclAllReduce(MAX, int64) per step"),
                 "precision": "distance GEMM (fp16 hi/mid/lo split, 2^-33) and K* L^-T (fp16 hi/lo split, A operand "
                              "in tensor memory) on tcgen05, fp32 TMEM accumulate; packed-fp32 Matern epilogue and MC",
                 "best": {"value": best_val, "index": best_idx},

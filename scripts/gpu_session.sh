@@ -62,13 +62,13 @@ for st in $STAGES; do
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > $OUT/bench_n2.json 2> $OUT/bench_n2.err; echo "bench2 rc=$?"
       cat $OUT/bench_n2.json | cut -c1-3000; tail -15 $OUT/bench_n2.err ;;
     benchN)   # NG GPUs (gpurun --gpus NG): headline weak + strong scaling line
-      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus ${NG:-2} --steps 20 --warmup 3 > $OUT/bench_n${NG:-2}.json 2> $OUT/bench_n${NG:-2}.err; echo "benchN rc=$?"
+      timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus ${NG:-2} --steps 20 --warmup 3 > $OUT/bench_n${NG:-2}.json 2> $OUT/bench_n${NG:-2}.err; echo "benchN rc=$?"
       cat $OUT/bench_n${NG:-2}.json | cut -c1-2500; tail -8 $OUT/bench_n${NG:-2}.err ;;
     cfg45N)   # BASELINE configs 4 (10M fingerprints sharded) and 5 (4 x 250k, top-k merge) on NG GPUs
-      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29523 bench.py --config 5 --gpus ${NG:-2} --steps 10 --warmup 3 > $OUT/bench_cfg5_n${NG:-2}.json 2> $OUT/bench_cfg5_n${NG:-2}.err; echo "cfg5 rc=$?"; cat $OUT/bench_cfg5_n${NG:-2}.json | cut -c1-1500; tail -3 $OUT/bench_cfg5_n${NG:-2}.err
-      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29525 bench.py --config 4 --gpus ${NG:-2} --steps 5 --warmup 3 > $OUT/bench_cfg4_n${NG:-2}.json 2> $OUT/bench_cfg4_n${NG:-2}.err; echo "cfg4 rc=$?"; cat $OUT/bench_cfg4_n${NG:-2}.json | cut -c1-1500; tail -3 $OUT/bench_cfg4_n${NG:-2}.err ;;
+      timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29523 bench.py --config 5 --gpus ${NG:-2} --steps 10 --warmup 3 > $OUT/bench_cfg5_n${NG:-2}.json 2> $OUT/bench_cfg5_n${NG:-2}.err; echo "cfg5 rc=$?"; cat $OUT/bench_cfg5_n${NG:-2}.json | cut -c1-1500; tail -3 $OUT/bench_cfg5_n${NG:-2}.err
+      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29525 bench.py --config 4 --gpus ${NG:-2} --steps 5 --warmup 3 > $OUT/bench_cfg4_n${NG:-2}.json 2> $OUT/bench_cfg4_n${NG:-2}.err; echo "cfg4 rc=$?"; cat $OUT/bench_cfg4_n${NG:-2}.json | cut -c1-1500; tail -3 $OUT/bench_cfg4_n${NG:-2}.err ;;
     testsN)
-      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29527 scripts/multi_gpu_check.py > $OUT/multi_gpu_check_n${NG:-2}.txt 2>&1; echo "testsN rc=$?"
+      timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29527 scripts/multi_gpu_check.py > $OUT/multi_gpu_check_n${NG:-2}.txt 2>&1; echo "testsN rc=$?"
       tail -12 $OUT/multi_gpu_check_n${NG:-2}.txt ;;
     tests2)
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 scripts/multi_gpu_check.py > $OUT/multi_gpu_check.txt 2>&1; echo "tests2 rc=$?"
