@@ -107,6 +107,11 @@ typedef struct bb_model_desc {
  * Device-resident model caches (what GPyTorch's prediction strategy caches: alpha, the
  * inverse root R = L^-T, plus our fp16 hi/lo tensor-core image of it).  Filled by
  * bb_model_build; the pointers point INTO the caller-owned blob.
+ *
+ * Concurrency: the caches are read-only after the build, but the blob also holds per-call SCRATCH -- the K* block
+ * and pending-point images of the wide-feature path, the per-call qLogEI table (d_mc_table), the |V|^2 partial of
+ * two-panel models.  Calls that use one bb_model must therefore be ordered on ONE stream (or externally
+ * serialised); two streams need two models (two blobs built from the same bb_model_desc).
  */
 typedef struct bb_model {
   int32_t abi_version;

@@ -303,3 +303,45 @@ def test_model_registry_holds_models_weakly():
     del obj
     gc.collect()
     assert engine._registry.get(-1) is None
+
+
+def test_hybrid_search_by_scoring_finds_the_optimum_of_a_known_function():
+    """baybe_b200.hybrid.HybridSearch with a stand-in scorer on the CPU: the sweep over
+    (discrete configurations) x (shared Sobol points) plus the shrinking-box refinement must land on the maximiser of
+    a smooth function whose optimum lies in the interior of one configuration's box."""
+    import torch
+
+    from baybe_b200.hybrid import HybridSearch
+
+    disc = torch.tensor([[0.0, 0.0], [0.0, 1.0], [1.0, 0.0], [1.0, 1.0], [0.5, 0.5]], dtype=torch.float32)
+    opt_c = torch.tensor([0.3141, 0.7182, 0.55])
+
+    class Scorer:
+        calls = 0
+
+        def score(self, rows):
+            Scorer.calls += 1
+            dpart = -((rows[:, 0] - 1.0) ** 2 + (rows[:, 1] - 0.0) ** 2)  # configuration (1, 0) is best
+            cpart = -((rows[:, 2:] - opt_c) ** 2).sum(-1) * (1.0 + rows[:, 0])
+            return dpart + cpart
+
+    lo, hi = torch.zeros(3), torch.ones(3)
+    row, val = HybridSearch(n_sobol=256, n_seeds=16, n_local=64, n_rounds=8).best_point(Scorer(), disc, lo, hi, seed=3)
+    assert torch.equal(row[:2], torch.tensor([1.0, 0.0]))
+    assert float((row[2:] - opt_c).abs().max()) < 5e-3 and val > -1e-4
+    assert Scorer.calls == 1 + 8  # one global sweep + one sweep per refinement round
+    # deterministic for a seed
+    row2, val2 = HybridSearch(n_sobol=256, n_seeds=16, n_local=64, n_rounds=8).best_point(Scorer(), disc, lo, hi, seed=3)
+    assert torch.equal(row, row2) and val == val2
+
+
+def test_qnei_spec_is_mirrored_and_kept_off_the_fused_kernels():
+    from baybe_b200 import AcqConfig
+    from baybe_b200.acquisition import convert_acqf, qNoisyExpectedImprovement
+
+    spec = convert_acqf("qNEI")
+    assert isinstance(spec, qNoisyExpectedImprovement) and spec.supports_batching and spec.prune_baseline
+    cfg = AcqConfig(kind="qNEI", obj_scale=-1.0)
+    assert cfg.is_mc
+    with pytest.raises(NotImplementedError):
+        cfg.to_c()
