@@ -75,6 +75,28 @@ def test_status_codes_and_blob_size_queries_without_gpu(lib):
         _lib.check(rc, "bb_acq_score")
 
 
+def test_round2_entry_points_validate_their_arguments_before_any_cuda_call(lib):
+    import ctypes as C
+
+    from baybe_b200 import _lib
+
+    # bb_nei_reduce: the caller's GEMM buffer must hold S sample columns + m root columns per row
+    rc = lib.bb_nei_reduce(None, 10, 8, 4, None, None, None, None, C.c_float(1.0), C.c_float(0.0), 5, None, None)
+    assert rc == _lib.BB_ERR_INVALID and b"bad shape" in lib.bb_last_error()
+    assert lib.bb_nei_reduce(None, 12, 8, 4, None, None, None, None, C.c_float(1.0), C.c_float(0.0), 0, None, None) == 0
+    rc = lib.bb_nei_reduce(None, 12, 8, 4, None, None, None, None, C.c_float(1.0), C.c_float(0.0), 5, None, None)
+    assert rc == _lib.BB_ERR_INVALID and b"null" in lib.bb_last_error()
+    # bb_score_fused_overlapped: model / acquisition spec are checked first
+    rc = lib.bb_score_fused_overlapped(None, None, None, 0, 10, 20, None, 0, None, 0, None, None, None, None, 0, None,
+                                       None, 0, None, None)
+    assert rc == _lib.BB_ERR_INVALID and b"missing" in lib.bb_last_error()
+    # bb_allreduce_best: group sanity
+    g = _lib.PeerGroup()
+    g.rank, g.world = 3, 2
+    rc = lib.bb_allreduce_best(C.byref(g), C.c_void_p(8), 0, C.c_void_p(8), C.c_void_p(8), None)
+    assert rc == _lib.BB_ERR_INVALID and b"rank 3" in lib.bb_last_error()
+
+
 def test_product_has_no_cpu_fallback():
     import torch
 

@@ -183,3 +183,35 @@ def test_sharded_greedy_selection_matches_single_process_oracle():
         assert p.exitcode == 0
     chosen, ref = out.get()
     assert chosen == ref
+
+
+def _escape_hatch_worker(rank: int, world: int, port: int, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from baybe_b200.peers import NcclReduce
+
+    red = NcclReduce(torch.device("cpu"))  # the class only needs a process group; gloo + CPU tensors here
+    got = []
+    for epoch, (a, b) in enumerate([((0.5, 10), (0.5, 3)), ((-1.0, 7), (2.0, 900_000)), (None, (0.25, 5))]):
+        mine = (a, b)[rank]
+        key = -(1 << 63) if mine is None else pack_best(*mine)
+        got.append(unpack_best(int(red.allreduce_best(torch.tensor([key], dtype=torch.int64)).item())))
+    red.check()
+    if rank == 0:
+        out.put(got)
+    dist.destroy_process_group()
+
+
+def test_nccl_escape_hatch_reduces_like_the_peer_kernel():
+    """BB_PEER_REDUCE=0 path (baybe_b200/peers.py::NcclReduce): same contract as bb_allreduce_best -- maximum of
+    the packed keys, ties to the lowest index, empty keys ignored."""
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_escape_hatch_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get() == [(0.5, 3), (2.0, 900_000), (0.25, 5)]
