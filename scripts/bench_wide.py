@@ -52,7 +52,8 @@ def main():
     out.append(dict(case="cfg4_shard_bits", N=N, d=2048, n=512, ms_score=t_s, ms_posterior=t_p,
                     cand_per_s=N / t_s * 1e3, ms_kmat_262k=t_k,
                     kmat_dense_tflops=K.shape[0] * flops / t_k / 1e9,
-                    kmat_mma_tflops=3 * K.shape[0] * flops / t_k / 1e9))
+                    # the bit-linear form issues TWO fp16 split products (W hi, W mid): issued MMA work = 2x dense
+                    kmat_mma_tflops=2 * K.shape[0] * flops / t_k / 1e9))
     del packed, gp
     # ---- float descriptors: 1M x 128, n = 256, Matern-5/2 ----
     N2 = 1_000_000
