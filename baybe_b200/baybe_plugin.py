@@ -115,13 +115,29 @@ class B200BotorchRecommender(BayesianRecommender):
     _context = field(default=None, init=False, eq=False, repr=False)
     _last_acq_values: list = field(factory=list, init=False, eq=False, repr=False)
 
+    # ---- multi-target objectives (surrogates/composite.py:59-181) ------------------------------
+    def get_surrogate(self, searchspace, objective, measurements):
+        """The reference replicates single-output ``Surrogate`` subclasses per modelled quantity
+        (``bayesian/base.py:35-39``); the engine surrogate is a duck-typed ``SurrogateProtocol``, so the same
+        replication is done here -- with BayBE's OWN ``CompositeSurrogate``, which only needs ``fit`` and
+        ``posterior_stats`` of its members.  ``Campaign.posterior_stats`` / ``get_surrogate`` then work for Pareto and
+        desirability objectives; recommending still needs a multi-output acquisition function (not implemented:
+        ``_setup_botorch_acqf`` raises ``IncompatibleAcquisitionFunctionError``)."""
+        if objective.is_multi_output and isinstance(self._surrogate_model, GaussianProcessSurrogate):
+            from baybe.surrogates.composite import CompositeSurrogate
+
+            self._surrogate_model = CompositeSurrogate.from_replication(self._surrogate_model)
+        return super().get_surrogate(searchspace, objective, measurements)
+
     # ---- acquisition set-up: the engine config takes the place of the botorch acquisition function ----------
     def _setup_botorch_acqf(self, searchspace, objective, measurements, pending_experiments=None) -> None:
         self._objective = objective
         acqf = self._get_acquisition_function(objective)
         if objective.is_multi_output:
             raise IncompatibleAcquisitionFunctionError(
-                "multi-output objectives are outside the B200 engine's scope (single-target GP path)")
+                "recommending for multi-output objectives needs a multi-output acquisition function (qLogNEHVI, "
+                "bayesian/base.py:73), which the B200 engine does not implement; the per-target surrogates are "
+                "available through Campaign.get_surrogate / posterior_stats")
         surrogate = self.get_surrogate(searchspace, objective, measurements)
         cfg = mirror_acquisition_function(acqf).to_engine(surrogate, searchspace, objective, measurements,
                                                           pending_experiments)

@@ -220,3 +220,41 @@ def test_subset_generating_constraint_is_honoured(bb):
     camp.add_measurements(meas)
     batch = camp.recommend(batch_size=3)
     assert len(batch) == 3 and batch["cat"].nunique() == 1
+
+
+def test_multi_target_objectives_get_per_target_engine_surrogates(bb):
+    """BayBE's own ``CompositeSurrogate`` (surrogates/composite.py:59-181) replicates the engine
+    surrogate per modelled quantity; ``Campaign.posterior_stats`` then reports every target, each column identical
+    to a single-target campaign on that target; recommending raises the reference's error type (no multi-output
+    acquisition function on the engine)."""
+    from baybe import Campaign
+    from baybe.exceptions import IncompatibleAcquisitionFunctionError
+    from baybe.objectives import ParetoObjective, SingleTargetObjective
+    from baybe.surrogates.composite import CompositeSurrogate
+    from baybe.targets import NumericalTarget
+
+    from baybe_b200.surrogates import GaussianProcessSurrogate
+
+    rng = np.random.default_rng(4)
+    camp1, space = _campaign(bb)
+    d = len(space.comp_rep_columns)
+    hyper = {"lengthscale": np.full(d, 0.9), "noise": 5e-3, "mean_const": 0.0}
+    meas = _fake_measure(space.discrete.exp_rep.sample(14, random_state=2), rng)
+    meas["cost"] = 3.0 + 0.02 * meas["temperature"] + 2.0 * meas["concentration"] ** 2 + rng.normal(0, 0.05, len(meas))
+    obj = ParetoObjective([NumericalTarget("yield"), NumericalTarget("cost", minimize=True)])
+    rec = bb.B200BotorchRecommender(surrogate_model=GaussianProcessSurrogate(hyperparameters=hyper))
+    camp = Campaign(space, obj, rec)
+    camp.add_measurements(meas)
+    cands = space.discrete.exp_rep.head(40)
+    stats = camp.posterior_stats(cands)
+    assert list(stats.columns) == ["yield_mean", "yield_std", "cost_mean", "cost_std"]
+    assert isinstance(camp.get_surrogate(), CompositeSurrogate)
+    for tgt in ("yield", "cost"):
+        single = Campaign(space, SingleTargetObjective(NumericalTarget(tgt, minimize=(tgt == "cost"))),
+                          bb.B200BotorchRecommender(surrogate_model=GaussianProcessSurrogate(hyperparameters=hyper)))
+        single.add_measurements(meas.drop(columns=[c for c in ("yield", "cost") if c != tgt]))
+        ref = single.posterior_stats(cands)
+        assert np.allclose(stats[f"{tgt}_mean"], ref[f"{tgt}_mean"], rtol=1e-6, atol=1e-6)
+        assert np.allclose(stats[f"{tgt}_std"], ref[f"{tgt}_std"], rtol=1e-6, atol=1e-6)
+    with pytest.raises(IncompatibleAcquisitionFunctionError):
+        camp.recommend(batch_size=1)
