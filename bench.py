@@ -536,6 +536,58 @@ def _emit(line: dict) -> None:
 _REAL_STDOUT = 1
 
 
+def run_hybrid(args):
+    """BASELINE config 3 (extra line, single GPU): hybrid space of 8 discrete x 4 continuous parameters, qNEI with 512
+    MC samples, one batch recommendation q = 16 per step through baybe_b200.hybrid.recommend_hybrid (search by
+    scoring).  The unit stays candidates/s: rows swept by the qNEI scorer per second."""
+    import numpy as np
+    import torch
+
+    from baybe_b200 import AcqConfig, DeviceGP
+    from baybe_b200 import hybrid as hy
+
+    world, rank, local_rank, dev = _setup_dist()
+    if world > 1:
+        raise SystemExit("bench.py --config 3 is a single-GPU line")
+    rng = np.random.default_rng(0)
+    levels = [3, 3, 3, 3, 2, 2, 2, 2]  # 8 discrete parameters: 1296 configurations
+    grids = np.meshgrid(*[np.linspace(0.0, 1.0, k) for k in levels], indexing="ij")
+    disc = np.stack([g.reshape(-1) for g in grids], axis=1)
+    d_disc, d_cont, n = disc.shape[1], 4, 64
+    train_x = np.hstack([disc[rng.integers(0, len(disc), n)], rng.random((n, d_cont))])
+    f = train_x @ rng.normal(0, 1, d_disc + d_cont) + np.sin(3 * train_x[:, -1]) * (1 + train_x[:, 0])
+    train_y = f + 0.05 * rng.standard_normal(n)
+    bounds = np.array([[0.0] * (d_disc + d_cont), [1.0] * (d_disc + d_cont)])
+    gp = DeviceGP(train_x, train_y, bounds, "matern52", np.full(d_disc + d_cont, 0.8), 1e-2, 0.0, device=dev)
+    acq = AcqConfig(kind="qNEI")
+    search = hy.HybridSearch(n_sobol=1024, n_seeds=64, n_local=128, n_rounds=6)
+    rows_per_step = 16 * (len(disc) * min(search.n_sobol, search.max_rows // len(disc))
+                          + search.n_rounds * search.n_seeds * search.n_local)
+    cb = np.array([[0.0] * d_cont, [1.0] * d_cont])
+    steps, warmup = max(1, min(args.steps, 5)), 1
+
+    def step():
+        return hy.recommend_hybrid(gp, acq, disc, cb, 16, None, S, 3, search)
+
+    timed = _Timer(dev, world)
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(step, steps, warmup) / steps
+    pts, idx, value = step()
+    _emit({
+        "metric": "candidates/sec scored (qNEI S=512, hybrid 8 discrete x 4 continuous, q=16 batch)",
+        "value": rows_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE config 3: 1296 discrete configurations x 4 continuous parameters, n=64, "
+                               "qNEI (512 MC samples, baseline = training inputs), q=16 sequential greedy, "
+                               "search by scoring (1024 Sobol points per configuration + 6 refinement sweeps)",
+                   "rows_scored_per_recommendation": rows_per_step},
+        "e2e": None, "gpu_launches": None, "clocks": clocks.summary(), "roofline": None, "cpu_baseline": None,
+        "notes": {"joint_qnei_of_batch": value, "first_point": pts[0].tolist(),
+                  "pipeline": "bb_kernel_matrix + bb_posterior(+cross) + cuBLAS GEMM (library) + bb_nei_reduce"},
+    })
+
+
 def main():
     global _REAL_STDOUT
     # NCCL / torch may print banners to stdout; keep stdout clean for the single JSON line
@@ -547,13 +599,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--config", type=int, choices=[2, 4, 5], default=2)
+    ap.add_argument("--config", type=int, choices=[2, 3, 4, 5], default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.config == 2:
         run_b200(args)
+    elif args.config == 3:
+        run_hybrid(args)
     else:
         run_other(args)
 
