@@ -10,8 +10,8 @@ for st in $STAGES; do
   echo "=== stage $st $(date +%T) ==="
   case $st in
     ubench)
-      timeout 100 scripts/ubench/mma_rate 1 > $OUT/mma_rate_cg1.txt 2>&1; echo "rc=$?" >> $OUT/mma_rate_cg1.txt
-      timeout 100 scripts/ubench/mma_rate 2 > $OUT/mma_rate_cg2.txt 2>&1; echo "rc=$?" >> $OUT/mma_rate_cg2.txt
+      # build here: (cd scripts/ubench && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../../baybe_b200/csrc -I../../include mma_rate.cu -o mma_rate)
+      timeout 100 scripts/ubench/mma_rate > $OUT/mma_rate_cg1.txt 2>&1; echo "rc=$?" >> $OUT/mma_rate_cg1.txt
       grep -E "elect=1|rc=" $OUT/mma_rate_cg1.txt | grep -E "bg=0|rc=" ;;
     light)
       timeout 200 python scripts/ts_first_light.py > $OUT/ts_first_light.txt 2>&1; echo "light rc=$?"
