@@ -214,6 +214,14 @@ class _JointPosterior:
             covariance_matrix=self.covariance.double().cpu() + 1e-9 * torch.eye(self.covariance.shape[0], dtype=torch.float64))
 
 
+def default_preset_name(searchspace) -> str:
+    """The reference's default dispatches on search-space content (``presets/baybe.py:151-197``, ``_dispatch``): a
+    ``SubstanceParameter`` anywhere in the space switches kernel, mean and likelihood to the Chen preset
+    (``presets/chen.py:35-61``); every other space gets the custom-scaled BayBE preset."""
+    has_substance = any(type(p_).__name__ == "SubstanceParameter" for p_ in getattr(searchspace, "parameters", ()))
+    return "CHEN" if has_substance else "BAYBE"
+
+
 @define
 class GaussianProcessSurrogate:
     """GP surrogate whose posterior runs on the B200 engine."""
@@ -274,11 +282,7 @@ class GaussianProcessSurrogate:
 
             kf = self.kernel_or_factory
             if kf is None:
-                # presets/baybe.py:151-197 (_dispatch): a SubstanceParameter anywhere in the search space switches
-                # kernel, mean and likelihood to the Chen preset; otherwise the custom-scaled BayBE preset
-                has_substance = any(type(p_).__name__ == "SubstanceParameter"
-                                    for p_ in getattr(searchspace, "parameters", ()))
-                config = gp_preset("CHEN" if has_substance else "BAYBE", len(active))
+                config = gp_preset(default_preset_name(searchspace), len(active))
             elif isinstance(kf, str):
                 config = gp_preset(kf, len(active))
             elif isinstance(kf, Kernel):

@@ -345,3 +345,25 @@ def test_qnei_spec_is_mirrored_and_kept_off_the_fused_kernels():
     assert cfg.is_mc
     with pytest.raises(NotImplementedError):
         cfg.to_c()
+
+
+def test_default_preset_dispatches_on_search_space_content():
+    """presets/baybe.py:151-197: Substance parameters -> Chen preset, everything else -> BayBE preset; task spaces
+    select the leave-one-out criterion (presets/baybe.py:270-281)."""
+    from types import SimpleNamespace
+
+    from baybe_b200.kernels import gp_preset
+    from baybe_b200.surrogates import default_preset_name
+
+    class SubstanceParameter:  # the dispatch keys on the reference's class name
+        pass
+
+    class NumericalDiscreteParameter:
+        pass
+
+    plain = SimpleNamespace(parameters=(NumericalDiscreteParameter(), NumericalDiscreteParameter()))
+    chem = SimpleNamespace(parameters=(NumericalDiscreteParameter(), SubstanceParameter()))
+    assert default_preset_name(plain) == "BAYBE" and default_preset_name(chem) == "CHEN"
+    assert default_preset_name(SimpleNamespace()) == "BAYBE"
+    chen, baybe = gp_preset("CHEN", 12), gp_preset("BAYBE", 12)
+    assert chen != baybe  # different kernel / prior / likelihood numbers
