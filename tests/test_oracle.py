@@ -340,3 +340,35 @@ def test_qnei_conditional_form_equals_the_joint_cholesky():
             ref.append(float((o[:, nb:].amax(-1) - o[:, :nb].amax(-1)).clamp_min(0).mean()))
         assert np.abs(np.array(ref) - got.numpy()).max() < 1e-7
         assert float(got.max()) > 0
+
+
+def test_leave_one_out_closed_form_equals_brute_force_refits():
+    """The fit criterion of transfer-learning spaces (presets/baybe.py:270-281): the closed form used by the device
+    kernel and its host twin -- sigma_i^2 = 1/[K^-1]_ii, mu_i = y_i - alpha_i sigma_i^2  [U: gpytorch
+    LeaveOneOutPseudoLikelihood] -- against n explicit refits that leave one observation out and evaluate its
+    Gaussian predictive log density (noisy observation)."""
+    from tests.helpers import HostMLL
+
+    rng = np.random.default_rng(7)
+    n, d = 9, 3
+    X = rng.random((n, d))
+    y = np.sin(3 * X[:, 0]) + X[:, 1] ** 2 + 0.1 * rng.standard_normal(n)
+    ls, noise, c = np.array([0.7, 0.9, 1.1]), 0.05, 0.2
+    theta = np.concatenate([ls, [noise, c], [1.0]])
+    got, _, ok = HostMLL(X, y, None, 1, "matern52", criterion="loo")(theta)
+    assert ok
+
+    def kern(A, B):
+        r = np.sqrt((((A[:, None, :] - B[None, :, :]) / ls) ** 2).sum(-1))
+        return (1 + np.sqrt(5) * r + 5 / 3 * r * r) * np.exp(-np.sqrt(5) * r)
+
+    ref = 0.0
+    for i in range(n):
+        m = np.arange(n) != i
+        Kmm = kern(X[m], X[m]) + noise * np.eye(n - 1)
+        kim = kern(X[i : i + 1], X[m])[0]
+        sol = np.linalg.solve(Kmm, np.stack([y[m] - c, kim], axis=1))
+        mu = c + kim @ sol[:, 0]
+        var = 1.0 + noise - kim @ sol[:, 1]
+        ref += -0.5 * np.log(2 * np.pi * var) - 0.5 * (y[i] - mu) ** 2 / var
+    assert abs(got - ref) < 1e-9 * max(1.0, abs(ref))
