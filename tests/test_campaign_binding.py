@@ -258,3 +258,58 @@ def test_multi_target_objectives_get_per_target_engine_surrogates(bb):
         assert np.allclose(stats[f"{tgt}_std"], ref[f"{tgt}_std"], rtol=1e-6, atol=1e-6)
     with pytest.raises(IncompatibleAcquisitionFunctionError):
         camp.recommend(batch_size=1)
+
+
+def test_hybrid_space_reaches_the_device_search_through_the_reference_hook(bb, monkeypatch):
+    """SURVEY.md 8f-2 glue: a hybrid SearchSpace + qNoisyExpectedImprovement under the unmodified ``Campaign`` ends in
+    ``B200BotorchRecommender._recommend_hybrid(searchspace, candidates_exp, batch_size)`` (pure/base.py:300-302), which
+    hands the discrete comp-rep rows, the continuous bounds and the engine config to ``baybe_b200.hybrid`` and
+    assembles the reference's frame layout (hybrid.py:137-161).  The device search itself is replaced by a recorder
+    here (it needs the GPU: tests/test_gpu_zz_hybrid.py)."""
+    from baybe import Campaign
+    from baybe.acquisition import qNoisyExpectedImprovement
+    from baybe.objectives import SingleTargetObjective
+    from baybe.parameters import CategoricalParameter, NumericalContinuousParameter, NumericalDiscreteParameter
+    from baybe.searchspace import SearchSpace
+    from baybe.targets import NumericalTarget
+
+    import baybe_b200.hybrid as hy
+    from baybe_b200.surrogates import GaussianProcessSurrogate
+
+    params = [
+        NumericalDiscreteParameter("temperature", values=[60, 80, 100]),
+        CategoricalParameter("solvent", values=["A", "B"], encoding="OHE"),
+        NumericalContinuousParameter("pressure", bounds=(1.0, 5.0)),
+        NumericalContinuousParameter("ratio", bounds=(0.0, 1.0)),
+    ]
+    space = SearchSpace.from_product(params)
+    assert space.type.name == "HYBRID"
+    d = len(space.comp_rep_columns)
+    hyper = {"lengthscale": np.full(d, 0.9), "noise": 5e-3, "mean_const": 0.0}
+    rec = bb.B200BotorchRecommender(surrogate_model=GaussianProcessSurrogate(hyperparameters=hyper),
+                                    acquisition_function=qNoisyExpectedImprovement())
+    camp = Campaign(space, SingleTargetObjective(NumericalTarget("yield")), rec)
+    rng = np.random.default_rng(1)
+    meas = space.discrete.exp_rep.sample(8, random_state=3, replace=True).reset_index(drop=True)
+    meas["pressure"] = rng.uniform(1, 5, len(meas))
+    meas["ratio"] = rng.uniform(0, 1, len(meas))
+    meas["yield"] = 0.3 * meas["temperature"] + 2 * meas["pressure"] - 5 * (meas["ratio"] - 0.4) ** 2 + rng.normal(0, 0.1, len(meas))
+    camp.add_measurements(meas)
+    seen = {}
+
+    def fake(gp, acq, disc_comp, cont_bounds, batch_size, pending, n_samples, seed, search=None):
+        seen.update(acq=acq, disc=np.array(disc_comp), cb=np.array(cont_bounds), q=batch_size, pending=pending)
+        idx = [1, 1, 4][:batch_size]  # the same configuration twice: duplicate index labels must survive
+        pts = np.hstack([np.array(disc_comp)[idx], np.array([[2.5, 0.25], [3.5, 0.75], [1.0, 1.0]])[:batch_size]])
+        return pts, idx, 0.123
+
+    monkeypatch.setattr(hy, "recommend_hybrid", fake)
+    out = camp.recommend(batch_size=3)
+    assert seen["acq"].kind == "qNEI" and seen["q"] == 3 and seen["pending"] is None
+    assert seen["disc"].shape == (6, len(space.discrete.comp_rep.columns))
+    assert np.allclose(seen["cb"], [[1.0, 0.0], [5.0, 1.0]])
+    assert list(out.columns) == ["temperature", "solvent", "pressure", "ratio"] and len(out) == 3
+    assert np.allclose(out["pressure"], [2.5, 3.5, 1.0]) and np.allclose(out["ratio"], [0.25, 0.75, 1.0])
+    exp = space.discrete.exp_rep
+    assert out.iloc[0]["temperature"] == exp.iloc[1]["temperature"] and out.iloc[0]["solvent"] == exp.iloc[1]["solvent"]
+    assert out.iloc[2]["temperature"] == exp.iloc[4]["temperature"]

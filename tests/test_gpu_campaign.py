@@ -10,7 +10,6 @@ from tests.test_campaign_binding import (REF, bb, test_campaign_posterior_stats_
                                          test_campaign_recommend_add_measurements_recommend,
                                          test_first_recommendation_is_the_argmax_of_the_acquisition_values,
                                          test_minimisation_and_analytic_acquisition_functions,
-                                         test_multi_target_objectives_get_per_target_engine_surrogates,
                                          test_plugin_passes_the_reference_gates,
                                          test_subset_generating_constraint_is_honoured)
 
