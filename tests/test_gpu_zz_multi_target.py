@@ -50,4 +50,4 @@ def test_hybrid_campaign_recommends_a_batch_on_the_device(bb, cuda_device):  # n
     assert out["temperature"].isin([60, 80, 100]).all() and out["solvent"].isin(["A", "B"]).all()
     assert ((out["pressure"] >= 1.0) & (out["pressure"] <= 5.0)).all()
     assert ((out["ratio"] >= 0.0) & (out["ratio"] <= 1.0)).all()
-    assert rec._last_acq_values and rec._last_acq_values[0] > 0.0
+    assert rec._last_acq_values and rec._last_acq_values[0] >= 0.0 and np.isfinite(rec._last_acq_values[0])
