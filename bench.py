@@ -327,6 +327,8 @@ def run_b200(args):
         _, key = gp.score(acq, x_host, z, index_offset=offset, want_scores=False)
         return finish(key)
 
+    if world > 1:
+        dist.barrier()  # the ranks finish their set-up seconds apart; the peer reduction waits ~11 s at most
     with ClockSampler(local_rank) as clocks:
         total_ms = timed(step_device, steps, warmup)
     best_val, best_idx = unpack_best(int(key_host.item()))
@@ -496,6 +498,8 @@ def run_other(args):
         key_host.copy_(key, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    if world > 1:
+        dist.barrier()  # data generation differs per rank by seconds; the peer reduction waits ~11 s at most
     with ClockSampler(local_rank) as clocks:
         total_ms = timed(step, steps, warmup)
     kern_ms = timed(kernel_fn, steps, 2) / steps

@@ -287,7 +287,7 @@ int bb_topk(const float* d_score, const uint8_t* d_keep, int64_t N, int32_t k, f
  * the caller's stream: atomicMax.sys of the local packed key into every rank's slot, a system fence, a bump of
  * every rank's counter, a bounded wait for `world` arrivals at the own counter, copy-out and re-arm.  No host
  * code and no NCCL call sits between the scoring kernel and the reduced key.  `epoch` must be the same on all ranks
- * and increase by one per call; *d_status = 1 if a peer did not arrive within ~2 s (d_out_key then holds the local
+ * and increase by one per call; *d_status = 1 if a peer did not arrive within ~11 s (d_out_key then holds the local
  * key).  Replaces torch.argmax over the full candidate set inside botorch.optim.optimize_acqf_discrete
  * (baybe/recommenders/pure/bayesian/botorch/discrete.py:124-126) for a candidate set sharded over GPUs. */
 #define BB_MAX_PEERS 8
